@@ -1,0 +1,1 @@
+"""oracle/ -- TEST INFRASTRUCTURE ONLY (see oracle/oracle.py)."""
