@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- k-mers counted per second (whole job) at k=21 on synthetic 1 kb reads.
+
+    python bench.py --gpus 1 --steps K --warmup W            # this repository's CUDA path
+    python bench.py --impl reference --steps K --warmup W     # the reference's C functions on the host cores
+
+One "step" = one full pass of the hot path (generate_kmers over every row + GROUP BY count) over one
+batch.  N=1 workload = BASELINE.json configs[1]: k=21 count over 1 GB of synthetic DNA
+(1 000 000 reads x 1 000 bases, i.i.d. uniform ACGT, seed 2 -- kmer-extension_b200/datagen.py restates
+the reference's data_generator.py distribution).
+
+value : k-mers/s with the input already resident in HBM (CUDA events around K steps, max over ranks)
+e2e   : the same metric through the host-buffer C ABI call kmer_cuda_submit_count (pinned host input,
+        H2D + kernels + D2H of the (k-mer,count) table inside the timed region)
+roofline     : dominant kernel, algorithmic bytes / its own CUDA-event duration vs MEASURED_PEAKS.json
+roofline_step: whole step against SURVEY section 8(d)'s B_alg = N_bases + 16*D
+cpu_baseline : the reference's own C code (oracle/_ref, PG executor emulated) on the host cores,
+               bounded sample, rank 0 only
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "kmers_counted_per_sec_k21"
+UNIT = "k-mers/s"
+READ_LEN = 1000
+K = 21
+
+
+def load_pkg():
+    import __graft_entry__ as g
+    g.load_package()
+    from kmer_extension_b200 import api, datagen
+    return g, api, datagen
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(datagen, n_reads: int, threads: int, steps: int, warmup: int):
+    """The reference's own kmer.c (oracle/_ref) or, failing that, the C port, on the host cores."""
+    from oracle import oracle as O
+    flat, off = datagen.synth_reads(2, n_reads, READ_LEN)
+    if O.REF_SO.exists():
+        R = O.Ref()
+        kind = "reference"
+        run = lambda: R.count(flat, off, K, threads=threads)[2]
+    else:
+        O.build(ref=False)
+        Cc = O.COracle()
+        kind, threads = "port", 1
+        run = lambda: Cc.count(flat, off, K)[2]
+    for _ in range(warmup):
+        run()
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(steps):
+        n += run()
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"{n_reads} reads x {READ_LEN} bases (seed 2 prefix of the workload), k={K}, "
+                      f"generate_kmers + hash aggregate (Partial per thread + serial Finalize), {steps} pass(es)",
+            "seconds": dt, "steps": steps}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    _, api, datagen = load_pkg()
+    threads = host_threads()
+    n_reads = args.ref_reads
+    r = cpu_reference_run(datagen, n_reads, threads, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"k=21 count, bounded sample of configs[1]: {n_reads} reads x 1000 bases per step",
+                       "k": K, "read_len": READ_LEN},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU (1 kb each); default = 1 GB")
+    ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 dense, 2 hash, 3 minimizer partition")
+    ap.add_argument("--ref-reads", type=int, default=4000, help="sample size of the reference arm per step")
+    ap.add_argument("--cpu-reads", type=int, default=20000, help="sample size of the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        print(f"note: warmup {args.warmup} < 3 is below the timing rule", file=sys.stderr)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    g, api, datagen = load_pkg()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world > 1:
+        raise SystemExit("multi-GPU counting is not wired into bench.py yet")
+
+    eng = api.KmerCuda(local_rank)
+    n_rows = args.reads
+    flat, off = datagen.synth_reads(2 + rank, n_rows, READ_LEN)
+    n_bases = int(off[-1])
+    n_kmers = n_rows * (READ_LEN - K + 1)
+
+    # ---------------------------------------------------------------- resident-data arm
+    h_seq = torch.empty(n_bases + 64, dtype=torch.uint8).pin_memory()
+    h_seq[:n_bases] = torch.from_numpy(flat)
+    h_seq[n_bases:] = 0
+    h_off = torch.from_numpy(off.astype(np.int64)).pin_memory()
+    d_seq = h_seq.cuda(non_blocking=True)
+    d_off = h_off.cuda(non_blocking=True)
+    cap = eng.max_kmers(n_bases, n_rows, K)
+    d_pairs = torch.empty((cap, 2), dtype=torch.int64, device="cuda")
+    stream = torch.cuda.current_stream()
+    torch.cuda.synchronize()
+
+    launches0 = eng.launches
+
+    def step():
+        eng.dev_count(d_seq, n_bases, d_off, n_rows, K, d_pairs, algo=args.algo, stream=stream)
+        return eng.dev_finish(stream)
+
+    for _ in range(args.warmup):
+        res = step()
+    assert res.n_kmers == n_kmers, (res.n_kmers, n_kmers)
+    n_distinct = int(res.n_distinct)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    torch.cuda.synchronize()
+    l0 = eng.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        res = step()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    launches = eng.launches - l0
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    ms_step = ms_total / args.steps
+    value = n_kmers * args.steps / (ms_total * 1e-3)
+
+    # ---------------------------------------------------------------- per-kernel phases (separate pass, not the timed one)
+    eng.set_profiling(True)
+    phase_acc = {}
+    for _ in range(max(2, min(args.steps, 5))):
+        step()
+        for name, ms in eng.phases():
+            phase_acc.setdefault(name, []).append(ms)
+    eng.set_profiling(False)
+    phases = {n: float(np.mean(v)) for n, v in phase_acc.items()}
+    peak, peak_src = measured_peaks()
+    b_alg_step = n_bases + 16 * n_distinct
+    # algorithmic bytes of each kernel (DESIGN.md "Kernels"): what it must read + write once
+    alg_bytes = {
+        "count_hash_insert": n_bases + 16 * n_distinct,          # read every base once, create every group once
+        "hash_compact": 16 * n_distinct * 2,                     # read + write every group once
+        "hash_clear": 0,
+        "count_dense+compact": n_bases + 16 * n_distinct,
+        "minimizer_partition": n_bases,                         # + super-k-mer records, counted in DESIGN.md
+        "bucket_count": 16 * n_distinct,
+    }
+    dom = max(phases, key=phases.get) if phases else None
+    roofline = None
+    if dom:
+        ab = alg_bytes.get(dom, b_alg_step)
+        ach = ab / (phases[dom] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "alg_bytes_per_launch": ab, "kernel_ms": phases[dom],
+                    "share_of_step": phases[dom] / max(sum(phases.values()), 1e-9), "peak_source": peak_src}
+    ach_step = b_alg_step / (ms_step * 1e-3) / 1e9
+    roofline_step = {"bound": "hbm", "achieved": ach_step, "peak": peak, "unit": "GB/s", "frac": ach_step / peak,
+                     "alg_bytes_per_step": b_alg_step, "formula": "N_bases + 16*D (SURVEY 8d)", "frac_of_8000_nominal": ach_step / 8000.0}
+
+    # ---------------------------------------------------------------- e2e arm: host buffers through the C ABI
+    e2e = None
+    if not args.no_e2e:
+        import psutil
+        need = 16 * n_distinct + (1 << 30)
+        if psutil.virtual_memory().available < 2 * need:
+            e2e = {"value": None, "unit": UNIT, "skipped": "host memory too small for a pinned result buffer"}
+        else:
+            pairs, d, nk = C.c_void_p(), C.c_uint64(), C.c_uint64()
+            seq_ptr, off_ptr = h_seq.data_ptr(), h_off.data_ptr()
+
+            def e2e_step():
+                rc = eng.lib.kmer_cuda_submit_count(eng.ctx, seq_ptr, off_ptr, n_rows, K, C.byref(pairs), C.byref(d), C.byref(nk))
+                if rc:
+                    eng._raise(eng.ctx)
+                chk = (C.c_uint64 * 2).from_address(pairs.value)  # touch the result on the host
+                got = (int(chk[0]), int(chk[1]), int(d.value), int(nk.value))
+                eng.lib.kmer_cuda_release(eng.ctx, pairs)
+                return got
+
+            e2e_steps = max(1, min(args.steps, 3))
+            for _ in range(2):
+                e2e_step()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                got = e2e_step()
+            dt = time.perf_counter() - t0
+            assert got[2] == n_distinct and got[3] == n_kmers
+            e2e = {"value": n_kmers * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": n_bases + 8 * (n_rows + 1),
+                   "d2h_bytes_per_step": 16 * n_distinct, "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
+                   "api": "kmer_cuda_submit_count (pinned host input -> pinned host (k-mer,count) table)"}
+
+    # ---------------------------------------------------------------- CPU baseline beside it (rank 0, bounded sample)
+    cpu = None
+    if not args.no_cpu and rank == 0:
+        try:
+            r = cpu_reference_run(datagen, args.cpu_reads, host_threads(), 1, 0)
+            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as ex:  # the baseline must never take the GPU number down with it
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic",
+            "config": {"workload": f"configs[1]: k=21 count over {n_bases / 1e9:.3g} GB synthetic DNA per GPU "
+                                   f"({n_rows} reads x {READ_LEN}, seed 2+rank)", "k": K, "read_len": READ_LEN,
+                       "reads_per_gpu": n_rows, "algo": args.algo, "n_kmers_per_step": n_kmers * world,
+                       "n_distinct_rank0": n_distinct, "l2": "inputs and tables larger than L2 (no flush needed)",
+                       "bases_per_sec": n_bases * world * args.steps / (ms_total * 1e-3)},
+            "roofline": roofline, "roofline_step": roofline_step, "phases_ms": phases, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()

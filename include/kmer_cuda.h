@@ -1,0 +1,189 @@
+/*
+ * kmer_cuda.h -- C ABI of libkmer_cuda.so, the B200 (sm_100a) batch engine for the data-parallel
+ * hot path of the PostgreSQL `kmer` extension (NishantSushmakar/kmer-extension).
+ *
+ * The reference has no batch interface: PostgreSQL calls its C functions once per row / per k-mer
+ * through fmgr-V1 (`Datum f(PG_FUNCTION_ARGS)`, kmer.c:84-365).  This header is what new C glue in
+ * the extension binds instead, one call per column batch.  Each entry point
+ * cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - Plain C linkage, plain pointers and sizes; nothing is thrown or longjmp'ed across the boundary.
+ *     Every call returns a kmer_status; kmer_cuda_last_error() gives SQLSTATE / message / detail /
+ *     offending row exactly as the reference's ereport() would (kmer.c:33-36,117-119,151-153,
+ *     179-181,311-313), so the glue can re-raise it unchanged.
+ *   - Rows are a flat text buffer plus offsets: row r is seq[row_off[r] .. row_off[r+1]) -- the
+ *     payload of a `dna` varlena (kmer.h:9; 1 byte per base, any case).  row_off[0] must be 0.
+ *   - A k-mer is a uint64 code: a=0 c=1 g=2 t=3, first base in the most significant USED bit pair
+ *     (code < 4^k).  For equal k, code order == memcmp order of the lower-case text the reference
+ *     stores (kmer.c:28-29,124-126) and a prefix is the high bits.  k <= 32 = MAX_KMER_LENGTH
+ *     (kmer.h:18).  Columns of mixed-length k-mers carry a parallel uint8 length array.
+ *   - There is no CPU fallback.  Without a usable CUDA device every call fails with
+ *     KMER_ERR_NO_DEVICE / KMER_ERR_CUDA.
+ *   - A context is process-local and NOT thread-safe: one in-flight batch per context.  It creates
+ *     its CUDA context lazily inside kmer_cuda_init, so a PostgreSQL backend must call it after
+ *     fork(), never in the postmaster.
+ */
+#ifndef KMER_CUDA_H
+#define KMER_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KMER_CUDA_MAX_K 32 /* MAX_KMER_LENGTH, kmer.h:18 */
+#define KMER_CUDA_ABI_VERSION 1
+
+typedef enum kmer_status
+{
+	KMER_OK = 0,
+	/* errors the reference raises (same SQLSTATE / text) */
+	KMER_ERR_INVALID_DNA = 1,	 /* 22P02 "Invalid DNA Sequence" + detail     validate_sequence kmer.c:31-37 */
+	KMER_ERR_KMER_TOO_LONG = 2,	 /* 22001 "KMer Sequence larger than length 32"          kmer_in kmer.c:115-120 */
+	KMER_ERR_INVALID_QKMER = 3,	 /* 22P02 "Invalid QKMer Sequence"                      qkmer_in kmer.c:177-182 */
+	KMER_ERR_INVALID_K = 4,		 /* 22023 "Invalid KMER Length"                   generate_kmers kmer.c:310-313 */
+	KMER_ERR_QKMER_TOO_LONG = 5, /* 22001 "QKMer Sequence larger than length 32"        qkmer_in kmer.c:149-154 */
+	/* errors of the engine itself (SQLSTATE XX000 / 53200 in the glue) */
+	KMER_ERR_BAD_ARGUMENT = 16,
+	KMER_ERR_CUDA = 17,
+	KMER_ERR_OOM = 18,
+	KMER_ERR_NO_DEVICE = 19,
+	KMER_ERR_CAPACITY = 20 /* caller-provided output buffer too small */
+} kmer_status;
+
+typedef struct kmer_cuda_error
+{
+	int status;			 /* kmer_status */
+	char sqlstate[6];	 /* "22P02", "22001", "22023", "XX000", "53200" */
+	char message[160];	 /* errmsg, verbatim for the reference's errors */
+	char detail[160];	 /* errdetail or "" */
+	int64_t row;		 /* first offending row of the batch, or -1 */
+} kmer_cuda_error;
+
+/* One group of `SELECT kmer, count(*) ... GROUP BY kmer`: the k-mer and its bigint count. */
+typedef struct kmer_count_pair
+{
+	uint64_t code;
+	uint64_t count;
+} kmer_count_pair;
+
+typedef struct kmer_cuda_ctx kmer_cuda_ctx;
+
+/* predicate selectors for kmer_cuda_*_match (the column is always the `kmer` operand) */
+typedef enum kmer_match_op
+{
+	KMER_OP_EQUALS = 0,		 /* kmer = const          equals(kmer,kmer)        kmer_equals kmer.c:226-245 */
+	KMER_OP_STARTS_WITH = 1, /* kmer ^@ const  ==  starts_with(const, kmer)    kmer_starts_with[_op] kmer.c:248-265 */
+	KMER_OP_CONTAINS = 2	 /* const::qkmer @> kmer == kmer <@ const          kmer_contains/_containing kmer.c:268-285 */
+} kmer_match_op;
+
+/* ---------------------------------------------------------------- lifecycle */
+
+int kmer_cuda_abi_version(void);
+/* number of CUDA devices visible, 0 if none / no driver */
+int kmer_cuda_device_count(void);
+/* Creates a context on `device` (creates the CUDA primary context lazily, here). */
+int kmer_cuda_init(kmer_cuda_ctx **ctx, int device);
+void kmer_cuda_shutdown(kmer_cuda_ctx *ctx);
+/* Error record of the last failing call on ctx (ctx may be NULL: error of the last failed init). */
+const kmer_cuda_error *kmer_cuda_last_error(const kmer_cuda_ctx *ctx);
+/* Frees a result buffer returned by a kmer_cuda_submit_* call (pinned host memory). */
+void kmer_cuda_release(kmer_cuda_ctx *ctx, void *result);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t kmer_cuda_launch_count(const kmer_cuda_ctx *ctx);
+
+/* Phase timing for benchmarks: when on, CUDA events bracket every kernel phase of a dev_* call;
+ * after kmer_cuda_dev_finish(), kmer_cuda_get_phases() returns the phase names (static strings)
+ * and their device durations in ms.  Returns the number of phases of the last finished call. */
+void kmer_cuda_set_profiling(kmer_cuda_ctx *ctx, int on);
+int kmer_cuda_get_phases(const kmer_cuda_ctx *ctx, const char **names, float *ms, int capacity);
+
+/* ---------------------------------------------------------------- host-buffer batch submit
+ * Inputs are caller-owned host memory (pageable or pinned); results are library-owned pinned host
+ * buffers, valid until kmer_cuda_release().  Calls block until the result is complete. */
+
+/* Replaces one generate_kmers SRF scan per row (kmer.c:289-351) for a whole column:
+ * (*codes)[0..*n_kmers) = every window of every row, rows in order, positions in order.
+ * Any row shorter than k, or k outside 1..32, fails the batch with KMER_ERR_INVALID_K
+ * (kmer.c:310-313); any byte outside ACGTacgt fails it with KMER_ERR_INVALID_DNA (kmer.c:20-41).
+ * The first offending row decides, as in a sequential scan. */
+int kmer_cuda_submit_extract(kmer_cuda_ctx *ctx, const char *seq, const uint64_t *row_off, uint64_t n_rows,
+							 int k, uint64_t **codes, uint64_t *n_kmers);
+
+/* Replaces `SELECT kmer, count(*) FROM (SELECT generate_kmers(dna,k) ...) GROUP BY kmer`
+ * (generate_kmers kmer.c:289-351 + HashAggregate over kmer_hash kmer.c:353-365 / kmer_equals
+ * kmer.c:226-245): (*pairs)[0..*n_distinct) in unspecified order, like a hash aggregate's output.
+ * Same error behaviour as kmer_cuda_submit_extract.  *n_kmers = total windows counted. */
+int kmer_cuda_submit_count(kmer_cuda_ctx *ctx, const char *seq, const uint64_t *row_off, uint64_t n_rows,
+						   int k, kmer_count_pair **pairs, uint64_t *n_distinct, uint64_t *n_kmers);
+
+/* Replaces per-row calls of kmer_equals / kmer_starts_with[_op] / kmer_contains / kmer_containing
+ * (kmer.c:226-285) over a column of m k-mers against n_consts constants given as text:
+ *   KMER_OP_EQUALS, KMER_OP_STARTS_WITH : constants are kmer literals   (kmer_in rules, kmer.c:109-129)
+ *   KMER_OP_CONTAINS                    : constants are qkmer literals  (qkmer_in rules, kmer.c:141-190)
+ * ops == NULL: every constant uses `op`; else ops[c] (a kmer_match_op) selects the predicate of
+ * constant c, so that e.g. an equals and a starts_with filter share one pass over the column.
+ * lens == NULL: every k-mer has length k; else lens[i] (0..32) is the length of codes[i].
+ * Result: bit matrix, row c = constant c, (*bits)[c * words_per_row + (i >> 5)] bit (i & 31) is the
+ * boolean the reference returns for (const c, kmer i); words_per_row = ceil(m / 32), returned in
+ * *words_per_row; (*hits)[c] = number of set bits of row c. */
+int kmer_cuda_submit_match(kmer_cuda_ctx *ctx, int op, const int *ops, const uint64_t *codes, const uint8_t *lens,
+						   uint64_t m, int k, const char *const *consts, uint32_t n_consts, uint32_t **bits,
+						   uint64_t *words_per_row, uint64_t **hits);
+
+/* Text of a column of k-mers as the reference stores it: lower-case ASCII, kmer_out kmer.c:131-138.
+ * with_header == 0: (*text) is n*k bytes.  with_header != 0: n*(k+1) bytes, each k-mer prefixed by
+ * its 1-byte short varlena header ((k+1)<<1|1, SET_VARSIZE_SHORT kmer.c:341-342), i.e. the exact
+ * bytes of the `kmer` datums generate_kmers would have palloc'ed (little-endian servers). */
+int kmer_cuda_submit_decode(kmer_cuda_ctx *ctx, const uint64_t *codes, uint64_t n, int k, int with_header,
+							char **text);
+
+/* Parses a column of k-mer texts (n fixed-stride records of `stride` bytes, lens[i] bytes used,
+ * lens == NULL: all `stride`) into codes: batched kmer_in (kmer.c:109-129). */
+int kmer_cuda_submit_encode(kmer_cuda_ctx *ctx, const char *text, const uint8_t *lens, uint64_t n, int stride,
+							uint64_t **codes);
+
+/* ---------------------------------------------------------------- device-resident API
+ * Same operations on buffers already in HBM (device pointers), asynchronous on `stream`
+ * (a cudaStream_t passed as void*; NULL = the CUDA default stream).  Used for resident-data
+ * benchmarking and by the multi-GPU pipeline, which keeps shards in HBM between steps.
+ * d_seq must be 16-byte aligned and readable up to the next multiple of 16 bytes.
+ * Results that are counts land in the struct filled by kmer_cuda_dev_finish(), which synchronises
+ * the stream and reports input errors found by the kernels. */
+
+typedef struct kmer_dev_result
+{
+	uint64_t n_kmers;	 /* windows produced / counted by the last extract or count */
+	uint64_t n_distinct; /* groups written by the last count */
+	uint64_t n_overflow; /* k-mers that took the overflow (global hash) path; diagnostics */
+} kmer_dev_result;
+
+int kmer_cuda_dev_extract(kmer_cuda_ctx *ctx, const char *d_seq, uint64_t n_bases, const uint64_t *d_row_off,
+						  uint64_t n_rows, int k, uint64_t *d_codes, uint64_t codes_capacity, void *stream);
+
+/* algo: 0 = automatic, 1 = dense table (k small), 2 = global hash table, 3 = minimizer partition */
+int kmer_cuda_dev_count(kmer_cuda_ctx *ctx, const char *d_seq, uint64_t n_bases, const uint64_t *d_row_off,
+						uint64_t n_rows, int k, kmer_count_pair *d_pairs, uint64_t pairs_capacity, int algo,
+						void *stream);
+
+/* consts / ops are HOST arrays (they are compiled to masks on the host); d_* are device pointers.
+ * d_bits: n_consts * ceil(m/32) words; d_hits: n_consts counters. */
+int kmer_cuda_dev_match(kmer_cuda_ctx *ctx, int op, const int *ops, const uint64_t *d_codes, const uint8_t *d_lens,
+						uint64_t m, int k, const char *const *consts, uint32_t n_consts, uint32_t *d_bits,
+						uint64_t *d_hits, void *stream);
+
+int kmer_cuda_dev_decode(kmer_cuda_ctx *ctx, const uint64_t *d_codes, uint64_t n, int k, int with_header,
+						 char *d_text, void *stream);
+
+int kmer_cuda_dev_finish(kmer_cuda_ctx *ctx, void *stream, kmer_dev_result *result);
+
+/* Upper bound of the number of k-mers (= groups) a batch can produce: n_bases - n_rows*(k-1). */
+uint64_t kmer_cuda_max_kmers(uint64_t n_bases, uint64_t n_rows, int k);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMER_CUDA_H */

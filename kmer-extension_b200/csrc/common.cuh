@@ -1,0 +1,132 @@
+// common.cuh -- device helpers shared by the k-mer kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace kmer {
+
+constexpr int kMaxK = 32;              // MAX_KMER_LENGTH, reference kmer.h:18
+constexpr uint64_t kEmpty = ~0ull;     // empty-slot sentinel of the hash tables (== 't'*32 only at k=32)
+constexpr uint64_t kNoError = ~0ull;
+
+// ---------------------------------------------------------------------------------------------
+// status block shared by all kernels of one batch (device memory, mirrored to pinned host memory)
+struct DevStatus {
+    unsigned long long bad_char_pos;   // min flat position of a byte outside ACGTacgt (kmer.c:31-37)
+    unsigned long long short_row;      // min row index with len < k               (kmer.c:310-313)
+    unsigned long long n_kmers;        // windows produced
+    unsigned long long n_distinct;     // groups written
+    unsigned long long n_overflow;     // k-mers routed to the overflow table
+    unsigned long long special_count;  // occurrences of code ~0 (k == 32 only), kept out of the tables
+    unsigned long long out_overflow;   // set if an output buffer was too small
+    unsigned long long pad;
+};
+
+// ---------------------------------------------------------------------------------------------
+// ASCII -> 2-bit SWAR encode of 4 bases (validate_sequence, kmer.c:20-41: fold case, accept acgt).
+// byte 0 of w is the first base; result has the first base in bits 7..6.
+// bad != 0  <=>  some byte is not one of ACGTacgt (byte-wise: nonzero byte = offending position).
+__device__ __forceinline__ uint32_t enc4(uint32_t w, uint32_t& bad) {
+    uint32_t x = (w >> 1) & 0x03030303u;            // A->0 C->1 G->3 T->2 (same for lower case)
+    uint32_t e = x ^ ((x >> 1) & 0x01010101u);      // a=0 c=1 g=2 t=3
+    uint32_t t2 = (x >> 1) & ~x & 0x01010101u;      // x == 2 (t)
+    uint32_t recon = 0x61616161u + (x << 1) + t2 * 15u;  // lower-case ASCII the code stands for
+    bad = (w | 0x20202020u) ^ recon;
+    return (e * 0x40100401u) >> 24;
+}
+
+// 16 ASCII bytes -> one 32-bit word of 16 bases, first base in bits 31..30.
+__device__ __forceinline__ uint32_t enc16(uint4 v, uint32_t& bad) {
+    uint32_t b0, b1, b2, b3;
+    uint32_t p = (enc4(v.x, b0) << 24) | (enc4(v.y, b1) << 16) | (enc4(v.z, b2) << 8) | enc4(v.w, b3);
+    bad = b0 | b1 | b2 | b3;
+    return p;
+}
+
+// index (0..15) of the first offending byte among 16, given the four per-word bad masks
+__device__ __forceinline__ int first_bad_byte(uint4 v) {
+    uint32_t b[4];
+    enc4(v.x, b[0]); enc4(v.y, b[1]); enc4(v.z, b[2]); enc4(v.w, b[3]);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        if (b[i]) {
+            int byte = (__ffs(b[i]) - 1) >> 3;
+            return i * 4 + byte;
+        }
+    return 16;
+}
+
+// 64 bits of a 2-bit packed stream (uint32 words, first base in the MSBs) starting at base i
+__device__ __forceinline__ uint64_t window64(const uint32_t* packed, int i) {
+    int q = i >> 4, s = (i & 15) * 2;
+    uint32_t w0 = packed[q], w1 = packed[q + 1], w2 = packed[q + 2];
+    uint32_t hi = __funnelshift_l(w1, w0, s);
+    uint32_t lo = __funnelshift_l(w2, w1, s);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+// bits [b, b+32) of an LSB-first bit array
+__device__ __forceinline__ uint32_t bits32(const uint32_t* bits, int b) {
+    int q = b >> 5, s = b & 31;
+    return __funnelshift_r(bits[q], bits[q + 1], s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// hashes
+__device__ __host__ __forceinline__ uint64_t mix64(uint64_t x) {   // murmur3 finaliser (bijective)
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
+    x ^= x >> 33;
+    return x;
+}
+__device__ __host__ __forceinline__ uint32_t mix32(uint32_t x) {   // lowbias32 (bijective)
+    x ^= x >> 16; x *= 0x7feb352du;
+    x ^= x >> 15; x *= 0x846ca68bu;
+    x ^= x >> 16;
+    return x;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier + 1-D bulk async copy (TMA engine, SASS: UBLKCP) -- global -> shared staging
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// bytes must be a multiple of 16; src and dst 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ uint64_t ld_nc_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 ld_nc_u128(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+}  // namespace kmer

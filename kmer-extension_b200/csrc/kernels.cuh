@@ -1,0 +1,60 @@
+// kernels.cuh -- launch wrappers implemented across the .cu files of libkmer_cuda.so
+#pragma once
+#include "common.cuh"
+#include "scan.cuh"
+#include "../../include/kmer_cuda.h"
+
+namespace kmer {
+
+// number of CTAs the tile-scanning kernels are launched with (filled at init: SMs x resident CTAs)
+struct DeviceInfo {
+    int device;
+    int sm_count;
+    size_t total_mem;
+};
+
+// rows.cu ---------------------------------------------------------------------------------------
+// zeroes + fills the row-start mask, flags rows shorter than k (or non-monotone offsets)
+void launch_rows_prepare(const uint64_t* d_off, uint64_t n_rows, uint64_t n_bases, int k, uint32_t* d_mask,
+                         uint64_t mask_words, DevStatus* d_status, cudaStream_t st);
+// row index of the row containing the first base of every tile
+void launch_tile_row_base(const uint64_t* d_off, uint64_t n_rows, uint64_t n_tiles, uint32_t* d_tile_row, cudaStream_t st);
+
+// extract.cu ------------------------------------------------------------------------------------
+void launch_extract(const DeviceInfo& di, const ScanArgs& a, const uint32_t* d_tile_row, uint64_t* d_codes,
+                    uint64_t capacity, cudaStream_t st);
+
+// count_dense.cu --------------------------------------------------------------------------------
+// k <= 13: direct-addressed counters (4^k uint64, zeroed here), then compaction of non-zero bins
+void launch_count_dense(const DeviceInfo& di, const ScanArgs& a, unsigned long long* d_table,
+                        kmer_count_pair* d_pairs, uint64_t capacity, cudaStream_t st);
+
+// count_hash.cu ---------------------------------------------------------------------------------
+// open-addressing table of (code,count) slots in HBM; slots must be filled with 0xFF bytes
+void launch_hash_clear(kmer_count_pair* d_slots, uint64_t n_slots, cudaStream_t st);
+void launch_count_hash_insert(const DeviceInfo& di, const ScanArgs& a, kmer_count_pair* d_slots, uint64_t n_slots,
+                              cudaStream_t st);
+// appends every occupied slot (+ the k==32 special key) to d_pairs, bumping status->n_distinct
+void launch_hash_compact(const DeviceInfo& di, const kmer_count_pair* d_slots, uint64_t n_slots, int k,
+                         kmer_count_pair* d_pairs, uint64_t capacity, DevStatus* d_status, cudaStream_t st);
+
+// match.cu --------------------------------------------------------------------------------------
+struct MatchConst {          // one compiled constant
+    uint64_t code;           // equals / starts_with: the literal's code
+    uint64_t m0, m1, m2, m3; // contains: for base value b, bit j of m_b set <=> pattern position j (from the
+                             // LAST base, j = 0) admits base b          (match(), kmer.h:21-53)
+    uint32_t len;            // literal length
+    uint32_t pad;
+};
+// d_ops: optional per-constant op (device array), else `op` for all; any_contains: some constant is a qkmer
+void launch_match(const DeviceInfo& di, int op, const int* d_ops, bool any_contains, const uint64_t* d_codes,
+                  const uint8_t* d_lens, uint64_t m, int k, const MatchConst* d_consts, uint32_t n_consts,
+                  uint32_t* d_bits, uint64_t words_per_row, unsigned long long* d_hits, cudaStream_t st);
+
+// decode.cu -------------------------------------------------------------------------------------
+void launch_decode(const DeviceInfo& di, const uint64_t* d_codes, uint64_t n, int k, int with_header, char* d_text,
+                   cudaStream_t st);
+void launch_encode(const DeviceInfo& di, const char* d_text, const uint8_t* d_lens, uint64_t n, int stride,
+                   uint64_t* d_codes, DevStatus* d_status, cudaStream_t st);
+
+}  // namespace kmer

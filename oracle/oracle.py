@@ -321,7 +321,8 @@ def np_match(op: int, codes: np.ndarray, k: int, const: str, lens: np.ndarray | 
         if op == 0:
             return ((lk == lc) & (codes == ccode)).astype(np.uint8)
         sh = (2 * np.maximum(lk - lc, 0)).astype(np.uint64)
-        return ((lk >= lc) & ((codes >> sh) == ccode)).astype(np.uint8)
+        shifted = np.where(sh >= 64, np.uint64(0), codes >> np.minimum(sh, np.uint64(63)))
+        return ((lk >= lc) & (shifted == ccode)).astype(np.uint8)
     ok = lk == lc
     for j, ch in enumerate(c):
         base = ((codes >> np.uint64(2 * max(lc - 1 - j, 0))) & np.uint64(3)).astype(np.int64)

@@ -424,11 +424,26 @@ typedef struct AggTable
 {
 	AggEntry *slots;
 	uint64_t cap, used;
+	uint32_t hash_iv; /* per-worker perturbation, as PostgreSQL's TupleHashTable does for parallel
+					   * aggregation (execGrouping.c, use_variable_hash_iv): without it the leader
+					   * re-inserts groups in the workers' bucket order and linear probing goes quadratic */
 	PgShimArena keys; /* group keys live in the aggregate's own context */
 } AggTable;
 
-static void agg_init(AggTable *t, uint64_t cap)
+static inline uint32_t agg_bucket(const AggTable *t, uint32_t h)
 {
+	uint32_t x = h ^ t->hash_iv; /* murmurhash32 finaliser, like execGrouping.c */
+	x ^= x >> 16;
+	x *= 0x85ebca6bu;
+	x ^= x >> 13;
+	x *= 0xc2b2ae35u;
+	x ^= x >> 16;
+	return x;
+}
+
+static void agg_init(AggTable *t, uint64_t cap, uint32_t iv)
+{
+	t->hash_iv = iv;
 	uint64_t c = 1024;
 	while (c < cap)
 		c <<= 1;
@@ -447,7 +462,7 @@ static AggEntry *agg_lookup(AggTable *t, struct varlena *key, uint32_t h)
 {
 	if (t->used * 4 >= t->cap * 3)
 		agg_grow(t);
-	uint64_t mask = t->cap - 1, i = h & mask;
+	uint64_t mask = t->cap - 1, i = agg_bucket(t, h) & mask;
 	for (;;)
 	{
 		AggEntry *e = &t->slots[i];
@@ -479,7 +494,7 @@ static void agg_grow(AggTable *t)
 	for (uint64_t j = 0; j < oc; j++)
 		if (old[j].key)
 		{
-			uint64_t i = old[j].hash & mask;
+			uint64_t i = agg_bucket(t, old[j].hash) & mask;
 			while (t->slots[i].key)
 				i = (i + 1) & mask;
 			t->slots[i] = old[j];
@@ -583,7 +598,7 @@ int ref_count(const char *flat, const uint64_t *off, uint64_t n_rows, int k, int
 		ws[t].row_lo = n_rows * (uint64_t) t / (uint64_t) threads;
 		ws[t].row_hi = n_rows * (uint64_t) (t + 1) / (uint64_t) threads;
 		ws[t].k = k;
-		agg_init(&ws[t].table, 1 << 12);
+		agg_init(&ws[t].table, 1 << 12, (uint32_t) t * 0x9e3779b9u);
 	}
 	if (threads == 1)
 		worker_main(&ws[0]);
