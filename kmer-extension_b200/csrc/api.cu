@@ -38,7 +38,8 @@ struct kmer_cuda_ctx {
     DevStatus* d_status = nullptr;
     DevStatus* h_status = nullptr;  // pinned
     // device workspaces, grown on demand and kept between calls
-    Buf seq, off, mask, tile_row, table, consts, ops, codes, pairs, bits, hits, lens, text;
+    Buf seq, off, mask, tile_row, table, consts, ops, codes, pairs, bits, hits, lens, text, fill, recs;
+    uint64_t last_overflow = 0;   // k-mers the partition counter could not place (batch was recounted)
     std::vector<PinnedBuf> pinned;
     // the operation kmer_cuda_dev_finish() has to report on
     PendingOp pending = OP_NONE;
@@ -331,7 +332,7 @@ extern "C" void kmer_cuda_shutdown(kmer_cuda_ctx* c) {
     cudaSetDevice(c->di.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     Buf* all[] = {&c->seq, &c->off, &c->mask, &c->tile_row, &c->table, &c->consts, &c->ops,
-                  &c->codes, &c->pairs, &c->bits, &c->hits, &c->lens, &c->text};
+                  &c->codes, &c->pairs, &c->bits, &c->hits, &c->lens, &c->text, &c->fill, &c->recs};
     for (Buf* b : all) buf_free(*b);
     for (auto& p : c->pinned) cudaFreeHost(p.p);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -443,6 +444,15 @@ extern "C" int kmer_cuda_dev_extract(kmer_cuda_ctx* c, const char* d_seq, uint64
     return KMER_OK;
 }
 
+struct MarkArg {
+    kmer_cuda_ctx* c;
+    cudaStream_t st;
+};
+static void mark_cb(void* arg, const char* name) {
+    MarkArg* m = (MarkArg*)arg;
+    mark(m->c, m->st, name);
+}
+
 static uint64_t next_pow2(uint64_t v) {
     uint64_t p = 1;
     while (p < v) p <<= 1;
@@ -466,7 +476,32 @@ extern "C" int kmer_cuda_dev_count(kmer_cuda_ctx* c, const char* d_seq, uint64_t
     ScanArgs a;
     rc = prepare_rows(c, d_row_off, n_bases, n_rows, k, st, &a, d_seq);
     if (rc) return rc;
-    if (algo == 0) algo = (k <= 13) ? 1 : 2;
+    if (algo == 0) algo = (k <= 13) ? 1 : 3;
+    c->last_overflow = 0;
+    if (algo == 3) {
+        if (k < 14) return bad_arg(c, "minimizer-partition counting needs k >= 14");
+        PartitionPlan plan = make_partition_plan(c->p_expected_kmers, k);
+        rc = ws(c, c->fill, (size_t)plan.n_buckets * 8);
+        if (!rc) rc = ws(c, c->recs, partition_record_bytes(plan));
+        if (rc) return rc;
+        MarkArg ma{c, st};
+        launch_count_partition(c->di, a, plan, (unsigned long long*)c->fill.p, c->recs.p, d_pairs, pairs_capacity, st,
+                               mark_cb, &ma);
+        c->launches += 3;
+        // Did everything fit?  (One host round trip; repetitive input is recounted through the hash table.)
+        CU(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, st), "D2H status");
+        CU(cudaStreamSynchronize(st), "stream sync");
+        if (c->h_status->n_overflow == 0 || c->h_status->bad_char_pos != kNoError || c->h_status->short_row != kNoError) {
+            algo = -1;  // done (or failing with an input error that finish() reports)
+        } else {
+            c->last_overflow = c->h_status->n_overflow;
+            unsigned long long keep_short = c->h_status->short_row;
+            (void)keep_short;
+            status_reset_kernel<<<1, 1, 0, st>>>(c->d_status);
+            c->launches++;
+            algo = 2;
+        }
+    }
     if (algo == 1) {
         if (k > 13) return bad_arg(c, "dense counting needs k <= 13");
         uint64_t nbins = 1ull << (2 * k);
@@ -488,7 +523,7 @@ extern "C" int kmer_cuda_dev_count(kmer_cuda_ctx* c, const char* d_seq, uint64_t
         launch_hash_compact(c->di, (const kmer_count_pair*)c->table.p, n_slots, k, d_pairs, pairs_capacity, c->d_status, st);
         c->launches += 2;
         mark(c, st, "hash_compact");
-    } else
+    } else if (algo != -1)
         return bad_arg(c, "unknown counting algorithm");
     resolve_bad_row_kernel<<<1, 1, 0, st>>>(c->d_status, d_row_off, n_rows);
     c->launches++;
@@ -598,7 +633,7 @@ extern "C" int kmer_cuda_dev_finish(kmer_cuda_ctx* c, void* stream, kmer_dev_res
         if (result) {
             result->n_kmers = op == OP_EXTRACT ? c->p_expected_kmers : s.n_kmers;
             result->n_distinct = s.n_distinct;
-            result->n_overflow = s.n_overflow;
+            result->n_overflow = c->last_overflow;
         }
         if (op == OP_COUNT && s.n_kmers != c->p_expected_kmers)
             return set_error(&c->err, KMER_ERR_CUDA, "XX000", "kmer_cuda: internal error: counted k-mers != windows", "", -1);

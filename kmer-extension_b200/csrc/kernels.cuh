@@ -38,6 +38,23 @@ void launch_count_hash_insert(const DeviceInfo& di, const ScanArgs& a, kmer_coun
 void launch_hash_compact(const DeviceInfo& di, const kmer_count_pair* d_slots, uint64_t n_slots, int k,
                          kmer_count_pair* d_pairs, uint64_t capacity, DevStatus* d_status, cudaStream_t st);
 
+// count_part.cu --------------------------------------------------------------------------------
+struct PartitionPlan {
+    uint32_t n_buckets;   // buckets the k-mers are spread over (about 2400 k-mers each)
+    uint32_t cap;         // records a bucket region holds
+    int w;                // m-mers per minimizer window (4, 8 or 16)
+    int m;                // m-mer length (<= 16)
+    int recw;             // 64-bit words per super-k-mer record (1: k <= 26, 2: k >= 27)
+    int rmax;             // max k-mers per record
+};
+PartitionPlan make_partition_plan(uint64_t n_kmers, int k);
+size_t partition_record_bytes(const PartitionPlan& p);
+// minimizer partition + per-bucket shared-memory counting (14 <= k <= 32).  Anything that does not
+// fit is reported in DevStatus::n_overflow (then the result is incomplete and must be discarded).
+void launch_count_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPlan& p, unsigned long long* d_fill,
+                            void* d_recs, kmer_count_pair* d_pairs, uint64_t capacity, cudaStream_t st,
+                            void (*mark)(void*, const char*), void* mark_arg);
+
 // match.cu --------------------------------------------------------------------------------------
 struct MatchConst {          // one compiled constant
     uint64_t code;           // equals / starts_with: the literal's code
