@@ -251,8 +251,9 @@ def main():
         "hash_compact": 16 * n_distinct * 2,                     # read + write every group once
         "hash_clear": 0,
         "count_dense+compact": n_bases + 16 * n_distinct,
-        "minimizer_partition": n_bases,                         # + super-k-mer records, counted in DESIGN.md
-        "bucket_count": 16 * n_distinct,
+        "minimizer_partition": n_bases,                         # compulsory: read every base once (records are overhead)
+        "bucket_count": 16 * n_distinct,                        # compulsory: write every group once
+        "tier2_insert": 0, "tier2_compact": 0,
     }
     dom = max(phases, key=phases.get) if phases else None
     roofline = None
@@ -313,7 +314,8 @@ def main():
             "config": {"workload": f"configs[1]: k=21 count over {n_bases / 1e9:.3g} GB synthetic DNA per GPU "
                                    f"({n_rows} reads x {READ_LEN}, seed 2+rank)", "k": K, "read_len": READ_LEN,
                        "reads_per_gpu": n_rows, "algo": args.algo, "n_kmers_per_step": n_kmers * world,
-                       "n_distinct_rank0": n_distinct, "l2": "inputs and tables larger than L2 (no flush needed)",
+                       "n_distinct_rank0": n_distinct, "recounted_kmers": int(res.n_overflow),
+                       "tier2_kmers": int(res.n_tier2), "l2": "inputs and tables larger than L2 (no flush needed)",
                        "bases_per_sec": n_bases * world * args.steps / (ms_total * 1e-3)},
             "roofline": roofline, "roofline_step": roofline_step, "phases_ms": phases, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks}

@@ -158,7 +158,10 @@ typedef struct kmer_dev_result
 {
 	uint64_t n_kmers;	 /* windows produced / counted by the last extract or count */
 	uint64_t n_distinct; /* groups written by the last count */
-	uint64_t n_overflow; /* k-mers that took the overflow (global hash) path; diagnostics */
+	uint64_t n_overflow; /* != 0: the partition counter gave up and the batch was recounted through the
+						  * global hash table (highly repetitive input); diagnostics only */
+	uint64_t n_tier2;	 /* k-mers of buckets that did not fit on chip and were counted by the tier-2
+						  * kernel instead; diagnostics only */
 } kmer_dev_result;
 
 int kmer_cuda_dev_extract(kmer_cuda_ctx *ctx, const char *d_seq, uint64_t n_bases, const uint64_t *d_row_off,

@@ -47,7 +47,7 @@ class KmerCudaError(C.Structure):
 
 
 class KmerDevResult(C.Structure):
-    _fields_ = [("n_kmers", C.c_uint64), ("n_distinct", C.c_uint64), ("n_overflow", C.c_uint64)]
+    _fields_ = [("n_kmers", C.c_uint64), ("n_distinct", C.c_uint64), ("n_overflow", C.c_uint64), ("n_tier2", C.c_uint64)]
 
 
 class KmerSqlError(Exception):

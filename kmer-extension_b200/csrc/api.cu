@@ -38,7 +38,8 @@ struct kmer_cuda_ctx {
     DevStatus* d_status = nullptr;
     DevStatus* h_status = nullptr;  // pinned
     // device workspaces, grown on demand and kept between calls
-    Buf seq, off, mask, tile_row, table, consts, ops, codes, pairs, bits, hits, lens, text, fill, recs;
+    Buf seq, off, mask, tile_row, table, consts, ops, codes, pairs, bits, hits, lens, text, fill, recs, spill, failed;
+    uint64_t last_tier2 = 0;      // k-mers counted by the tier-2 kernel in the last count
     uint64_t last_overflow = 0;   // k-mers the partition counter could not place (batch was recounted)
     std::vector<PinnedBuf> pinned;
     // the operation kmer_cuda_dev_finish() has to report on
@@ -191,6 +192,10 @@ __global__ void status_reset_kernel(DevStatus* s) {
     s->special_count = 0;
     s->out_overflow = 0;
     s->pad = kNoError;
+    s->n_spill = 0;
+    s->n_failed = 0;
+    s->failed_kmers = 0;
+    s->reserved = 0;
 }
 
 // pad := row containing bad_char_pos (so the host never needs the offsets)
@@ -332,7 +337,7 @@ extern "C" void kmer_cuda_shutdown(kmer_cuda_ctx* c) {
     cudaSetDevice(c->di.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     Buf* all[] = {&c->seq, &c->off, &c->mask, &c->tile_row, &c->table, &c->consts, &c->ops,
-                  &c->codes, &c->pairs, &c->bits, &c->hits, &c->lens, &c->text, &c->fill, &c->recs};
+                  &c->codes, &c->pairs, &c->bits, &c->hits, &c->lens, &c->text, &c->fill, &c->recs, &c->spill, &c->failed};
     for (Buf* b : all) buf_free(*b);
     for (auto& p : c->pinned) cudaFreeHost(p.p);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -478,28 +483,49 @@ extern "C" int kmer_cuda_dev_count(kmer_cuda_ctx* c, const char* d_seq, uint64_t
     if (rc) return rc;
     if (algo == 0) algo = (k <= 13) ? 1 : 3;
     c->last_overflow = 0;
+    c->last_tier2 = 0;
     if (algo == 3) {
         if (k < 14) return bad_arg(c, "minimizer-partition counting needs k >= 14");
         PartitionPlan plan = make_partition_plan(c->p_expected_kmers, k);
         rc = ws(c, c->fill, (size_t)plan.n_buckets * 8);
         if (!rc) rc = ws(c, c->recs, partition_record_bytes(plan));
+        if (!rc) rc = ws(c, c->spill, partition_spill_bytes(plan));
+        if (!rc) rc = ws(c, c->failed, (size_t)plan.n_buckets * 4);
         if (rc) return rc;
         MarkArg ma{c, st};
-        launch_count_partition(c->di, a, plan, (unsigned long long*)c->fill.p, c->recs.p, d_pairs, pairs_capacity, st,
-                               mark_cb, &ma);
-        c->launches += 3;
-        // Did everything fit?  (One host round trip; repetitive input is recounted through the hash table.)
+        launch_count_partition(c->di, a, plan, (unsigned long long*)c->fill.p, c->recs.p, c->spill.p, (uint32_t*)c->failed.p,
+                               d_pairs, pairs_capacity, st, mark_cb, &ma);
+        c->launches += 2;
+        // Did everything fit?  (One host round trip; skewed input needs tier 2 or a full recount.)
         CU(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, st), "D2H status");
         CU(cudaStreamSynchronize(st), "stream sync");
-        if (c->h_status->n_overflow == 0 || c->h_status->bad_char_pos != kNoError || c->h_status->short_row != kNoError) {
-            algo = -1;  // done (or failing with an input error that finish() reports)
-        } else {
-            c->last_overflow = c->h_status->n_overflow;
-            unsigned long long keep_short = c->h_status->short_row;
-            (void)keep_short;
+        const DevStatus hs = *c->h_status;
+        if (hs.bad_char_pos != kNoError || hs.short_row != kNoError) {
+            algo = -1;  // failing with an input error that finish() reports
+        } else if (hs.n_overflow != 0) {
+            c->last_overflow = hs.n_overflow;        // tier 3: recount the batch through the global hash table
             status_reset_kernel<<<1, 1, 0, st>>>(c->d_status);
             c->launches++;
             algo = 2;
+        } else {
+            if (hs.n_failed || hs.n_spill) {         // tier 2: only the buckets that did not fit
+                uint64_t n_slots = next_pow2(std::max<uint64_t>(1024, hs.failed_kmers * 2));
+                rc = ws(c, c->table, n_slots * sizeof(kmer_count_pair));
+                if (rc) return rc;
+                launch_hash_clear((kmer_count_pair*)c->table.p, n_slots, st);
+                launch_partition_tier2(c->di, plan, k, (const unsigned long long*)c->fill.p, c->recs.p, c->spill.p,
+                                       (const uint32_t*)c->failed.p, (kmer_count_pair*)c->table.p, n_slots, c->d_status, st);
+                mark(c, st, "tier2_insert");
+                // compaction appends the table and the k==32 special key and adds both to n_kmers
+                launch_hash_compact(c->di, (const kmer_count_pair*)c->table.p, n_slots, k, d_pairs, pairs_capacity, c->d_status, st);
+                mark(c, st, "tier2_compact");
+                c->launches += 2;
+                c->last_tier2 = hs.failed_kmers;
+            } else {
+                launch_append_special(d_pairs, pairs_capacity, c->d_status, st);
+                c->launches++;
+            }
+            algo = -1;
         }
     }
     if (algo == 1) {
@@ -620,6 +646,7 @@ extern "C" int kmer_cuda_dev_finish(kmer_cuda_ctx* c, void* stream, kmer_dev_res
         result->n_kmers = 0;
         result->n_distinct = 0;
         result->n_overflow = 0;
+        result->n_tier2 = 0;
     }
     PendingOp op = c->pending;
     c->pending = OP_NONE;
@@ -634,6 +661,7 @@ extern "C" int kmer_cuda_dev_finish(kmer_cuda_ctx* c, void* stream, kmer_dev_res
             result->n_kmers = op == OP_EXTRACT ? c->p_expected_kmers : s.n_kmers;
             result->n_distinct = s.n_distinct;
             result->n_overflow = c->last_overflow;
+            result->n_tier2 = c->last_tier2;
         }
         if (op == OP_COUNT && s.n_kmers != c->p_expected_kmers)
             return set_error(&c->err, KMER_ERR_CUDA, "XX000", "kmer_cuda: internal error: counted k-mers != windows", "", -1);

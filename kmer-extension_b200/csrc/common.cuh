@@ -19,7 +19,11 @@ struct DevStatus {
     unsigned long long n_overflow;     // k-mers routed to the overflow table
     unsigned long long special_count;  // occurrences of code ~0 (k == 32 only), kept out of the tables
     unsigned long long out_overflow;   // set if an output buffer was too small
-    unsigned long long pad;
+    unsigned long long pad;            // row containing bad_char_pos (resolve_bad_row_kernel)
+    unsigned long long n_spill;        // partition: records that did not fit their bucket region
+    unsigned long long n_failed;       // partition: buckets handed to the tier-2 kernel
+    unsigned long long failed_kmers;   // k-mers (instances) in those buckets
+    unsigned long long reserved;
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -16,17 +16,19 @@
 //
 // HBM traffic: read N bases once, write + read ~2.3 B per k-mer of records, write 16 B per group.
 //
-// Anything that does not fit (a bucket region overflowing, or a bucket holding more k-mers than its
-// shared-memory table takes: highly repetitive input) is only counted in DevStatus::n_overflow; the
-// caller then recounts the batch with the global-hash-table path (count_hash.cu).  No result is
-// produced from a partially counted batch.
+// What does not fit is handled in tiers (skewed / repetitive input):
+//   tier 2  a bucket whose region overflowed (extra records go to a spill list) or whose distinct
+//           k-mers overflow the shared table is put on a failed list and emits nothing; one more
+//           kernel counts exactly those buckets' records in a global hash table and appends them;
+//   tier 3  if even the spill list overflows, DevStatus::n_overflow is set and the caller recounts
+//           the whole batch with the global-hash-table path (count_hash.cu).
 #include "kernels.cuh"
 
 namespace kmer {
 
 constexpr int LEAF_SLOTS = 4096;          // shared-memory table slots per bucket
-constexpr int LEAF_MAX_KMERS = 3400;      // refuse buckets above this load (0.83)
-constexpr int LEAF_THREADS = 256;
+constexpr int LEAF_THREADS = 512;
+constexpr uint32_t TARGET_KMERS_PER_BUCKET = 2000;   // mean load 0.49 of the table; the tail is handled by tier 2
 
 // ---------------------------------------------------------------------------------------------
 // record formats
@@ -50,7 +52,7 @@ struct alignas(16) Rec<2> {
 
 template <int W, int RECW>
 __global__ void __launch_bounds__(NT) partition_kernel(ScanArgs a, PartitionPlan plan, unsigned long long* __restrict__ fill,
-                                                       Rec<RECW>* __restrict__ recs) {
+                                                       Rec<RECW>* __restrict__ recs, Rec<RECW>* __restrict__ spill) {
     __shared__ ScanSmem s;
     __shared__ uint32_t sbucket[TILE];
     TileScanner sc(a, s);
@@ -122,21 +124,26 @@ __global__ void __launch_bounds__(NT) partition_kernel(ScanArgs a, PartitionPlan
                 const int nb = L + k - 1;                          // bases covered
                 unsigned long long old = atomicAdd(&fill[b], ((unsigned long long)L << 32) | 1ull);
                 uint32_t slot = (uint32_t)old;
-                if (slot < plan.cap) {
+                Rec<RECW>* dst = nullptr;
+                if (slot < plan.cap) dst = recs + ((uint64_t)b * plan.cap + slot);
+                else {                                              // region full: spill list (tier 2), else recount
+                    unsigned long long si = atomicAdd(&a.status->n_spill, 1ull);
+                    if (si < plan.spill_cap) dst = spill + si;
+                    else overflow_kmers += L;
+                }
+                if (dst) {
                     if (RECW == 1) {
                         uint64_t v = ((uint64_t)r0 << 32) | r1;
                         v &= ~0ull << (64 - 2 * nb);               // nb <= 30
-                        reinterpret_cast<uint64_t*>(recs)[(uint64_t)b * plan.cap + slot] = v | (uint64_t)(L - 1);
+                        reinterpret_cast<uint64_t*>(dst)[0] = v | (uint64_t)(L - 1);
                     } else {
                         uint64_t hi = ((uint64_t)r0 << 32) | r1;
                         uint64_t lo = (uint64_t)r2 << 32;          // bases 32..47 (nb <= 47)
                         if (nb <= 32) { hi &= ~0ull << (64 - 2 * nb); lo = 0; }
                         else lo &= ~0ull << (128 - 2 * nb);
                         ulonglong2 o; o.x = hi; o.y = lo | (uint64_t)(L - 1);
-                        reinterpret_cast<ulonglong2*>(recs)[(uint64_t)b * plan.cap + slot] = o;
+                        reinterpret_cast<ulonglong2*>(dst)[0] = o;
                     }
-                } else {
-                    overflow_kmers += L;
                 }
             }
         }
@@ -147,100 +154,232 @@ __global__ void __launch_bounds__(NT) partition_kernel(ScanArgs a, PartitionPlan
 
 // ---------------------------------------------------------------------------------------------
 // per-bucket counting
+//
+// One CTA per bucket, three phases separated by __syncthreads:
+//   expand : every record is unpacked into its k-mers, written to a shared key array (a shared
+//            atomicAdd per RECORD reserves the range) -- after this the work is one k-mer per lane,
+//            perfectly balanced, whatever the record lengths were;
+//   insert : each thread inserts 4 independent keys at a time into the 4096-slot table with 64-bit
+//            shared atomicCAS (4 CAS in flight per thread hide the shared-atomic latency); a key that
+//            is already present bumps a 32-bit counter;
+//   emit   : one global atomicAdd per bucket reserves the output range, the table is scanned and the
+//            occupied slots are written as 16-byte (k-mer, count) pairs.
+// A bucket whose distinct keys do not fit the table, or whose region overflowed in the partition
+// pass, is appended to the failed list and emits nothing (its k-mers are counted by the tier-2 kernel).
+
+constexpr int KEYS_CAP = 4096;            // k-mers expanded per pass
+constexpr int RECS_PER_SMALL_PASS = KEYS_CAP / 16;
+
+__device__ __forceinline__ uint32_t leaf_hash(uint64_t key) {
+    uint32_t h = ((uint32_t)key * 0x9E3779B1u) ^ ((uint32_t)(key >> 32) * 0x85EBCA6Bu);
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 13;
+    return h & (LEAF_SLOTS - 1);
+}
 
 template <int RECW>
 __global__ void __launch_bounds__(LEAF_THREADS) bucket_count_kernel(PartitionPlan plan, int k,
                                                                     const unsigned long long* __restrict__ fill,
                                                                     const Rec<RECW>* __restrict__ recs,
                                                                     kmer_count_pair* __restrict__ out, uint64_t capacity,
-                                                                    DevStatus* status) {
+                                                                    uint32_t* __restrict__ failed_ids, DevStatus* status) {
     extern __shared__ __align__(16) unsigned char leaf_dyn[];
-    unsigned long long* tbl = reinterpret_cast<unsigned long long*>(leaf_dyn);             // [LEAF_SLOTS]
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(leaf_dyn + LEAF_SLOTS * sizeof(unsigned long long));  // [LEAF_SLOTS]
+    unsigned long long* tbl = reinterpret_cast<unsigned long long*>(leaf_dyn);                         // [LEAF_SLOTS]
+    unsigned long long* keys = tbl + LEAF_SLOTS;                                                        // [KEYS_CAP]
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(keys + KEYS_CAP);                                       // [LEAF_SLOTS]
     __shared__ uint32_t s_own[LEAF_THREADS / 32];
     __shared__ unsigned long long s_base;
-    __shared__ uint32_t s_cursor;
+    __shared__ uint32_t s_cursor, s_nkeys, s_failed, s_special;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int kshift = 64 - 2 * k;
-    unsigned long long special = 0, total_kmers = 0, skipped = 0;
+    unsigned long long special_total = 0, kmers_total = 0;
 
     for (uint32_t b = blockIdx.x; b < plan.n_buckets; b += gridDim.x) {
         const unsigned long long f = fill[b];
         const uint32_t nrec_all = (uint32_t)f, nk = (uint32_t)(f >> 32);
-        if (nrec_all == 0) continue;
-        if (nrec_all > plan.cap || nk > LEAF_MAX_KMERS) {   // uniform across the CTA
-            if (t == 0) skipped += nk;       // this bucket's k-mers are not counted here: the batch is recounted
+        if (nrec_all == 0) continue;                                    // uniform across the CTA
+        if (nrec_all > plan.cap) {                                      // region overflowed: tier 2 counts it
+            if (t == 0) {
+                uint32_t idx = (uint32_t)atomicAdd(&status->n_failed, 1ull);
+                failed_ids[idx] = b;
+                atomicAdd(&status->failed_kmers, (unsigned long long)nk);
+            }
             continue;
         }
         for (int i = t; i < LEAF_SLOTS; i += LEAF_THREADS) { tbl[i] = kEmpty; cnt[i] = 0; }
-        if (t == 0) s_cursor = 0;
+        if (t == 0) { s_cursor = 0; s_nkeys = 0; s_failed = 0; s_special = 0; }
         __syncthreads();
         uint32_t own = 0;
         const Rec<RECW>* base = recs + (uint64_t)b * plan.cap;
-        for (uint32_t r = t; r < nrec_all; r += LEAF_THREADS) {
-            uint64_t hi, lo = 0;
-            int L;
-            if (RECW == 1) {
-                hi = ld_nc_u64(reinterpret_cast<const uint64_t*>(base) + r);
-                L = (int)(hi & 15u) + 1;
-            } else {
-                uint4 raw = ld_nc_u128(base + r);
-                hi = ((uint64_t)raw.y << 32) | raw.x;
-                lo = ((uint64_t)raw.w << 32) | raw.z;
-                L = (int)(lo & 63u) + 1;
-            }
-            for (int o = 0; o < L; o++) {
-                uint64_t win = (RECW == 1 || o == 0) ? (hi << (2 * o)) : ((hi << (2 * o)) | (lo >> (64 - 2 * o)));
-                uint64_t key = win >> kshift;
-                if (key == kEmpty) { special++; continue; }           // k == 32, 't'*32
-                uint32_t hsh = (uint32_t)(mix64(key)) & (LEAF_SLOTS - 1);
-                for (;;) {
-                    unsigned long long old = atomicCAS(&tbl[hsh], kEmpty, key);
-                    if (old == kEmpty) { own++; break; }
-                    if (old == key) { atomicAdd(&cnt[hsh], 1u); break; }
-                    hsh = (hsh + 1) & (LEAF_SLOTS - 1);
+        const uint32_t pass_recs = nk <= KEYS_CAP ? nrec_all : RECS_PER_SMALL_PASS;
+        for (uint32_t r0 = 0; r0 < nrec_all; r0 += pass_recs) {
+            const uint32_t r1 = min(nrec_all, r0 + pass_recs);
+            // ---- expand
+            for (uint32_t r = r0 + t; r < r1; r += LEAF_THREADS) {
+                uint64_t hi, lo = 0;
+                int L;
+                if (RECW == 1) {
+                    hi = ld_nc_u64(reinterpret_cast<const uint64_t*>(base) + r);
+                    L = (int)(hi & 15u) + 1;
+                } else {
+                    uint4 raw = ld_nc_u128(base + r);
+                    hi = ((uint64_t)raw.y << 32) | raw.x;
+                    lo = ((uint64_t)raw.w << 32) | raw.z;
+                    L = (int)(lo & 63u) + 1;
+                }
+                uint32_t pos = atomicAdd(&s_nkeys, (uint32_t)L);
+                for (int o = 0; o < L; o++) {
+                    uint64_t win = (RECW == 1 || o == 0) ? (hi << (2 * o)) : ((hi << (2 * o)) | (lo >> (64 - 2 * o)));
+                    keys[pos + o] = win >> kshift;
                 }
             }
-            total_kmers += L;
+            __syncthreads();
+            const uint32_t n_keys = s_nkeys;
+            // ---- insert, 4 independent probes per thread
+            for (uint32_t i0 = t; i0 < n_keys; i0 += 4 * LEAF_THREADS) {
+                uint64_t key[4];
+                uint32_t h[4], tries[4];
+                uint32_t pend = 0;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    uint32_t i = i0 + q * LEAF_THREADS;
+                    key[q] = i < n_keys ? keys[i] : kEmpty;
+                    h[q] = leaf_hash(key[q]);
+                    tries[q] = 0;
+                    if (i < n_keys) {
+                        if (key[q] == kEmpty) atomicAdd(&s_special, 1u);     // k == 32, 't'*32: kept out of the table
+                        else pend |= 1u << q;
+                    }
+                }
+                while (pend) {
+                    unsigned long long old[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        old[q] = (pend >> q) & 1u ? atomicCAS(&tbl[h[q]], kEmpty, key[q]) : 0ull;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        if (!((pend >> q) & 1u)) continue;
+                        if (old[q] == kEmpty) { own++; pend &= ~(1u << q); }
+                        else if (old[q] == key[q]) { atomicAdd(&cnt[h[q]], 1u); pend &= ~(1u << q); }
+                        else {
+                            h[q] = (h[q] + 1) & (LEAF_SLOTS - 1);
+                            if (++tries[q] >= LEAF_SLOTS) { s_failed = 1; pend &= ~(1u << q); }   // table full
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (t == 0) s_nkeys = 0;
+            __syncthreads();
         }
-        // distinct keys of this bucket -> one reservation in the result
+        // ---- emit
         for (int d = 16; d; d >>= 1) own += __shfl_xor_sync(0xffffffffu, own, d);
         if (lane == 0) s_own[warp] = own;
         __syncthreads();
+        const bool failed = s_failed != 0;
         if (t == 0) {
-            uint32_t tot = 0;
-            for (int i = 0; i < LEAF_THREADS / 32; i++) tot += s_own[i];
-            s_base = tot ? atomicAdd(&status->n_distinct, (unsigned long long)tot) : 0ull;
+            if (failed) {
+                uint32_t idx = (uint32_t)atomicAdd(&status->n_failed, 1ull);
+                failed_ids[idx] = b;
+                atomicAdd(&status->failed_kmers, (unsigned long long)nk);
+            } else {
+                uint32_t tot = 0;
+                for (int i = 0; i < LEAF_THREADS / 32; i++) tot += s_own[i];
+                s_base = tot ? atomicAdd(&status->n_distinct, (unsigned long long)tot) : 0ull;
+                special_total += s_special;
+                kmers_total += nk - s_special;
+            }
         }
         __syncthreads();
-        const unsigned long long obase = s_base;
-        for (int i = t; i < LEAF_SLOTS; i += LEAF_THREADS) {
-            unsigned long long key = tbl[i];
-            bool occ = key != kEmpty;
-            uint32_t m = __ballot_sync(0xffffffffu, occ);
-            if (!m) continue;
-            uint32_t pos = 0;
-            if (lane == 0) pos = atomicAdd(&s_cursor, (uint32_t)__popc(m));
-            pos = __shfl_sync(0xffffffffu, pos, 0);
-            if (occ) {
-                uint64_t idx = obase + pos + __popc(m & ((1u << lane) - 1));
-                if (idx < capacity) {
-                    ulonglong2 o; o.x = key; o.y = 1ull + cnt[i];
-                    reinterpret_cast<ulonglong2*>(out)[idx] = o;
-                } else status->out_overflow = 1;
+        if (!failed) {
+            const unsigned long long obase = s_base;
+            for (int i = t; i < LEAF_SLOTS; i += LEAF_THREADS) {
+                unsigned long long key = tbl[i];
+                bool occ = key != kEmpty;
+                uint32_t m = __ballot_sync(0xffffffffu, occ);
+                if (!m) continue;
+                uint32_t pos = 0;
+                if (lane == 0) pos = atomicAdd(&s_cursor, (uint32_t)__popc(m));
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+                if (occ) {
+                    uint64_t idx = obase + pos + __popc(m & ((1u << lane) - 1));
+                    if (idx < capacity) {
+                        ulonglong2 o; o.x = key; o.y = 1ull + cnt[i];
+                        reinterpret_cast<ulonglong2*>(out)[idx] = o;
+                    } else status->out_overflow = 1;
+                }
             }
         }
         __syncthreads();   // table is re-initialised for the next bucket
     }
-    for (int d = 16; d; d >>= 1) {
-        special += __shfl_xor_sync(0xffffffffu, special, d);
-        total_kmers += __shfl_xor_sync(0xffffffffu, total_kmers, d);
+    if (t == 0) {
+        if (special_total) atomicAdd(&status->special_count, special_total);
+        if (kmers_total) atomicAdd(&status->n_kmers, kmers_total);
     }
-    if (lane == 0) {
-        if (special) atomicAdd(&status->special_count, special);
-        if (total_kmers) atomicAdd(&status->n_kmers, total_kmers);
+}
+
+// tier 2: every k-mer of the failed buckets (their in-region records) and of the spill list goes into
+// a global open-addressing table (count_hash.cu layout); hash_compact then appends it to the result.
+// Failed buckets and spilled records hold k-mers of the same buckets only, so nothing here can also
+// have been emitted by bucket_count_kernel.
+__device__ __forceinline__ void global_table_add(kmer_count_pair* slots, uint64_t mask, uint64_t code, unsigned long long c) {
+    uint64_t h = mix64(code) & mask;
+    for (;;) {
+        unsigned long long prev = atomicCAS((unsigned long long*)&slots[h].code, kEmpty, code);
+        if (prev == kEmpty || prev == code) { atomicAdd((unsigned long long*)&slots[h].count, c); return; }
+        h = (h + 1) & mask;
     }
-    if (skipped) atomicAdd(&status->n_overflow, skipped);
+}
+
+template <int RECW>
+__device__ __forceinline__ void tier2_add_record(const Rec<RECW>* p, int kshift, kmer_count_pair* slots, uint64_t mask,
+                                                 DevStatus* status, bool active) {
+    uint64_t hi = 0, lo = 0;
+    int L = 0;
+    if (active) {
+        if (RECW == 1) { hi = reinterpret_cast<const uint64_t*>(p)[0]; L = (int)(hi & 15u) + 1; }
+        else { hi = reinterpret_cast<const uint64_t*>(p)[0]; lo = reinterpret_cast<const uint64_t*>(p)[1]; L = (int)(lo & 63u) + 1; }
+    }
+    const int lane = threadIdx.x & 31;
+    int maxL = L;
+    for (int d = 16; d; d >>= 1) maxL = max(maxL, __shfl_xor_sync(0xffffffffu, maxL, d));
+    for (int o = 0; o < maxL; o++) {
+        bool v = o < L;
+        uint64_t win = (RECW == 1 || o == 0) ? (hi << (2 * o)) : ((hi << (2 * o)) | (lo >> (64 - 2 * o)));
+        uint64_t key = win >> kshift;
+        uint32_t vm = __ballot_sync(0xffffffffu, v);
+        uint32_t same = __match_any_sync(0xffffffffu, key) & vm;     // repetitive input: aggregate equal keys
+        if (v && lane == __ffs(same) - 1) {
+            unsigned long long c = __popc(same);
+            if (key == kEmpty) atomicAdd(&status->special_count, c);
+            else global_table_add(slots, mask, key, c);
+        }
+    }
+}
+
+template <int RECW>
+__global__ void __launch_bounds__(256) tier2_insert_kernel(PartitionPlan plan, int k, const unsigned long long* __restrict__ fill,
+                                                           const Rec<RECW>* __restrict__ recs, const uint32_t* __restrict__ failed_ids,
+                                                           const Rec<RECW>* __restrict__ spill, kmer_count_pair* __restrict__ slots,
+                                                           uint64_t mask, DevStatus* status) {
+    const int kshift = 64 - 2 * k;
+    const uint32_t n_failed = (uint32_t)status->n_failed;
+    for (uint32_t fi = blockIdx.x; fi < n_failed; fi += gridDim.x) {
+        const uint32_t b = failed_ids[fi];
+        const uint32_t nrec = min((uint32_t)fill[b], plan.cap);
+        const Rec<RECW>* base = recs + (uint64_t)b * plan.cap;
+        for (uint32_t r0 = 0; r0 < nrec; r0 += blockDim.x) {
+            uint32_t r = r0 + threadIdx.x;
+            tier2_add_record<RECW>(base + min(r, nrec - 1), kshift, slots, mask, status, r < nrec);
+        }
+    }
+    const uint64_t n_spill = min((uint64_t)status->n_spill, (uint64_t)plan.spill_cap);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r0 = (uint64_t)blockIdx.x * blockDim.x; r0 < n_spill; r0 += stride) {
+        uint64_t r = r0 + threadIdx.x;
+        tier2_add_record<RECW>(spill + min(r, n_spill - 1), kshift, slots, mask, status, r < n_spill);
+    }
 }
 
 // appends the k == 32 all-ones key, whose occurrences were kept out of the tables
@@ -250,6 +389,7 @@ __global__ void append_special_kernel(kmer_count_pair* out, uint64_t capacity, D
     unsigned long long idx = atomicAdd(&status->n_distinct, 1ull);
     if (idx < capacity) { out[idx].code = kEmpty; out[idx].count = sc; }
     else status->out_overflow = 1;
+    atomicAdd(&status->n_kmers, sc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -262,40 +402,64 @@ PartitionPlan make_partition_plan(uint64_t n_kmers, int k) {
     int m = k - p.w + 1;
     p.m = m > 16 ? 16 : m;
     p.rmax = p.recw == 1 ? (30 - k + 1 > 16 ? 16 : 30 - k + 1) : 16;
-    uint64_t nb = (n_kmers + 2399) / 2400;
+    uint64_t nb = (n_kmers + TARGET_KMERS_PER_BUCKET - 1) / TARGET_KMERS_PER_BUCKET;
     if (nb < 1) nb = 1;
     if (nb > 0x7fffffffull) nb = 0x7fffffffull;
     p.n_buckets = (uint32_t)nb;
-    p.cap = p.recw == 1 ? 1536u : 1024u;
+    p.cap = p.recw == 1 ? 1280u : 896u;
+    uint64_t sc = (uint64_t)p.n_buckets * p.cap / 8;          // spill list: 1/8 of the bucket regions
+    p.spill_cap = sc < 4096 ? 4096 : sc;
     return p;
 }
 
 size_t partition_record_bytes(const PartitionPlan& p) { return (size_t)p.n_buckets * p.cap * (p.recw == 1 ? 8 : 16); }
+size_t partition_spill_bytes(const PartitionPlan& p) { return (size_t)p.spill_cap * (p.recw == 1 ? 8 : 16); }
 
 void launch_count_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPlan& p, unsigned long long* d_fill,
-                            void* d_recs, kmer_count_pair* d_pairs, uint64_t capacity, cudaStream_t st,
-                            void (*mark)(void*, const char*), void* mark_arg) {
+                            void* d_recs, void* d_spill, uint32_t* d_failed_ids, kmer_count_pair* d_pairs, uint64_t capacity,
+                            cudaStream_t st, void (*mark)(void*, const char*), void* mark_arg) {
     cudaMemsetAsync(d_fill, 0, (size_t)p.n_buckets * sizeof(unsigned long long), st);
     uint64_t n_tiles = (a.n_bases + TILE - 1) / TILE;
     uint64_t grid = (uint64_t)di.sm_count * 6;
     if (grid > n_tiles) grid = n_tiles;
     if (n_tiles) {
-        if (p.w == 4) partition_kernel<4, 1><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<1>*)d_recs);
-        else if (p.w == 8) partition_kernel<8, 1><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<1>*)d_recs);
-        else partition_kernel<16, 2><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<2>*)d_recs);
+        if (p.w == 4) partition_kernel<4, 1><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill);
+        else if (p.w == 8) partition_kernel<8, 1><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill);
+        else partition_kernel<16, 2><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<2>*)d_recs, (Rec<2>*)d_spill);
     }
     if (mark) mark(mark_arg, "minimizer_partition");
-    uint64_t lgrid = (uint64_t)di.sm_count * 4;
+    uint64_t lgrid = (uint64_t)di.sm_count * 2;
     if (lgrid > p.n_buckets) lgrid = p.n_buckets;
-    const size_t leaf_smem = LEAF_SLOTS * (sizeof(unsigned long long) + sizeof(uint32_t));
-    cudaFuncSetAttribute(bucket_count_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leaf_smem);
-    cudaFuncSetAttribute(bucket_count_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leaf_smem);
-    if (p.recw == 1)
-        bucket_count_kernel<1><<<(unsigned)lgrid, LEAF_THREADS, leaf_smem, st>>>(p, a.k, d_fill, (const Rec<1>*)d_recs, d_pairs, capacity, a.status);
-    else
-        bucket_count_kernel<2><<<(unsigned)lgrid, LEAF_THREADS, leaf_smem, st>>>(p, a.k, d_fill, (const Rec<2>*)d_recs, d_pairs, capacity, a.status);
-    append_special_kernel<<<1, 1, 0, st>>>(d_pairs, capacity, a.status);
+    const size_t leaf_smem = LEAF_SLOTS * (sizeof(unsigned long long) + sizeof(uint32_t)) + KEYS_CAP * sizeof(unsigned long long);
+    if (p.recw == 1) {
+        cudaFuncSetAttribute(bucket_count_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leaf_smem);
+        cudaFuncSetAttribute(bucket_count_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        bucket_count_kernel<1><<<(unsigned)lgrid, LEAF_THREADS, leaf_smem, st>>>(p, a.k, d_fill, (const Rec<1>*)d_recs, d_pairs,
+                                                                                capacity, d_failed_ids, a.status);
+    } else {
+        cudaFuncSetAttribute(bucket_count_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leaf_smem);
+        cudaFuncSetAttribute(bucket_count_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        bucket_count_kernel<2><<<(unsigned)lgrid, LEAF_THREADS, leaf_smem, st>>>(p, a.k, d_fill, (const Rec<2>*)d_recs, d_pairs,
+                                                                                capacity, d_failed_ids, a.status);
+    }
     if (mark) mark(mark_arg, "bucket_count");
+}
+
+// tier 2 (only when the host saw n_failed or n_spill): slots must be cleared to 0xFF (launch_hash_clear)
+void launch_partition_tier2(const DeviceInfo& di, const PartitionPlan& p, int k, const unsigned long long* d_fill,
+                            const void* d_recs, const void* d_spill, const uint32_t* d_failed_ids, kmer_count_pair* d_slots,
+                            uint64_t n_slots, DevStatus* d_status, cudaStream_t st) {
+    unsigned grid = (unsigned)di.sm_count * 8;
+    if (p.recw == 1)
+        tier2_insert_kernel<1><<<grid, 256, 0, st>>>(p, k, d_fill, (const Rec<1>*)d_recs, d_failed_ids, (const Rec<1>*)d_spill,
+                                                     d_slots, n_slots - 1, d_status);
+    else
+        tier2_insert_kernel<2><<<grid, 256, 0, st>>>(p, k, d_fill, (const Rec<2>*)d_recs, d_failed_ids, (const Rec<2>*)d_spill,
+                                                     d_slots, n_slots - 1, d_status);
+}
+
+void launch_append_special(kmer_count_pair* d_pairs, uint64_t capacity, DevStatus* d_status, cudaStream_t st) {
+    append_special_kernel<<<1, 1, 0, st>>>(d_pairs, capacity, d_status);
 }
 
 }  // namespace kmer

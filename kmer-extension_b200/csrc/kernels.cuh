@@ -46,14 +46,20 @@ struct PartitionPlan {
     int m;                // m-mer length (<= 16)
     int recw;             // 64-bit words per super-k-mer record (1: k <= 26, 2: k >= 27)
     int rmax;             // max k-mers per record
+    uint64_t spill_cap;   // records the spill list holds
 };
 PartitionPlan make_partition_plan(uint64_t n_kmers, int k);
 size_t partition_record_bytes(const PartitionPlan& p);
-// minimizer partition + per-bucket shared-memory counting (14 <= k <= 32).  Anything that does not
-// fit is reported in DevStatus::n_overflow (then the result is incomplete and must be discarded).
+size_t partition_spill_bytes(const PartitionPlan& p);
+// minimizer partition + per-bucket shared-memory counting (14 <= k <= 32).  Afterwards the host reads
+// DevStatus: n_overflow != 0 -> discard and recount (tier 3); n_failed / n_spill != 0 -> run tier 2.
 void launch_count_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPlan& p, unsigned long long* d_fill,
-                            void* d_recs, kmer_count_pair* d_pairs, uint64_t capacity, cudaStream_t st,
-                            void (*mark)(void*, const char*), void* mark_arg);
+                            void* d_recs, void* d_spill, uint32_t* d_failed_ids, kmer_count_pair* d_pairs, uint64_t capacity,
+                            cudaStream_t st, void (*mark)(void*, const char*), void* mark_arg);
+void launch_partition_tier2(const DeviceInfo& di, const PartitionPlan& p, int k, const unsigned long long* d_fill,
+                            const void* d_recs, const void* d_spill, const uint32_t* d_failed_ids, kmer_count_pair* d_slots,
+                            uint64_t n_slots, DevStatus* d_status, cudaStream_t st);
+void launch_append_special(kmer_count_pair* d_pairs, uint64_t capacity, DevStatus* d_status, cudaStream_t st);
 
 // match.cu --------------------------------------------------------------------------------------
 struct MatchConst {          // one compiled constant
