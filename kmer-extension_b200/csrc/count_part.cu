@@ -27,7 +27,7 @@
 namespace kmer {
 
 constexpr int LEAF_SLOTS = 4096;          // shared-memory table slots per bucket
-constexpr int LEAF_THREADS = 512;
+constexpr int LEAF_THREADS = 256;
 constexpr uint32_t TARGET_KMERS_PER_BUCKET = 2000;   // mean load 0.49 of the table; the tail is handled by tier 2
 
 // ---------------------------------------------------------------------------------------------
@@ -111,38 +111,54 @@ __global__ void __launch_bounds__(NT) partition_kernel(ScanArgs a, PartitionPlan
                 starts |= (uint32_t)st << j;
                 prevb = b;
             }
-            // emit one record per run
+            // emit one record per run, four runs at a time: the four slot reservations (64-bit atomicAdd
+            // with return, ~2 us under load) are in flight together instead of back to back
             const uint32_t stops = starts | ~vmask | 0x10000u;   // a run ends before the next start / invalid / chunk end
             while (starts) {
-                const int j = __ffs(starts) - 1;
-                starts &= starts - 1;
-                const int L = __ffs(stops >> (j + 1));             // 1..16 windows
-                const uint32_t b = sbucket[16 * t + j];
-                const int sh = 2 * j;
-                const uint32_t r0 = __funnelshift_l(w[1], w[0], sh), r1 = __funnelshift_l(w[2], w[1], sh),
-                               r2 = __funnelshift_l(w[3], w[2], sh);
-                const int nb = L + k - 1;                          // bases covered
-                unsigned long long old = atomicAdd(&fill[b], ((unsigned long long)L << 32) | 1ull);
-                uint32_t slot = (uint32_t)old;
-                Rec<RECW>* dst = nullptr;
-                if (slot < plan.cap) dst = recs + ((uint64_t)b * plan.cap + slot);
-                else {                                              // region full: spill list (tier 2), else recount
-                    unsigned long long si = atomicAdd(&a.status->n_spill, 1ull);
-                    if (si < plan.spill_cap) dst = spill + si;
-                    else overflow_kmers += L;
+                int jq[4], Lq[4];
+                uint32_t bq[4];
+                unsigned long long oldq[4];
+                bool act[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    act[q] = starts != 0;
+                    jq[q] = act[q] ? __ffs(starts) - 1 : 0;
+                    starts &= starts - 1;                          // 0 stays 0
+                    Lq[q] = __ffs(stops >> (jq[q] + 1));           // 1..16 windows
+                    bq[q] = sbucket[16 * t + jq[q]];
                 }
-                if (dst) {
-                    if (RECW == 1) {
-                        uint64_t v = ((uint64_t)r0 << 32) | r1;
-                        v &= ~0ull << (64 - 2 * nb);               // nb <= 30
-                        reinterpret_cast<uint64_t*>(dst)[0] = v | (uint64_t)(L - 1);
-                    } else {
-                        uint64_t hi = ((uint64_t)r0 << 32) | r1;
-                        uint64_t lo = (uint64_t)r2 << 32;          // bases 32..47 (nb <= 47)
-                        if (nb <= 32) { hi &= ~0ull << (64 - 2 * nb); lo = 0; }
-                        else lo &= ~0ull << (128 - 2 * nb);
-                        ulonglong2 o; o.x = hi; o.y = lo | (uint64_t)(L - 1);
-                        reinterpret_cast<ulonglong2*>(dst)[0] = o;
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    oldq[q] = act[q] ? atomicAdd(&fill[bq[q]], ((unsigned long long)Lq[q] << 32) | 1ull) : 0ull;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (!act[q]) continue;
+                    const int L = Lq[q];
+                    const int sh = 2 * jq[q];
+                    const uint32_t r0 = __funnelshift_l(w[1], w[0], sh), r1 = __funnelshift_l(w[2], w[1], sh),
+                                   r2 = __funnelshift_l(w[3], w[2], sh);
+                    const int nb = L + k - 1;                      // bases covered
+                    const uint32_t slot = (uint32_t)oldq[q];
+                    Rec<RECW>* dst = nullptr;
+                    if (slot < plan.cap) dst = recs + ((uint64_t)bq[q] * plan.cap + slot);
+                    else {                                          // region full: spill list (tier 2), else recount
+                        unsigned long long si = atomicAdd(&a.status->n_spill, 1ull);
+                        if (si < plan.spill_cap) dst = spill + si;
+                        else overflow_kmers += L;
+                    }
+                    if (dst) {
+                        if (RECW == 1) {
+                            uint64_t v = ((uint64_t)r0 << 32) | r1;
+                            v &= ~0ull << (64 - 2 * nb);           // nb <= 30
+                            reinterpret_cast<uint64_t*>(dst)[0] = v | (uint64_t)(L - 1);
+                        } else {
+                            uint64_t hi = ((uint64_t)r0 << 32) | r1;
+                            uint64_t lo = (uint64_t)r2 << 32;      // bases 32..47 (nb <= 47)
+                            if (nb <= 32) { hi &= ~0ull << (64 - 2 * nb); lo = 0; }
+                            else lo &= ~0ull << (128 - 2 * nb);
+                            ulonglong2 o; o.x = hi; o.y = lo | (uint64_t)(L - 1);
+                            reinterpret_cast<ulonglong2*>(dst)[0] = o;
+                        }
                     }
                 }
             }
@@ -155,20 +171,21 @@ __global__ void __launch_bounds__(NT) partition_kernel(ScanArgs a, PartitionPlan
 // ---------------------------------------------------------------------------------------------
 // per-bucket counting
 //
-// One CTA per bucket, three phases separated by __syncthreads:
-//   expand : every record is unpacked into its k-mers, written to a shared key array (a shared
-//            atomicAdd per RECORD reserves the range) -- after this the work is one k-mer per lane,
-//            perfectly balanced, whatever the record lengths were;
-//   insert : each thread inserts 4 independent keys at a time into the 4096-slot table with 64-bit
-//            shared atomicCAS (4 CAS in flight per thread hide the shared-atomic latency); a key that
-//            is already present bumps a 32-bit counter;
-//   emit   : one global atomicAdd per bucket reserves the output range, the table is scanned and the
-//            occupied slots are written as 16-byte (k-mer, count) pairs.
+// One CTA per bucket.  Between the table initialisation and the emission the warps run without any
+// block barrier:
+//   a warp takes 32 records, unpacks them into its private shared key buffer (positions from a warp
+//   prefix sum of the record lengths), and then its lanes walk that buffer with PERSISTENT-LANE
+//   probing: every loop iteration issues exactly one 64-bit shared atomicCAS per lane; a lane whose
+//   key is placed (or found) immediately moves on to its next key, so no lane waits for the longest
+//   probe sequence of the warp.  A lane that claims an empty slot appends the slot index to the
+//   bucket's winner list (one shared atomicAdd per warp iteration, ballot-aggregated).
+//   Emission walks the winner list -- exactly one entry per distinct k-mer -- and writes fully
+//   coalesced 16-byte (k-mer, count) pairs; the table is never scanned.
 // A bucket whose distinct keys do not fit the table, or whose region overflowed in the partition
 // pass, is appended to the failed list and emits nothing (its k-mers are counted by the tier-2 kernel).
 
-constexpr int KEYS_CAP = 4096;            // k-mers expanded per pass
-constexpr int RECS_PER_SMALL_PASS = KEYS_CAP / 16;
+constexpr int LEAF_WARPS = LEAF_THREADS / 32;
+constexpr int WBUF_KEYS = 32 * 16;        // keys of one 32-record chunk (a record holds <= 16 k-mers)
 
 __device__ __forceinline__ uint32_t leaf_hash(uint64_t key) {
     uint32_t h = ((uint32_t)key * 0x9E3779B1u) ^ ((uint32_t)(key >> 32) * 0x85EBCA6Bu);
@@ -186,12 +203,14 @@ __global__ void __launch_bounds__(LEAF_THREADS) bucket_count_kernel(PartitionPla
                                                                     uint32_t* __restrict__ failed_ids, DevStatus* status) {
     extern __shared__ __align__(16) unsigned char leaf_dyn[];
     unsigned long long* tbl = reinterpret_cast<unsigned long long*>(leaf_dyn);                         // [LEAF_SLOTS]
-    unsigned long long* keys = tbl + LEAF_SLOTS;                                                        // [KEYS_CAP]
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(keys + KEYS_CAP);                                       // [LEAF_SLOTS]
-    __shared__ uint32_t s_own[LEAF_THREADS / 32];
+    unsigned long long* wbuf_all = tbl + LEAF_SLOTS;                                                    // [LEAF_WARPS][WBUF_KEYS]
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(wbuf_all + LEAF_WARPS * WBUF_KEYS);                     // [LEAF_SLOTS]
+    unsigned short* winners = reinterpret_cast<unsigned short*>(cnt + LEAF_SLOTS);                      // [LEAF_SLOTS]
     __shared__ unsigned long long s_base;
-    __shared__ uint32_t s_cursor, s_nkeys, s_failed, s_special;
+    __shared__ uint32_t s_nwin, s_failed, s_special;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t lane_lt = (1u << lane) - 1u;
+    unsigned long long* wbuf = wbuf_all + warp * WBUF_KEYS;
     const int kshift = 64 - 2 * k;
     unsigned long long special_total = 0, kmers_total = 0;
 
@@ -207,18 +226,22 @@ __global__ void __launch_bounds__(LEAF_THREADS) bucket_count_kernel(PartitionPla
             }
             continue;
         }
-        for (int i = t; i < LEAF_SLOTS; i += LEAF_THREADS) { tbl[i] = kEmpty; cnt[i] = 0; }
-        if (t == 0) { s_cursor = 0; s_nkeys = 0; s_failed = 0; s_special = 0; }
+        {   // table := empty, counters := 0   (16-byte stores)
+            ulonglong2 e; e.x = kEmpty; e.y = kEmpty;
+            for (int i = t; i < LEAF_SLOTS / 2; i += LEAF_THREADS) reinterpret_cast<ulonglong2*>(tbl)[i] = e;
+            uint4 z = make_uint4(0, 0, 0, 0);
+            for (int i = t; i < LEAF_SLOTS / 4; i += LEAF_THREADS) reinterpret_cast<uint4*>(cnt)[i] = z;
+            if (t == 0) { s_nwin = 0; s_failed = 0; s_special = 0; }
+        }
         __syncthreads();
-        uint32_t own = 0;
         const Rec<RECW>* base = recs + (uint64_t)b * plan.cap;
-        const uint32_t pass_recs = nk <= KEYS_CAP ? nrec_all : RECS_PER_SMALL_PASS;
-        for (uint32_t r0 = 0; r0 < nrec_all; r0 += pass_recs) {
-            const uint32_t r1 = min(nrec_all, r0 + pass_recs);
-            // ---- expand
-            for (uint32_t r = r0 + t; r < r1; r += LEAF_THREADS) {
-                uint64_t hi, lo = 0;
-                int L;
+        uint32_t special = 0;
+        for (uint32_t r0 = warp * 32; r0 < nrec_all; r0 += LEAF_WARPS * 32) {
+            // ---- unpack 32 records into the warp's key buffer
+            const uint32_t r = r0 + lane;
+            uint64_t hi = 0, lo = 0;
+            int L = 0;
+            if (r < nrec_all) {
                 if (RECW == 1) {
                     hi = ld_nc_u64(reinterpret_cast<const uint64_t*>(base) + r);
                     L = (int)(hi & 15u) + 1;
@@ -228,65 +251,66 @@ __global__ void __launch_bounds__(LEAF_THREADS) bucket_count_kernel(PartitionPla
                     lo = ((uint64_t)raw.w << 32) | raw.z;
                     L = (int)(lo & 63u) + 1;
                 }
-                uint32_t pos = atomicAdd(&s_nkeys, (uint32_t)L);
-                for (int o = 0; o < L; o++) {
-                    uint64_t win = (RECW == 1 || o == 0) ? (hi << (2 * o)) : ((hi << (2 * o)) | (lo >> (64 - 2 * o)));
-                    keys[pos + o] = win >> kshift;
-                }
             }
-            __syncthreads();
-            const uint32_t n_keys = s_nkeys;
-            // ---- insert, 4 independent probes per thread
-            for (uint32_t i0 = t; i0 < n_keys; i0 += 4 * LEAF_THREADS) {
-                uint64_t key[4];
-                uint32_t h[4], tries[4];
-                uint32_t pend = 0;
+            int incl = L;
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    uint32_t i = i0 + q * LEAF_THREADS;
-                    key[q] = i < n_keys ? keys[i] : kEmpty;
-                    h[q] = leaf_hash(key[q]);
-                    tries[q] = 0;
-                    if (i < n_keys) {
-                        if (key[q] == kEmpty) atomicAdd(&s_special, 1u);     // k == 32, 't'*32: kept out of the table
-                        else pend |= 1u << q;
-                    }
-                }
-                while (pend) {
-                    unsigned long long old[4];
-#pragma unroll
-                    for (int q = 0; q < 4; q++)
-                        old[q] = (pend >> q) & 1u ? atomicCAS(&tbl[h[q]], kEmpty, key[q]) : 0ull;
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        if (!((pend >> q) & 1u)) continue;
-                        if (old[q] == kEmpty) { own++; pend &= ~(1u << q); }
-                        else if (old[q] == key[q]) { atomicAdd(&cnt[h[q]], 1u); pend &= ~(1u << q); }
+            for (int d = 1; d < 32; d <<= 1) {
+                int n = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += n;
+            }
+            const uint32_t total = (uint32_t)__shfl_sync(0xffffffffu, incl, 31);
+            const int pos = incl - L;
+            for (int o = 0; o < L; o++) {
+                uint64_t win = (RECW == 1 || o == 0) ? (hi << (2 * o)) : ((hi << (2 * o)) | (lo >> (64 - 2 * o)));
+                wbuf[pos + o] = win >> kshift;
+            }
+            __syncwarp();
+            // ---- persistent-lane insertion
+            uint32_t i = lane;
+            bool active = i < total;
+            uint64_t key = active ? wbuf[i] : 0;
+            uint32_t h = leaf_hash(key), tries = 0;
+            while (__any_sync(0xffffffffu, active)) {
+                bool won = false, done = false;
+                if (active) {
+                    if (key == kEmpty) { special++; done = true; }            // k == 32, 't'*32: kept out of the table
+                    else {
+                        unsigned long long old = atomicCAS(&tbl[h], kEmpty, key);
+                        if (old == kEmpty) { won = true; done = true; }
+                        else if (old == key) { atomicAdd(&cnt[h], 1u); done = true; }
                         else {
-                            h[q] = (h[q] + 1) & (LEAF_SLOTS - 1);
-                            if (++tries[q] >= LEAF_SLOTS) { s_failed = 1; pend &= ~(1u << q); }   // table full
+                            h = (h + 1) & (LEAF_SLOTS - 1);
+                            if (++tries >= LEAF_SLOTS) { s_failed = 1; done = true; }   // table full
                         }
                     }
                 }
+                const uint32_t wm = __ballot_sync(0xffffffffu, won);
+                if (wm) {
+                    uint32_t wbase = 0;
+                    if (lane == 0) wbase = atomicAdd(&s_nwin, (uint32_t)__popc(wm));
+                    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                    if (won) winners[wbase + __popc(wm & lane_lt)] = (unsigned short)h;
+                }
+                if (done) {
+                    i += 32;
+                    active = i < total;
+                    if (active) { key = wbuf[i]; h = leaf_hash(key); tries = 0; }
+                }
             }
-            __syncthreads();
-            if (t == 0) s_nkeys = 0;
-            __syncthreads();
+            __syncwarp();   // the buffer is rewritten by the next chunk
         }
-        // ---- emit
-        for (int d = 16; d; d >>= 1) own += __shfl_xor_sync(0xffffffffu, own, d);
-        if (lane == 0) s_own[warp] = own;
+        if (special) atomicAdd(&s_special, special);
         __syncthreads();
+        // ---- emit
         const bool failed = s_failed != 0;
+        const uint32_t nwin = s_nwin;
         if (t == 0) {
             if (failed) {
                 uint32_t idx = (uint32_t)atomicAdd(&status->n_failed, 1ull);
                 failed_ids[idx] = b;
                 atomicAdd(&status->failed_kmers, (unsigned long long)nk);
             } else {
-                uint32_t tot = 0;
-                for (int i = 0; i < LEAF_THREADS / 32; i++) tot += s_own[i];
-                s_base = tot ? atomicAdd(&status->n_distinct, (unsigned long long)tot) : 0ull;
+                s_base = nwin ? atomicAdd(&status->n_distinct, (unsigned long long)nwin) : 0ull;
                 special_total += s_special;
                 kmers_total += nk - s_special;
             }
@@ -294,21 +318,13 @@ __global__ void __launch_bounds__(LEAF_THREADS) bucket_count_kernel(PartitionPla
         __syncthreads();
         if (!failed) {
             const unsigned long long obase = s_base;
-            for (int i = t; i < LEAF_SLOTS; i += LEAF_THREADS) {
-                unsigned long long key = tbl[i];
-                bool occ = key != kEmpty;
-                uint32_t m = __ballot_sync(0xffffffffu, occ);
-                if (!m) continue;
-                uint32_t pos = 0;
-                if (lane == 0) pos = atomicAdd(&s_cursor, (uint32_t)__popc(m));
-                pos = __shfl_sync(0xffffffffu, pos, 0);
-                if (occ) {
-                    uint64_t idx = obase + pos + __popc(m & ((1u << lane) - 1));
-                    if (idx < capacity) {
-                        ulonglong2 o; o.x = key; o.y = 1ull + cnt[i];
-                        reinterpret_cast<ulonglong2*>(out)[idx] = o;
-                    } else status->out_overflow = 1;
-                }
+            for (uint32_t i = t; i < nwin; i += LEAF_THREADS) {
+                const uint32_t slot = winners[i];
+                const uint64_t idx = obase + i;
+                if (idx < capacity) {
+                    ulonglong2 o; o.x = tbl[slot]; o.y = 1ull + cnt[slot];
+                    reinterpret_cast<ulonglong2*>(out)[idx] = o;
+                } else status->out_overflow = 1;
             }
         }
         __syncthreads();   // table is re-initialised for the next bucket
@@ -428,9 +444,10 @@ void launch_count_partition(const DeviceInfo& di, const ScanArgs& a, const Parti
         else partition_kernel<16, 2><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<2>*)d_recs, (Rec<2>*)d_spill);
     }
     if (mark) mark(mark_arg, "minimizer_partition");
+    const size_t leaf_smem = LEAF_SLOTS * (sizeof(unsigned long long) + sizeof(uint32_t) + sizeof(unsigned short)) +
+                             (size_t)LEAF_WARPS * WBUF_KEYS * sizeof(unsigned long long);   // 32 + 16 + 8 + 32 KB
     uint64_t lgrid = (uint64_t)di.sm_count * 2;
     if (lgrid > p.n_buckets) lgrid = p.n_buckets;
-    const size_t leaf_smem = LEAF_SLOTS * (sizeof(unsigned long long) + sizeof(uint32_t)) + KEYS_CAP * sizeof(unsigned long long);
     if (p.recw == 1) {
         cudaFuncSetAttribute(bucket_count_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leaf_smem);
         cudaFuncSetAttribute(bucket_count_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
