@@ -171,21 +171,64 @@ __global__ void __launch_bounds__(NT) partition_kernel(ScanArgs a, PartitionPlan
 // ---------------------------------------------------------------------------------------------
 // per-bucket counting
 //
-// One CTA per bucket.  Between the table initialisation and the emission the warps run without any
-// block barrier:
-//   a warp takes 32 records, unpacks them into its private shared key buffer (positions from a warp
-//   prefix sum of the record lengths), and then its lanes walk that buffer with PERSISTENT-LANE
-//   probing: every loop iteration issues exactly one 64-bit shared atomicCAS per lane; a lane whose
-//   key is placed (or found) immediately moves on to its next key, so no lane waits for the longest
-//   probe sequence of the warp.  A lane that claims an empty slot appends the slot index to the
-//   bucket's winner list (one shared atomicAdd per warp iteration, ballot-aggregated).
-//   Emission walks the winner list -- exactly one entry per distinct k-mer -- and writes fully
-//   coalesced 16-byte (k-mer, count) pairs; the table is never scanned.
+// One CTA per bucket, in passes of at most KEYS_CAP k-mers (one pass for any ordinary bucket):
+//   expand  : every record is unpacked into the shared key array (a shared atomicAdd per RECORD
+//             reserves its range), so the next phase sees one k-mer per array slot whatever the
+//             record lengths were;
+//   probe   : PERSISTENT-LANE probing -- thread t walks keys t, t+256, ...; each loop iteration is
+//             one 64-bit shared atomicCAS, and a thread whose key is placed (or found) moves straight
+//             on to its next key, so nobody waits for the longest probe sequence of a warp.  A thread
+//             that claims an empty slot notes the slot index beside its key (slot_of[i]);
+//   compact : the noted slots are gathered into the bucket's winner list (ballot + one shared
+//             atomicAdd per warp iteration).
+// Emission walks the winner list -- exactly one entry per distinct k-mer -- and writes fully coalesced
+// 16-byte (k-mer, count) pairs after ONE global atomicAdd per bucket; the table is never scanned.
+// Shared memory is addressed through explicit 32-bit shared addresses (ld/st/atom.shared PTX), which
+// keeps the inner loop free of generic-address arithmetic.
 // A bucket whose distinct keys do not fit the table, or whose region overflowed in the partition
 // pass, is appended to the failed list and emits nothing (its k-mers are counted by the tier-2 kernel).
 
-constexpr int LEAF_WARPS = LEAF_THREADS / 32;
-constexpr int WBUF_KEYS = 32 * 16;        // keys of one 32-record chunk (a record holds <= 16 k-mers)
+constexpr int KEYS_CAP = 4096;                       // k-mers expanded per pass
+constexpr int RECS_PER_SMALL_PASS = KEYS_CAP / 16;   // a record holds <= 16 k-mers
+constexpr uint32_t NO_SLOT = 0xffffu;
+
+__device__ __forceinline__ unsigned long long atoms_cas64(uint32_t a, unsigned long long cmp, unsigned long long val) {
+    unsigned long long old;
+    asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(a), "l"(cmp), "l"(val) : "memory");
+    return old;
+}
+__device__ __forceinline__ uint32_t atoms_add32(uint32_t a, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void reds_add32(uint32_t a, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long lds64(uint32_t a) {
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, unsigned long long v) {
+    asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
 
 __device__ __forceinline__ uint32_t leaf_hash(uint64_t key) {
     uint32_t h = ((uint32_t)key * 0x9E3779B1u) ^ ((uint32_t)(key >> 32) * 0x85EBCA6Bu);
@@ -202,17 +245,21 @@ __global__ void __launch_bounds__(LEAF_THREADS) bucket_count_kernel(PartitionPla
                                                                     kmer_count_pair* __restrict__ out, uint64_t capacity,
                                                                     uint32_t* __restrict__ failed_ids, DevStatus* status) {
     extern __shared__ __align__(16) unsigned char leaf_dyn[];
-    unsigned long long* tbl = reinterpret_cast<unsigned long long*>(leaf_dyn);                         // [LEAF_SLOTS]
-    unsigned long long* wbuf_all = tbl + LEAF_SLOTS;                                                    // [LEAF_WARPS][WBUF_KEYS]
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(wbuf_all + LEAF_WARPS * WBUF_KEYS);                     // [LEAF_SLOTS]
-    unsigned short* winners = reinterpret_cast<unsigned short*>(cnt + LEAF_SLOTS);                      // [LEAF_SLOTS]
+    // layout: tbl u64[SLOTS] | keys u64[KEYS_CAP] | cnt u32[SLOTS] | slot_of u16[KEYS_CAP] | winners u16[SLOTS]
+    const uint32_t tbl_s = smem_u32(leaf_dyn);
+    const uint32_t keys_s = tbl_s + LEAF_SLOTS * 8;
+    const uint32_t cnt_s = keys_s + KEYS_CAP * 8;
+    const uint32_t slot_s = cnt_s + LEAF_SLOTS * 4;
+    const uint32_t win_s = slot_s + KEYS_CAP * 2;
     __shared__ unsigned long long s_base;
-    __shared__ uint32_t s_nwin, s_failed, s_special;
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    __shared__ uint32_t s_nkeys, s_nwin, s_failed, s_special;
+    const uint32_t nkeys_s = smem_u32(&s_nkeys), nwin_s = smem_u32(&s_nwin);
+    const int t = threadIdx.x, lane = t & 31;
     const uint32_t lane_lt = (1u << lane) - 1u;
-    unsigned long long* wbuf = wbuf_all + warp * WBUF_KEYS;
     const int kshift = 64 - 2 * k;
     unsigned long long special_total = 0, kmers_total = 0;
+    if (t == 0) { s_nkeys = 0; s_nwin = 0; s_failed = 0; s_special = 0; }
+    __syncthreads();
 
     for (uint32_t b = blockIdx.x; b < plan.n_buckets; b += gridDim.x) {
         const unsigned long long f = fill[b];
@@ -226,22 +273,18 @@ __global__ void __launch_bounds__(LEAF_THREADS) bucket_count_kernel(PartitionPla
             }
             continue;
         }
-        {   // table := empty, counters := 0   (16-byte stores)
-            ulonglong2 e; e.x = kEmpty; e.y = kEmpty;
-            for (int i = t; i < LEAF_SLOTS / 2; i += LEAF_THREADS) reinterpret_cast<ulonglong2*>(tbl)[i] = e;
-            uint4 z = make_uint4(0, 0, 0, 0);
-            for (int i = t; i < LEAF_SLOTS / 4; i += LEAF_THREADS) reinterpret_cast<uint4*>(cnt)[i] = z;
-            if (t == 0) { s_nwin = 0; s_failed = 0; s_special = 0; }
-        }
-        __syncthreads();
+        // table := empty, counters := 0 (16-byte stores); overlaps with the first expansion
+        for (int i = t; i < LEAF_SLOTS / 2; i += LEAF_THREADS) sts128(tbl_s + 16 * i, ~0u, ~0u, ~0u, ~0u);
+        for (int i = t; i < LEAF_SLOTS / 4; i += LEAF_THREADS) sts128(cnt_s + 16 * i, 0u, 0u, 0u, 0u);
         const Rec<RECW>* base = recs + (uint64_t)b * plan.cap;
+        const uint32_t pass_recs = nk <= KEYS_CAP ? nrec_all : RECS_PER_SMALL_PASS;
         uint32_t special = 0;
-        for (uint32_t r0 = warp * 32; r0 < nrec_all; r0 += LEAF_WARPS * 32) {
-            // ---- unpack 32 records into the warp's key buffer
-            const uint32_t r = r0 + lane;
-            uint64_t hi = 0, lo = 0;
-            int L = 0;
-            if (r < nrec_all) {
+        for (uint32_t r0 = 0; r0 < nrec_all; r0 += pass_recs) {
+            const uint32_t r1 = min(nrec_all, r0 + pass_recs);
+            // ---- expand
+            for (uint32_t r = r0 + t; r < r1; r += LEAF_THREADS) {
+                uint64_t hi, lo = 0;
+                int L;
                 if (RECW == 1) {
                     hi = ld_nc_u64(reinterpret_cast<const uint64_t*>(base) + r);
                     L = (int)(hi & 15u) + 1;
@@ -251,57 +294,65 @@ __global__ void __launch_bounds__(LEAF_THREADS) bucket_count_kernel(PartitionPla
                     lo = ((uint64_t)raw.w << 32) | raw.z;
                     L = (int)(lo & 63u) + 1;
                 }
+                uint32_t a = keys_s + 8 * atoms_add32(nkeys_s, (uint32_t)L);
+                for (int o = 0; o < L; o++, a += 8) {
+                    uint64_t win = (RECW == 1 || o == 0) ? (hi << (2 * o)) : ((hi << (2 * o)) | (lo >> (64 - 2 * o)));
+                    sts64(a, win >> kshift);
+                }
             }
-            int incl = L;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                int n = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += n;
-            }
-            const uint32_t total = (uint32_t)__shfl_sync(0xffffffffu, incl, 31);
-            const int pos = incl - L;
-            for (int o = 0; o < L; o++) {
-                uint64_t win = (RECW == 1 || o == 0) ? (hi << (2 * o)) : ((hi << (2 * o)) | (lo >> (64 - 2 * o)));
-                wbuf[pos + o] = win >> kshift;
-            }
-            __syncwarp();
-            // ---- persistent-lane insertion
-            uint32_t i = lane;
-            bool active = i < total;
-            uint64_t key = active ? wbuf[i] : 0;
-            uint32_t h = leaf_hash(key), tries = 0;
-            while (__any_sync(0xffffffffu, active)) {
-                bool won = false, done = false;
-                if (active) {
-                    if (key == kEmpty) { special++; done = true; }            // k == 32, 't'*32: kept out of the table
-                    else {
-                        unsigned long long old = atomicCAS(&tbl[h], kEmpty, key);
-                        if (old == kEmpty) { won = true; done = true; }
-                        else if (old == key) { atomicAdd(&cnt[h], 1u); done = true; }
+            __syncthreads();                                            // (A)
+            const uint32_t n_keys = s_nkeys;
+            // ---- probe: one CAS per iteration, a finished thread moves on to its next key at once
+            {
+                uint32_t i = t;
+                if (i < n_keys) {
+                    uint64_t key = lds64(keys_s + 8 * i);
+                    uint32_t h = leaf_hash(key), tries = 0;
+                    for (;;) {
+                        uint32_t res;                                   // slot claimed, or NO_SLOT when done without claiming
+                        bool done = true;
+                        if (key == kEmpty) { special++; res = NO_SLOT; }   // k == 32, 't'*32: kept out of the table
                         else {
-                            h = (h + 1) & (LEAF_SLOTS - 1);
-                            if (++tries >= LEAF_SLOTS) { s_failed = 1; done = true; }   // table full
+                            unsigned long long old = atoms_cas64(tbl_s + 8 * h, kEmpty, key);
+                            if (old == kEmpty) res = h;
+                            else if (old == key) { reds_add32(cnt_s + 4 * h, 1u); res = NO_SLOT; }
+                            else {
+                                h = (h + 1) & (LEAF_SLOTS - 1);
+                                done = false;
+                                res = NO_SLOT;
+                                if (++tries >= LEAF_SLOTS) { s_failed = 1; done = true; }   // table full
+                            }
+                        }
+                        if (done) {
+                            sts16(slot_s + 2 * i, res);
+                            i += LEAF_THREADS;
+                            if (i >= n_keys) break;
+                            key = lds64(keys_s + 8 * i);
+                            h = leaf_hash(key);
+                            tries = 0;
                         }
                     }
                 }
-                const uint32_t wm = __ballot_sync(0xffffffffu, won);
-                if (wm) {
-                    uint32_t wbase = 0;
-                    if (lane == 0) wbase = atomicAdd(&s_nwin, (uint32_t)__popc(wm));
-                    wbase = __shfl_sync(0xffffffffu, wbase, 0);
-                    if (won) winners[wbase + __popc(wm & lane_lt)] = (unsigned short)h;
-                }
-                if (done) {
-                    i += 32;
-                    active = i < total;
-                    if (active) { key = wbuf[i]; h = leaf_hash(key); tries = 0; }
+            }
+            __syncthreads();                                            // (B)
+            // ---- compact the claimed slots into the winner list
+            for (uint32_t i0 = 0; i0 < n_keys; i0 += LEAF_THREADS) {
+                const uint32_t i = i0 + t;
+                const uint32_t sl = i < n_keys ? lds16(slot_s + 2 * i) : NO_SLOT;
+                const bool w = sl != NO_SLOT;
+                const uint32_t m = __ballot_sync(0xffffffffu, w);
+                if (m) {
+                    uint32_t wb = 0;
+                    if (lane == 0) wb = atoms_add32(nwin_s, (uint32_t)__popc(m));
+                    wb = __shfl_sync(0xffffffffu, wb, 0);
+                    if (w) sts16(win_s + 2 * (wb + __popc(m & lane_lt)), sl);
                 }
             }
-            __syncwarp();   // the buffer is rewritten by the next chunk
+            if (t == 0) s_nkeys = 0;
+            __syncthreads();                                            // (B2)
         }
         if (special) atomicAdd(&s_special, special);
-        __syncthreads();
-        // ---- emit
+        // ---- reserve the output range
         const bool failed = s_failed != 0;
         const uint32_t nwin = s_nwin;
         if (t == 0) {
@@ -311,23 +362,23 @@ __global__ void __launch_bounds__(LEAF_THREADS) bucket_count_kernel(PartitionPla
                 atomicAdd(&status->failed_kmers, (unsigned long long)nk);
             } else {
                 s_base = nwin ? atomicAdd(&status->n_distinct, (unsigned long long)nwin) : 0ull;
-                special_total += s_special;
-                kmers_total += nk - s_special;
             }
         }
-        __syncthreads();
+        __syncthreads();                                                // (C)
         if (!failed) {
             const unsigned long long obase = s_base;
             for (uint32_t i = t; i < nwin; i += LEAF_THREADS) {
-                const uint32_t slot = winners[i];
+                const uint32_t slot = lds16(win_s + 2 * i);
                 const uint64_t idx = obase + i;
                 if (idx < capacity) {
-                    ulonglong2 o; o.x = tbl[slot]; o.y = 1ull + cnt[slot];
+                    ulonglong2 o; o.x = lds64(tbl_s + 8 * slot); o.y = 1ull + lds32(cnt_s + 4 * slot);
                     reinterpret_cast<ulonglong2*>(out)[idx] = o;
                 } else status->out_overflow = 1;
             }
+            if (t == 0) { special_total += s_special; kmers_total += nk - s_special; }
         }
-        __syncthreads();   // table is re-initialised for the next bucket
+        __syncthreads();                                                // (D) table and lists are reused by the next bucket
+        if (t == 0) { s_nwin = 0; s_failed = 0; s_special = 0; }
     }
     if (t == 0) {
         if (special_total) atomicAdd(&status->special_count, special_total);
@@ -444,8 +495,7 @@ void launch_count_partition(const DeviceInfo& di, const ScanArgs& a, const Parti
         else partition_kernel<16, 2><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<2>*)d_recs, (Rec<2>*)d_spill);
     }
     if (mark) mark(mark_arg, "minimizer_partition");
-    const size_t leaf_smem = LEAF_SLOTS * (sizeof(unsigned long long) + sizeof(uint32_t) + sizeof(unsigned short)) +
-                             (size_t)LEAF_WARPS * WBUF_KEYS * sizeof(unsigned long long);   // 32 + 16 + 8 + 32 KB
+    const size_t leaf_smem = LEAF_SLOTS * (8 + 4 + 2) + KEYS_CAP * (8 + 2);   // 32 + 16 + 8 + 32 + 8 = 96 KB
     uint64_t lgrid = (uint64_t)di.sm_count * 2;
     if (lgrid > p.n_buckets) lgrid = p.n_buckets;
     if (p.recw == 1) {
