@@ -54,9 +54,10 @@ template <int W, int RECW>
 __global__ void __launch_bounds__(NT) partition_kernel(ScanArgs a, PartitionPlan plan, unsigned long long* __restrict__ fill,
                                                        Rec<RECW>* __restrict__ recs, Rec<RECW>* __restrict__ spill) {
     __shared__ ScanSmem s;
-    __shared__ uint32_t sbucket[TILE];
+    __shared__ unsigned long long runs[TILE];   // (bucket << 32) | (L << 16) | tile-relative start base
+    __shared__ uint32_t wtot[NT / 32];
     TileScanner sc(a, s);
-    const int t = threadIdx.x;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int k = a.k;
     const int m = plan.m;
     const int rmax = plan.rmax;
@@ -66,8 +67,8 @@ __global__ void __launch_bounds__(NT) partition_kernel(ScanArgs a, PartitionPlan
     while (sc.next()) {
         const uint32_t* bnd = sc.bnd();
         // this thread's 16 windows start at tile-relative bases 16t .. 16t+15 and need bases up to 16t+46
-        uint32_t w[4];
-        w[0] = s.packed[t]; w[1] = s.packed[t + 1]; w[2] = s.packed[t + 2]; w[3] = s.packed[t + 3];
+        uint32_t w[3];
+        w[0] = s.packed[t]; w[1] = s.packed[t + 1]; w[2] = s.packed[t + 2];
         // validity of the 16 windows: no row start in (i, i+k-1], and inside the input
         uint32_t vmask = 0;
         {
@@ -81,6 +82,8 @@ __global__ void __launch_bounds__(NT) partition_kernel(ScanArgs a, PartitionPlan
                 vmask |= (uint32_t)ok << j;
             }
         }
+        uint32_t starts = 0, stops = 0x10000u;
+        uint32_t bk[16];
         if (vmask) {
             // hashed m-mers at bases 0 .. 15+W-1 of this chunk
             uint32_t h[16 + W - 1];
@@ -99,66 +102,91 @@ __global__ void __launch_bounds__(NT) partition_kernel(ScanArgs a, PartitionPlan
                 for (int j = 0; j < 16 + W - 1 - step; j++) h[j] = min(h[j], h[j + step]);
             }
             // bucket of every window; run starts
-            uint32_t starts = 0, prevb = 0;
+            uint32_t prevb = 0;
             int len = 0;
 #pragma unroll
             for (int j = 0; j < 16; j++) {
                 uint32_t b = __umulhi(mix32(h[j]), plan.n_buckets);
-                sbucket[16 * t + j] = b;
+                bk[j] = b;
                 bool v = (vmask >> j) & 1u;
                 bool st = v && (len == 0 || b != prevb || len == rmax);
                 len = st ? 1 : (v ? len + 1 : 0);
                 starts |= (uint32_t)st << j;
                 prevb = b;
             }
-            // emit one record per run, four runs at a time: the four slot reservations (64-bit atomicAdd
-            // with return, ~2 us under load) are in flight together instead of back to back
-            const uint32_t stops = starts | ~vmask | 0x10000u;   // a run ends before the next start / invalid / chunk end
-            while (starts) {
-                int jq[4], Lq[4];
-                uint32_t bq[4];
-                unsigned long long oldq[4];
-                bool act[4];
+            stops = starts | ~vmask | 0x10000u;   // a run ends before the next start / invalid / chunk end
+        }
+        // ---- the tile's runs, compacted into one list (block-wide exclusive scan of the per-thread run counts)
+        const uint32_t nrun = __popc(starts);
+        uint32_t incl = nrun;
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    act[q] = starts != 0;
-                    jq[q] = act[q] ? __ffs(starts) - 1 : 0;
-                    starts &= starts - 1;                          // 0 stays 0
-                    Lq[q] = __ffs(stops >> (jq[q] + 1));           // 1..16 windows
-                    bq[q] = sbucket[16 * t + jq[q]];
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += n;
+        }
+        if (lane == 31) wtot[warp] = incl;
+        __syncthreads();
+        uint32_t rbase = incl - nrun, n_tile_runs = 0;
+#pragma unroll
+        for (int q = 0; q < NT / 32; q++) {
+            uint32_t v = wtot[q];
+            if (q < warp) rbase += v;
+            n_tile_runs += v;
+        }
+        if (vmask) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                if ((starts >> j) & 1u) {
+                    const uint32_t L = __ffs(stops >> (j + 1));            // 1..16 windows
+                    runs[rbase++] = ((unsigned long long)bk[j] << 32) | (L << 16) | (uint32_t)(16 * t + j);
                 }
+            }
+        }
+        __syncthreads();
+        // ---- flat emission: run r of the tile is handled by thread r % NT; four slot reservations
+        //      (64-bit atomicAdd with return) are in flight per thread before any of them is consumed
+        for (uint32_t r0 = 0; r0 < n_tile_runs; r0 += 4 * NT) {
+            unsigned long long d[4], oldq[4];
+            bool act[4];
 #pragma unroll
-                for (int q = 0; q < 4; q++)
-                    oldq[q] = act[q] ? atomicAdd(&fill[bq[q]], ((unsigned long long)Lq[q] << 32) | 1ull) : 0ull;
+            for (int q = 0; q < 4; q++) {
+                const uint32_t r = r0 + q * NT + t;
+                act[q] = r < n_tile_runs;
+                d[q] = act[q] ? runs[r] : 0ull;
+            }
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    if (!act[q]) continue;
-                    const int L = Lq[q];
-                    const int sh = 2 * jq[q];
-                    const uint32_t r0 = __funnelshift_l(w[1], w[0], sh), r1 = __funnelshift_l(w[2], w[1], sh),
-                                   r2 = __funnelshift_l(w[3], w[2], sh);
-                    const int nb = L + k - 1;                      // bases covered
-                    const uint32_t slot = (uint32_t)oldq[q];
-                    Rec<RECW>* dst = nullptr;
-                    if (slot < plan.cap) dst = recs + ((uint64_t)bq[q] * plan.cap + slot);
-                    else {                                          // region full: spill list (tier 2), else recount
-                        unsigned long long si = atomicAdd(&a.status->n_spill, 1ull);
-                        if (si < plan.spill_cap) dst = spill + si;
-                        else overflow_kmers += L;
-                    }
-                    if (dst) {
-                        if (RECW == 1) {
-                            uint64_t v = ((uint64_t)r0 << 32) | r1;
-                            v &= ~0ull << (64 - 2 * nb);           // nb <= 30
-                            reinterpret_cast<uint64_t*>(dst)[0] = v | (uint64_t)(L - 1);
-                        } else {
-                            uint64_t hi = ((uint64_t)r0 << 32) | r1;
-                            uint64_t lo = (uint64_t)r2 << 32;      // bases 32..47 (nb <= 47)
-                            if (nb <= 32) { hi &= ~0ull << (64 - 2 * nb); lo = 0; }
-                            else lo &= ~0ull << (128 - 2 * nb);
-                            ulonglong2 o; o.x = hi; o.y = lo | (uint64_t)(L - 1);
-                            reinterpret_cast<ulonglong2*>(dst)[0] = o;
-                        }
+            for (int q = 0; q < 4; q++)
+                oldq[q] = act[q] ? atomicAdd(&fill[(uint32_t)(d[q] >> 32)], ((d[q] & 0xff0000ull) << 16) | 1ull) : 0ull;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (!act[q]) continue;
+                const uint32_t b = (uint32_t)(d[q] >> 32);
+                const int L = (int)((d[q] >> 16) & 0xffu);
+                const int p = (int)(d[q] & 0xffffu);
+                const int c = p >> 4, sh = 2 * (p & 15);
+                const uint32_t w0 = s.packed[c], w1 = s.packed[c + 1], w2 = s.packed[c + 2], w3 = s.packed[c + 3];
+                const uint32_t r0w = __funnelshift_l(w1, w0, sh), r1w = __funnelshift_l(w2, w1, sh), r2w = __funnelshift_l(w3, w2, sh);
+                const int nb = L + k - 1;                                  // bases covered
+                const uint32_t slot = (uint32_t)oldq[q];
+                Rec<RECW>* dst = nullptr;
+                if (slot < plan.cap) dst = recs + ((uint64_t)b * plan.cap + slot);
+                else {                                                      // region full: spill list (tier 2), else recount
+                    unsigned long long si = atomicAdd(&a.status->n_spill, 1ull);
+                    if (si < plan.spill_cap) dst = spill + si;
+                    else overflow_kmers += L;
+                }
+                if (dst) {
+                    if (RECW == 1) {
+                        uint64_t v = ((uint64_t)r0w << 32) | r1w;
+                        v &= ~0ull << (64 - 2 * nb);                       // nb <= 30
+                        reinterpret_cast<uint64_t*>(dst)[0] = v | (uint64_t)(L - 1);
+                    } else {
+                        uint64_t hi = ((uint64_t)r0w << 32) | r1w;
+                        uint64_t lo = (uint64_t)r2w << 32;                  // bases 32..47 (nb <= 47)
+                        if (nb <= 32) { hi &= ~0ull << (64 - 2 * nb); lo = 0; }
+                        else lo &= ~0ull << (128 - 2 * nb);
+                        ulonglong2 o; o.x = hi; o.y = lo | (uint64_t)(L - 1);
+                        reinterpret_cast<ulonglong2*>(dst)[0] = o;
                     }
                 }
             }
@@ -189,7 +217,6 @@ __global__ void __launch_bounds__(NT) partition_kernel(ScanArgs a, PartitionPlan
 // pass, is appended to the failed list and emits nothing (its k-mers are counted by the tier-2 kernel).
 
 constexpr int KEYS_CAP = 4096;                       // k-mers expanded per pass
-constexpr int RECS_PER_SMALL_PASS = KEYS_CAP / 16;   // a record holds <= 16 k-mers
 constexpr uint32_t NO_SLOT = 0xffffu;
 
 __device__ __forceinline__ unsigned long long atoms_cas64(uint32_t a, unsigned long long cmp, unsigned long long val) {
@@ -235,8 +262,12 @@ __device__ __forceinline__ uint32_t leaf_hash(uint64_t key) {
     h ^= h >> 15;
     h *= 0x2C1B3C6Du;
     h ^= h >> 13;
-    return h & (LEAF_SLOTS - 1);
+    return h;
 }
+
+struct LeafCounters {
+    uint32_t nkeys, nwin, arrived, failed, special, pad;
+};
 
 template <int RECW>
 __global__ void __launch_bounds__(LEAF_THREADS) bucket_count_kernel(PartitionPlan plan, int k,
@@ -245,27 +276,26 @@ __global__ void __launch_bounds__(LEAF_THREADS) bucket_count_kernel(PartitionPla
                                                                     kmer_count_pair* __restrict__ out, uint64_t capacity,
                                                                     uint32_t* __restrict__ failed_ids, DevStatus* status) {
     extern __shared__ __align__(16) unsigned char leaf_dyn[];
-    // layout: tbl u64[SLOTS] | keys u64[KEYS_CAP] | cnt u32[SLOTS] | slot_of u16[KEYS_CAP] | winners u16[SLOTS]
+    // layout: tbl u64[SLOTS] | keys u64[KEYS_CAP] | cnt u32[SLOTS] | slot_of u16[KEYS_CAP]
     const uint32_t tbl_s = smem_u32(leaf_dyn);
     const uint32_t keys_s = tbl_s + LEAF_SLOTS * 8;
     const uint32_t cnt_s = keys_s + KEYS_CAP * 8;
     const uint32_t slot_s = cnt_s + LEAF_SLOTS * 4;
-    const uint32_t win_s = slot_s + KEYS_CAP * 2;
-    __shared__ unsigned long long s_base;
-    __shared__ uint32_t s_nkeys, s_nwin, s_failed, s_special;
-    const uint32_t nkeys_s = smem_u32(&s_nkeys), nwin_s = smem_u32(&s_nwin);
+    __shared__ unsigned long long s_base[2];
+    __shared__ LeafCounters s_ctr[2];          // double-buffered by bucket parity: reset while the other set is live
     const int t = threadIdx.x, lane = t & 31;
     const uint32_t lane_lt = (1u << lane) - 1u;
     const int kshift = 64 - 2 * k;
     unsigned long long special_total = 0, kmers_total = 0;
-    if (t == 0) { s_nkeys = 0; s_nwin = 0; s_failed = 0; s_special = 0; }
+    if (t < 2) { s_ctr[t].nkeys = 0; s_ctr[t].nwin = 0; s_ctr[t].arrived = 0; s_ctr[t].failed = 0; s_ctr[t].special = 0; }
     __syncthreads();
+    uint32_t par = 0;
 
     for (uint32_t b = blockIdx.x; b < plan.n_buckets; b += gridDim.x) {
         const unsigned long long f = fill[b];
         const uint32_t nrec_all = (uint32_t)f, nk = (uint32_t)(f >> 32);
         if (nrec_all == 0) continue;                                    // uniform across the CTA
-        if (nrec_all > plan.cap) {                                      // region overflowed: tier 2 counts it
+        if (nrec_all > plan.cap || nk > KEYS_CAP) {                     // region overflowed / too many k-mers: tier 2
             if (t == 0) {
                 uint32_t idx = (uint32_t)atomicAdd(&status->n_failed, 1ull);
                 failed_ids[idx] = b;
@@ -273,112 +303,119 @@ __global__ void __launch_bounds__(LEAF_THREADS) bucket_count_kernel(PartitionPla
             }
             continue;
         }
-        // table := empty, counters := 0 (16-byte stores); overlaps with the first expansion
+        LeafCounters& C = s_ctr[par];
+        const uint32_t nkeys_s = smem_u32(&C.nkeys), nwin_s = smem_u32(&C.nwin), arrived_s = smem_u32(&C.arrived);
+        // table := empty, counters := 0 (16-byte stores); overlaps with the expansion
         for (int i = t; i < LEAF_SLOTS / 2; i += LEAF_THREADS) sts128(tbl_s + 16 * i, ~0u, ~0u, ~0u, ~0u);
         for (int i = t; i < LEAF_SLOTS / 4; i += LEAF_THREADS) sts128(cnt_s + 16 * i, 0u, 0u, 0u, 0u);
         const Rec<RECW>* base = recs + (uint64_t)b * plan.cap;
-        const uint32_t pass_recs = nk <= KEYS_CAP ? nrec_all : RECS_PER_SMALL_PASS;
-        uint32_t special = 0;
-        for (uint32_t r0 = 0; r0 < nrec_all; r0 += pass_recs) {
-            const uint32_t r1 = min(nrec_all, r0 + pass_recs);
-            // ---- expand
-            for (uint32_t r = r0 + t; r < r1; r += LEAF_THREADS) {
-                uint64_t hi, lo = 0;
-                int L;
-                if (RECW == 1) {
-                    hi = ld_nc_u64(reinterpret_cast<const uint64_t*>(base) + r);
-                    L = (int)(hi & 15u) + 1;
-                } else {
-                    uint4 raw = ld_nc_u128(base + r);
-                    hi = ((uint64_t)raw.y << 32) | raw.x;
-                    lo = ((uint64_t)raw.w << 32) | raw.z;
-                    L = (int)(lo & 63u) + 1;
-                }
-                uint32_t a = keys_s + 8 * atoms_add32(nkeys_s, (uint32_t)L);
-                for (int o = 0; o < L; o++, a += 8) {
-                    uint64_t win = (RECW == 1 || o == 0) ? (hi << (2 * o)) : ((hi << (2 * o)) | (lo >> (64 - 2 * o)));
-                    sts64(a, win >> kshift);
-                }
+        // ---- expand
+        for (uint32_t r = t; r < nrec_all; r += LEAF_THREADS) {
+            uint64_t hi, lo = 0;
+            int L;
+            if (RECW == 1) {
+                hi = ld_nc_u64(reinterpret_cast<const uint64_t*>(base) + r);
+                L = (int)(hi & 15u) + 1;
+            } else {
+                uint4 raw = ld_nc_u128(base + r);
+                hi = ((uint64_t)raw.y << 32) | raw.x;
+                lo = ((uint64_t)raw.w << 32) | raw.z;
+                L = (int)(lo & 63u) + 1;
             }
-            __syncthreads();                                            // (A)
-            const uint32_t n_keys = s_nkeys;
-            // ---- probe: one CAS per iteration, a finished thread moves on to its next key at once
-            {
-                uint32_t i = t;
-                if (i < n_keys) {
-                    uint64_t key = lds64(keys_s + 8 * i);
-                    uint32_t h = leaf_hash(key), tries = 0;
-                    for (;;) {
-                        uint32_t res;                                   // slot claimed, or NO_SLOT when done without claiming
-                        bool done = true;
-                        if (key == kEmpty) { special++; res = NO_SLOT; }   // k == 32, 't'*32: kept out of the table
+            uint32_t a = keys_s + 8 * atoms_add32(nkeys_s, (uint32_t)L);
+            for (int o = 0; o < L; o++, a += 8) {
+                uint64_t win = (RECW == 1 || o == 0) ? (hi << (2 * o)) : ((hi << (2 * o)) | (lo >> (64 - 2 * o)));
+                sts64(a, win >> kshift);
+            }
+        }
+        __syncthreads();                                                // (A)
+        if (t == 0) {                                                   // the other counter set is idle now: reset it
+            LeafCounters& N = s_ctr[par ^ 1];
+            N.nkeys = 0; N.nwin = 0; N.arrived = 0; N.failed = 0; N.special = 0;
+        }
+        const uint32_t n_keys = C.nkeys;
+        // ---- probe: one CAS per iteration, a finished thread moves on to its next key at once
+        uint32_t own = 0, special = 0;
+        {
+            uint32_t i = t;
+            if (i < n_keys) {
+                uint64_t key = lds64(keys_s + 8 * i);
+                uint32_t hf = leaf_hash(key);
+                uint32_t h = hf & (LEAF_SLOTS - 1), step = ((hf >> 12) | 1u) & (LEAF_SLOTS - 1), tries = 0;
+                for (;;) {
+                    uint32_t res = NO_SLOT;                             // slot claimed, or NO_SLOT
+                    bool done = true;
+                    if (key == kEmpty) special++;                       // k == 32, 't'*32: kept out of the table
+                    else {
+                        unsigned long long old = atoms_cas64(tbl_s + 8 * h, kEmpty, key);
+                        if (old == kEmpty) { res = h; own++; }
+                        else if (old == key) reds_add32(cnt_s + 4 * h, 1u);
                         else {
-                            unsigned long long old = atoms_cas64(tbl_s + 8 * h, kEmpty, key);
-                            if (old == kEmpty) res = h;
-                            else if (old == key) { reds_add32(cnt_s + 4 * h, 1u); res = NO_SLOT; }
-                            else {
-                                h = (h + 1) & (LEAF_SLOTS - 1);
-                                done = false;
-                                res = NO_SLOT;
-                                if (++tries >= LEAF_SLOTS) { s_failed = 1; done = true; }   // table full
-                            }
+                            h = (h + step) & (LEAF_SLOTS - 1);          // double hashing: odd step visits every slot
+                            done = false;
+                            if (++tries >= LEAF_SLOTS) { C.failed = 1; done = true; }   // table full
                         }
-                        if (done) {
-                            sts16(slot_s + 2 * i, res);
-                            i += LEAF_THREADS;
-                            if (i >= n_keys) break;
-                            key = lds64(keys_s + 8 * i);
-                            h = leaf_hash(key);
-                            tries = 0;
-                        }
+                    }
+                    if (done) {
+                        sts16(slot_s + 2 * i, res);
+                        i += LEAF_THREADS;
+                        if (i >= n_keys) break;
+                        key = lds64(keys_s + 8 * i);
+                        hf = leaf_hash(key);
+                        h = hf & (LEAF_SLOTS - 1);
+                        step = ((hf >> 12) | 1u) & (LEAF_SLOTS - 1);
+                        tries = 0;
                     }
                 }
             }
-            __syncthreads();                                            // (B)
-            // ---- compact the claimed slots into the winner list
-            for (uint32_t i0 = 0; i0 < n_keys; i0 += LEAF_THREADS) {
-                const uint32_t i = i0 + t;
-                const uint32_t sl = i < n_keys ? lds16(slot_s + 2 * i) : NO_SLOT;
-                const bool w = sl != NO_SLOT;
-                const uint32_t m = __ballot_sync(0xffffffffu, w);
-                if (m) {
-                    uint32_t wb = 0;
-                    if (lane == 0) wb = atoms_add32(nwin_s, (uint32_t)__popc(m));
-                    wb = __shfl_sync(0xffffffffu, wb, 0);
-                    if (w) sts16(win_s + 2 * (wb + __popc(m & lane_lt)), sl);
-                }
-            }
-            if (t == 0) s_nkeys = 0;
-            __syncthreads();                                            // (B2)
         }
-        if (special) atomicAdd(&s_special, special);
-        // ---- reserve the output range
-        const bool failed = s_failed != 0;
-        const uint32_t nwin = s_nwin;
-        if (t == 0) {
-            if (failed) {
+        // ---- per-warp offsets; the last warp to arrive reserves the bucket's output range
+        __syncwarp();
+        for (int d = 16; d; d >>= 1) {
+            own += __shfl_xor_sync(0xffffffffu, own, d);
+            special += __shfl_xor_sync(0xffffffffu, special, d);
+        }
+        uint32_t woff = 0;
+        if (lane == 0) {
+            if (special) atomicAdd(&C.special, special);
+            woff = atoms_add32(nwin_s, own);
+            __threadfence_block();
+            if (atoms_add32(arrived_s, 1u) == LEAF_THREADS / 32 - 1) {
+                const uint32_t total = lds32(nwin_s);
+                const bool failed = *reinterpret_cast<volatile uint32_t*>(&C.failed) != 0;
+                s_base[par] = (!failed && total) ? atomicAdd(&status->n_distinct, (unsigned long long)total) : 0ull;
+            }
+        }
+        woff = __shfl_sync(0xffffffffu, woff, 0);
+        __syncthreads();                                                // (B)
+        const bool failed = C.failed != 0;
+        if (failed) {
+            if (t == 0) {
                 uint32_t idx = (uint32_t)atomicAdd(&status->n_failed, 1ull);
                 failed_ids[idx] = b;
                 atomicAdd(&status->failed_kmers, (unsigned long long)nk);
-            } else {
-                s_base = nwin ? atomicAdd(&status->n_distinct, (unsigned long long)nwin) : 0ull;
             }
-        }
-        __syncthreads();                                                // (C)
-        if (!failed) {
-            const unsigned long long obase = s_base;
-            for (uint32_t i = t; i < nwin; i += LEAF_THREADS) {
-                const uint32_t slot = lds16(win_s + 2 * i);
-                const uint64_t idx = obase + i;
-                if (idx < capacity) {
-                    ulonglong2 o; o.x = lds64(tbl_s + 8 * slot); o.y = 1ull + lds32(cnt_s + 4 * slot);
-                    reinterpret_cast<ulonglong2*>(out)[idx] = o;
-                } else status->out_overflow = 1;
+        } else {
+            // ---- emit: every warp writes the k-mers its own lanes claimed
+            uint64_t obase = s_base[par] + woff;
+            for (uint32_t i0 = 0; i0 < n_keys; i0 += LEAF_THREADS) {
+                const uint32_t i = i0 + t;
+                const uint32_t sl = i < n_keys ? lds16(slot_s + 2 * i) : NO_SLOT;
+                const bool wv = sl != NO_SLOT;
+                const uint32_t mk = __ballot_sync(0xffffffffu, wv);
+                if (wv) {
+                    const uint64_t idx = obase + __popc(mk & lane_lt);
+                    if (idx < capacity) {
+                        ulonglong2 o; o.x = lds64(tbl_s + 8 * sl); o.y = 1ull + lds32(cnt_s + 4 * sl);
+                        reinterpret_cast<ulonglong2*>(out)[idx] = o;
+                    } else status->out_overflow = 1;
+                }
+                obase += __popc(mk);
             }
-            if (t == 0) { special_total += s_special; kmers_total += nk - s_special; }
+            if (t == 0) { special_total += C.special; kmers_total += nk - C.special; }
         }
-        __syncthreads();                                                // (D) table and lists are reused by the next bucket
-        if (t == 0) { s_nwin = 0; s_failed = 0; s_special = 0; }
+        __syncthreads();                                                // (D) table and key array are reused by the next bucket
+        par ^= 1;
     }
     if (t == 0) {
         if (special_total) atomicAdd(&status->special_count, special_total);
@@ -495,7 +532,7 @@ void launch_count_partition(const DeviceInfo& di, const ScanArgs& a, const Parti
         else partition_kernel<16, 2><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<2>*)d_recs, (Rec<2>*)d_spill);
     }
     if (mark) mark(mark_arg, "minimizer_partition");
-    const size_t leaf_smem = LEAF_SLOTS * (8 + 4 + 2) + KEYS_CAP * (8 + 2);   // 32 + 16 + 8 + 32 + 8 = 96 KB
+    const size_t leaf_smem = LEAF_SLOTS * (8 + 4) + KEYS_CAP * (8 + 2);   // 32 + 16 + 32 + 8 = 88 KB
     uint64_t lgrid = (uint64_t)di.sm_count * 2;
     if (lgrid > p.n_buckets) lgrid = p.n_buckets;
     if (p.recw == 1) {
