@@ -186,14 +186,12 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    if world > 1:
-        raise SystemExit("multi-GPU counting is not wired into bench.py yet")
-
     eng = api.KmerCuda(local_rank)
     n_rows = args.reads
     flat, off = datagen.synth_reads(2 + rank, n_rows, READ_LEN)
     n_bases = int(off[-1])
-    n_kmers = n_rows * (READ_LEN - K + 1)
+    n_kmers = n_rows * (READ_LEN - K + 1)          # per GPU (weak scaling: every rank brings its own 1 GB)
+    total_kmers = n_kmers * world
 
     # ---------------------------------------------------------------- resident-data arm
     h_seq = torch.empty(n_bases + 64, dtype=torch.uint8).pin_memory()
@@ -203,48 +201,75 @@ def main():
     d_seq = h_seq.cuda(non_blocking=True)
     d_off = h_off.cuda(non_blocking=True)
     cap = eng.max_kmers(n_bases, n_rows, K)
+    if world > 1:
+        cap = int(cap * 1.1) + (1 << 20)              # an owner's share of the groups fluctuates a little
     d_pairs = torch.empty((cap, 2), dtype=torch.int64, device="cuda")
     stream = torch.cuda.current_stream()
     torch.cuda.synchronize()
+    sharder = None
+    if world > 1:
+        from kmer_extension_b200 import sharded
+        sharder = sharded.ShardedCounter(eng)
 
-    launches0 = eng.launches
+    class _R:
+        pass
 
     def step():
-        eng.dev_count(d_seq, n_bases, d_off, n_rows, K, d_pairs, algo=args.algo, stream=stream)
-        return eng.dev_finish(stream)
+        if sharder is None:
+            eng.dev_count(d_seq, n_bases, d_off, n_rows, K, d_pairs, algo=args.algo, stream=stream)
+            return eng.dev_finish(stream)
+        nd, nk, info = sharder.count(d_seq, n_bases, d_off, n_rows, K, d_pairs, total_kmers=total_kmers)
+        r = _R()
+        r.n_kmers, r.n_distinct, r.n_overflow, r.n_tier2 = nk, nd, 0, info["tier2_kmers"]
+        return r
 
     for _ in range(args.warmup):
         res = step()
-    assert res.n_kmers == n_kmers, (res.n_kmers, n_kmers)
+    if world == 1:
+        assert res.n_kmers == n_kmers, (res.n_kmers, n_kmers)
     n_distinct = int(res.n_distinct)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    torch.cuda.synchronize()
+    barrier()
     l0 = eng.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(args.steps):
         res = step()
     ev1.record(stream)
-    torch.cuda.synchronize()
+    barrier()
     launches = eng.launches - l0
     clocks = sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
+    if world > 1:                                      # device time, max over ranks
+        tmax = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms_total = float(tmax.item())
+        dsum = torch.tensor([n_distinct], dtype=torch.int64, device="cuda")
+        dist.all_reduce(dsum)
+        n_distinct_total = int(dsum.item())
+    else:
+        n_distinct_total = n_distinct
     ms_step = ms_total / args.steps
-    value = n_kmers * args.steps / (ms_total * 1e-3)
+    value = total_kmers * args.steps / (ms_total * 1e-3)
 
     # ---------------------------------------------------------------- per-kernel phases (separate pass, not the timed one)
     eng.set_profiling(True)
     phase_acc = {}
     for _ in range(max(2, min(args.steps, 5))):
         step()
-        for name, ms in eng.phases():
+        for name, ms in (sharder.last_phases if sharder is not None else eng.phases()):
             phase_acc.setdefault(name, []).append(ms)
     eng.set_profiling(False)
     phases = {n: float(np.mean(v)) for n, v in phase_acc.items()}
     peak, peak_src = measured_peaks()
-    b_alg_step = n_bases + 16 * n_distinct
+    b_alg_step = n_bases * world + 16 * n_distinct_total
     # algorithmic bytes of each kernel (DESIGN.md "Kernels"): what it must read + write once
     alg_bytes = {
         "count_hash_insert": n_bases + 16 * n_distinct,          # read every base once, create every group once
@@ -264,17 +289,18 @@ def main():
                     "traffic": None, "alg_bytes_per_launch": ab, "kernel_ms": phases[dom],
                     "share_of_step": phases[dom] / max(sum(phases.values()), 1e-9), "peak_source": peak_src}
     ach_step = b_alg_step / (ms_step * 1e-3) / 1e9
-    roofline_step = {"bound": "hbm", "achieved": ach_step, "peak": peak, "unit": "GB/s", "frac": ach_step / peak,
-                     "alg_bytes_per_step": b_alg_step, "formula": "N_bases + 16*D (SURVEY 8d)", "frac_of_8000_nominal": ach_step / 8000.0}
+    roofline_step = {"bound": "hbm", "achieved": ach_step, "peak": peak * world, "unit": "GB/s", "frac": ach_step / (peak * world),
+                     "alg_bytes_per_step": b_alg_step, "formula": "N_bases + 16*D over all GPUs (SURVEY 8d); peak = n_gpus x measured HBM copy",
+                     "frac_of_8000_nominal": ach_step / (8000.0 * world)}
 
     # ---------------------------------------------------------------- e2e arm: host buffers through the C ABI
     e2e = None
     if not args.no_e2e:
         import psutil
         need = 16 * n_distinct + (1 << 30)
-        if psutil.virtual_memory().available < 2 * need:
+        if psutil.virtual_memory().available < 2 * need * max(world, 1):
             e2e = {"value": None, "unit": UNIT, "skipped": "host memory too small for a pinned result buffer"}
-        else:
+        elif world == 1:
             pairs, d, nk = C.c_void_p(), C.c_uint64(), C.c_uint64()
             seq_ptr, off_ptr = h_seq.data_ptr(), h_off.data_ptr()
 
@@ -298,6 +324,34 @@ def main():
             e2e = {"value": n_kmers * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": n_bases + 8 * (n_rows + 1),
                    "d2h_bytes_per_step": 16 * n_distinct, "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
                    "api": "kmer_cuda_submit_count (pinned host input -> pinned host (k-mer,count) table)"}
+        else:
+            # sharded e2e: every rank copies its rows from pinned host memory, counts with the all-to-all, and reads
+            # its share of the (k-mer,count) table back into pinned host memory
+            h_pairs = torch.empty((cap, 2), dtype=torch.int64).pin_memory()
+
+            def e2e_step():
+                d_seq.copy_(h_seq, non_blocking=True)
+                d_off.copy_(h_off, non_blocking=True)
+                nd, nk_, _ = sharder.count(d_seq, n_bases, d_off, n_rows, K, d_pairs, total_kmers=total_kmers)
+                h_pairs[:nd].copy_(d_pairs[:nd], non_blocking=True)
+                torch.cuda.synchronize()
+                return nd, int(h_pairs[0, 1])
+
+            e2e_steps = max(1, min(args.steps, 3))
+            for _ in range(2):
+                e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                nd, _ = e2e_step()
+            barrier()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            dt = float(dt.item())
+            e2e = {"value": total_kmers * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": (n_bases + 8 * (n_rows + 1)) * world,
+                   "d2h_bytes_per_step": 16 * n_distinct_total, "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
+                   "api": "ShardedCounter.count per rank: pinned host rows -> HBM, partition + NCCL all-to-all + bucket count, "
+                          "(k-mer,count) shares -> pinned host"}
 
     # ---------------------------------------------------------------- CPU baseline beside it (rank 0, bounded sample)
     cpu = None
@@ -315,7 +369,8 @@ def main():
                                    f"({n_rows} reads x {READ_LEN}, seed 2+rank)", "k": K, "read_len": READ_LEN,
                        "reads_per_gpu": n_rows, "algo": args.algo, "n_kmers_per_step": n_kmers * world,
                        "n_distinct_rank0": n_distinct, "recounted_kmers": int(res.n_overflow),
-                       "tier2_kmers": int(res.n_tier2), "l2": "inputs and tables larger than L2 (no flush needed)",
+                       "tier2_kmers": int(res.n_tier2), "n_distinct_total": n_distinct_total,
+                       "exchange_bytes_per_gpu_per_step": (sharder.last_exchange_bytes if sharder is not None else 0), "l2": "inputs and tables larger than L2 (no flush needed)",
                        "bases_per_sec": n_bases * world * args.steps / (ms_total * 1e-3)},
             "roofline": roofline, "roofline_step": roofline_step, "phases_ms": phases, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks}

@@ -183,6 +183,49 @@ int kmer_cuda_dev_decode(kmer_cuda_ctx *ctx, const uint64_t *d_codes, uint64_t n
 
 int kmer_cuda_dev_finish(kmer_cuda_ctx *ctx, void *stream, kmer_dev_result *result);
 
+/* ---------------------------------------------------------------- sharded counting (one process per GPU)
+ * Counting shards by row: every GPU partitions ITS rows' k-mers into the same global set of
+ * minimizer buckets, bucket b is owned by GPU b / buckets_per_rank, one all-to-all moves every
+ * bucket segment to its owner, and each owner counts its buckets.  Identical k-mers share a
+ * minimizer, hence a bucket, hence an owner: the per-GPU results are disjoint and the GROUP BY
+ * result is their concatenation.  The library does no communication itself; the caller runs the
+ * exchange (NCCL all-to-all with equal splits in bench.py / sharded.py; ncclSend/ncclRecv from C):
+ *
+ *   kmer_cuda_shard_plan()            same arguments on every rank -> same plan
+ *   kmer_cuda_dev_shard_partition()   rows -> send_recs [n_buckets][cap] records, send_fill [n_buckets]
+ *   all-to-all(send_recs, recs_bytes_per_peer)  and  all-to-all(send_fill, fill_bytes_per_peer)
+ *   kmer_cuda_dev_shard_count()       recv_recs [n_ranks][buckets_per_rank][cap], recv_fill [n_ranks][buckets_per_rank]
+ *                                     -> this rank's (k-mer, count) pairs
+ * 14 <= k <= 32.  (Smaller k: kmer_cuda_dev_dense_table + all-reduce + kmer_cuda_dev_dense_emit.) */
+typedef struct kmer_shard_plan
+{
+	uint32_t n_ranks;
+	uint32_t n_buckets;		   /* global; = n_ranks * buckets_per_rank */
+	uint32_t buckets_per_rank;
+	uint32_t cap;			   /* records per (bucket, source GPU) segment */
+	int32_t k;
+	int32_t rec_bytes;		   /* 8 (k <= 26) or 16 */
+	uint64_t recs_bytes_per_peer; /* buckets_per_rank * cap * rec_bytes */
+	uint64_t fill_bytes_per_peer; /* buckets_per_rank * 8 */
+	int32_t w, m, recw, rmax;  /* minimizer window / m-mer length / record words / max k-mers per record */
+} kmer_shard_plan;
+
+int kmer_cuda_shard_plan(uint64_t total_kmers_all_ranks, int k, uint32_t n_ranks, kmer_shard_plan *plan);
+/* Fails with KMER_ERR_CAPACITY (reported by kmer_cuda_dev_finish) if a segment overflows: input too
+ * repetitive for this path; nothing may be used then. */
+int kmer_cuda_dev_shard_partition(kmer_cuda_ctx *ctx, const char *d_seq, uint64_t n_bases, const uint64_t *d_row_off,
+								  uint64_t n_rows, const kmer_shard_plan *plan, void *d_send_recs,
+								  uint64_t *d_send_fill, void *stream);
+int kmer_cuda_dev_shard_count(kmer_cuda_ctx *ctx, const kmer_shard_plan *plan, const void *d_recv_recs,
+							  const uint64_t *d_recv_fill, kmer_count_pair *d_pairs, uint64_t pairs_capacity,
+							  void *stream);
+/* k <= 13: the dense 4^k table of uint64 counters of this rank's rows (to be summed across ranks),
+ * and the emission of the bins owned by `rank` (bin % n_ranks == rank) of a summed table. */
+int kmer_cuda_dev_dense_table(kmer_cuda_ctx *ctx, const char *d_seq, uint64_t n_bases, const uint64_t *d_row_off,
+							  uint64_t n_rows, int k, uint64_t *d_table, void *stream);
+int kmer_cuda_dev_dense_emit(kmer_cuda_ctx *ctx, const uint64_t *d_table, int k, uint32_t rank, uint32_t n_ranks,
+							 kmer_count_pair *d_pairs, uint64_t pairs_capacity, void *stream);
+
 /* Upper bound of the number of k-mers (= groups) a batch can produce: n_bases - n_rows*(k-1). */
 uint64_t kmer_cuda_max_kmers(uint64_t n_bases, uint64_t n_rows, int k);
 

@@ -38,6 +38,8 @@ ABI_SYMBOLS = [
     "kmer_cuda_submit_extract", "kmer_cuda_submit_count", "kmer_cuda_submit_match", "kmer_cuda_submit_decode",
     "kmer_cuda_submit_encode", "kmer_cuda_dev_extract", "kmer_cuda_dev_count", "kmer_cuda_dev_match",
     "kmer_cuda_dev_decode", "kmer_cuda_dev_finish", "kmer_cuda_set_profiling", "kmer_cuda_get_phases",
+    "kmer_cuda_shard_plan", "kmer_cuda_dev_shard_partition", "kmer_cuda_dev_shard_count", "kmer_cuda_dev_dense_table",
+    "kmer_cuda_dev_dense_emit",
 ]
 
 
@@ -48,6 +50,12 @@ class KmerCudaError(C.Structure):
 
 class KmerDevResult(C.Structure):
     _fields_ = [("n_kmers", C.c_uint64), ("n_distinct", C.c_uint64), ("n_overflow", C.c_uint64), ("n_tier2", C.c_uint64)]
+
+
+class KmerShardPlan(C.Structure):
+    _fields_ = [("n_ranks", C.c_uint32), ("n_buckets", C.c_uint32), ("buckets_per_rank", C.c_uint32), ("cap", C.c_uint32),
+                ("k", C.c_int32), ("rec_bytes", C.c_int32), ("recs_bytes_per_peer", C.c_uint64),
+                ("fill_bytes_per_peer", C.c_uint64), ("w", C.c_int32), ("m", C.c_int32), ("recw", C.c_int32), ("rmax", C.c_int32)]
 
 
 class KmerSqlError(Exception):
@@ -90,6 +98,11 @@ def load_library(path: Path = LIB_PATH) -> C.CDLL:
     L.kmer_cuda_set_profiling.argtypes = [vp, i32]
     L.kmer_cuda_set_profiling.restype = None
     L.kmer_cuda_get_phases.argtypes = [vp, C.POINTER(cp), C.POINTER(C.c_float), i32]
+    L.kmer_cuda_shard_plan.argtypes = [u64, i32, C.c_uint32, C.POINTER(KmerShardPlan)]
+    L.kmer_cuda_dev_shard_partition.argtypes = [vp, vp, u64, vp, u64, C.POINTER(KmerShardPlan), vp, vp, vp]
+    L.kmer_cuda_dev_shard_count.argtypes = [vp, C.POINTER(KmerShardPlan), vp, vp, vp, u64, vp]
+    L.kmer_cuda_dev_dense_table.argtypes = [vp, vp, u64, vp, u64, i32, vp, vp]
+    L.kmer_cuda_dev_dense_emit.argtypes = [vp, vp, i32, C.c_uint32, C.c_uint32, vp, u64, vp]
     return L
 
 
@@ -275,6 +288,30 @@ class KmerCuda:
     def dev_decode(self, d_codes, n: int, k: int, with_header: bool, d_text, stream=None):
         self._check(self.lib.kmer_cuda_dev_decode(self.ctx, d_codes.data_ptr(), n, k, int(with_header), d_text.data_ptr(),
                                                   self._stream_ptr(stream)))
+
+    # ------------------------------------------------------------------ sharded counting (the caller runs the exchange)
+    def shard_plan(self, total_kmers: int, k: int, n_ranks: int) -> KmerShardPlan:
+        plan = KmerShardPlan()
+        if self.lib.kmer_cuda_shard_plan(total_kmers, k, n_ranks, C.byref(plan)):
+            raise ValueError("kmer_cuda_shard_plan: needs 14 <= k <= 32 and n_ranks >= 1")
+        return plan
+
+    def dev_shard_partition(self, d_seq, n_bases: int, d_off, n_rows: int, plan: KmerShardPlan, d_send_recs, d_send_fill, stream=None):
+        self._check(self.lib.kmer_cuda_dev_shard_partition(self.ctx, d_seq.data_ptr(), n_bases, d_off.data_ptr(), n_rows,
+                                                           C.byref(plan), d_send_recs.data_ptr(), d_send_fill.data_ptr(),
+                                                           self._stream_ptr(stream)))
+
+    def dev_shard_count(self, plan: KmerShardPlan, d_recv_recs, d_recv_fill, d_pairs, stream=None):
+        self._check(self.lib.kmer_cuda_dev_shard_count(self.ctx, C.byref(plan), d_recv_recs.data_ptr(), d_recv_fill.data_ptr(),
+                                                       d_pairs.data_ptr(), d_pairs.numel() // 2, self._stream_ptr(stream)))
+
+    def dev_dense_table(self, d_seq, n_bases: int, d_off, n_rows: int, k: int, d_table, stream=None):
+        self._check(self.lib.kmer_cuda_dev_dense_table(self.ctx, d_seq.data_ptr(), n_bases, d_off.data_ptr(), n_rows, k,
+                                                       d_table.data_ptr(), self._stream_ptr(stream)))
+
+    def dev_dense_emit(self, d_table, k: int, rank: int, n_ranks: int, d_pairs, stream=None):
+        self._check(self.lib.kmer_cuda_dev_dense_emit(self.ctx, d_table.data_ptr(), k, rank, n_ranks, d_pairs.data_ptr(),
+                                                      d_pairs.numel() // 2, self._stream_ptr(stream)))
 
     def dev_finish(self, stream=None) -> KmerDevResult:
         r = KmerDevResult()

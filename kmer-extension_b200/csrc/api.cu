@@ -2,6 +2,7 @@
 // host-buffer batch submit and the device-resident entry points.  No CPU compute path exists here:
 // every operation is a sequence of CUDA kernels; without a device the calls fail.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -26,7 +27,7 @@ struct PinnedBuf {
     bool in_use;
 };
 
-enum PendingOp { OP_NONE = 0, OP_EXTRACT, OP_COUNT, OP_MATCH, OP_DECODE, OP_ENCODE };
+enum PendingOp { OP_NONE = 0, OP_EXTRACT, OP_COUNT, OP_MATCH, OP_DECODE, OP_ENCODE, OP_SHARD_PART, OP_SHARD_COUNT, OP_DENSE_TABLE };
 
 }  // namespace
 
@@ -513,7 +514,7 @@ extern "C" int kmer_cuda_dev_count(kmer_cuda_ctx* c, const char* d_seq, uint64_t
                 rc = ws(c, c->table, n_slots * sizeof(kmer_count_pair));
                 if (rc) return rc;
                 launch_hash_clear((kmer_count_pair*)c->table.p, n_slots, st);
-                launch_partition_tier2(c->di, plan, k, (const unsigned long long*)c->fill.p, c->recs.p, c->spill.p,
+                launch_partition_tier2(c->di, plan, k, 1, (const unsigned long long*)c->fill.p, c->recs.p, c->spill.p,
                                        (const uint32_t*)c->failed.p, (kmer_count_pair*)c->table.p, n_slots, c->d_status, st);
                 mark(c, st, "tier2_insert");
                 // compaction appends the table and the k==32 special key and adds both to n_kmers
@@ -665,9 +666,176 @@ extern "C" int kmer_cuda_dev_finish(kmer_cuda_ctx* c, void* stream, kmer_dev_res
         }
         if (op == OP_COUNT && s.n_kmers != c->p_expected_kmers)
             return set_error(&c->err, KMER_ERR_CUDA, "XX000", "kmer_cuda: internal error: counted k-mers != windows", "", -1);
+    } else if (op == OP_SHARD_PART || op == OP_DENSE_TABLE) {
+        uint64_t bad_row = s.bad_char_pos == kNoError ? kNoError : s.pad;
+        if (bad_row != kNoError && bad_row <= s.short_row) return ref_error(&c->err, KMER_ERR_INVALID_DNA, (int64_t)bad_row);
+        if (s.short_row != kNoError) return ref_error(&c->err, KMER_ERR_INVALID_K, (int64_t)s.short_row);
+        if (s.n_overflow)
+            return set_error(&c->err, KMER_ERR_CAPACITY, "XX000",
+                             "kmer_cuda: a bucket segment overflowed (input too repetitive for the sharded partition path)", "", -1);
+        if (result) result->n_kmers = c->p_expected_kmers;
+    } else if (op == OP_SHARD_COUNT) {
+        if (s.out_overflow)
+            return set_error(&c->err, KMER_ERR_CAPACITY, "XX000", "kmer_cuda: output buffer too small", "", -1);
+        if (result) {
+            result->n_kmers = s.n_kmers;
+            result->n_distinct = s.n_distinct;
+            result->n_tier2 = c->last_tier2;
+        }
     } else if (op == OP_ENCODE) {
         if (s.bad_char_pos != kNoError) return ref_error(&c->err, KMER_ERR_INVALID_DNA, (int64_t)s.bad_char_pos);
     }
+    return KMER_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sharded counting (the caller owns the exchange)
+
+extern "C" int kmer_cuda_shard_plan(uint64_t total_kmers, int k, uint32_t n_ranks, kmer_shard_plan* plan) {
+    if (!plan || n_ranks < 1 || k < 14 || k > KMER_CUDA_MAX_K) return KMER_ERR_BAD_ARGUMENT;
+    PartitionPlan p = make_partition_plan(total_kmers, k);
+    memset(plan, 0, sizeof(*plan));
+    plan->n_ranks = n_ranks;
+    plan->buckets_per_rank = (p.n_buckets + n_ranks - 1) / n_ranks;
+    plan->n_buckets = plan->buckets_per_rank * n_ranks;
+    plan->k = k;
+    plan->w = p.w; plan->m = p.m; plan->recw = p.recw; plan->rmax = p.rmax;
+    plan->rec_bytes = p.recw == 1 ? 8 : 16;
+    if (n_ranks == 1) plan->cap = p.cap;
+    else {
+        // records per (bucket, source): about 2/(w+1) + 1/16 records per k-mer, 1/n_ranks of a bucket's k-mers
+        double kmers_per_bucket = (double)total_kmers / (double)plan->n_buckets;
+        double rpk = 2.0 / (p.w + 1) + 1.0 / 16.0 + (p.rmax < p.w ? 1.0 / p.rmax : 0.0);
+        double mean = kmers_per_bucket * rpk / n_ranks;
+        double cap = 1.35 * mean + 6.0 * sqrt(2.0 * mean) + 16.0;
+        plan->cap = (uint32_t)cap;
+    }
+    plan->recs_bytes_per_peer = (uint64_t)plan->buckets_per_rank * plan->cap * plan->rec_bytes;
+    plan->fill_bytes_per_peer = (uint64_t)plan->buckets_per_rank * 8;
+    return KMER_OK;
+}
+
+static PartitionPlan to_partition_plan(const kmer_shard_plan* sp, uint32_t n_buckets) {
+    PartitionPlan p{};
+    p.n_buckets = n_buckets;
+    p.cap = sp->cap;
+    p.w = sp->w; p.m = sp->m; p.recw = sp->recw; p.rmax = sp->rmax;
+    p.spill_cap = 0;   // no spill list when sharded: a full segment is an error reported by finish()
+    p.debug = 0;
+    return p;
+}
+
+extern "C" int kmer_cuda_dev_shard_partition(kmer_cuda_ctx* c, const char* d_seq, uint64_t n_bases, const uint64_t* d_row_off,
+                                             uint64_t n_rows, const kmer_shard_plan* sp, void* d_send_recs,
+                                             uint64_t* d_send_fill, void* stream) {
+    if (!c || !sp) return KMER_ERR_BAD_ARGUMENT;
+    cudaStream_t st = pick_stream(c, stream);
+    int rc = begin_op(c, st);
+    if (rc) return rc;
+    c->pending = OP_SHARD_PART;
+    c->p_n_bases = n_bases; c->p_n_rows = n_rows; c->p_k = sp->k;
+    c->p_expected_kmers = kmer_cuda_max_kmers(n_bases, n_rows, sp->k);
+    PartitionPlan plan = to_partition_plan(sp, sp->n_buckets);
+    if (n_rows == 0 || n_bases == 0) {
+        if (n_rows) return ref_error(&c->err, KMER_ERR_INVALID_K, 0);
+        CU(cudaMemsetAsync(d_send_fill, 0, (size_t)sp->n_buckets * 8, st), "memset fill");
+        return KMER_OK;
+    }
+    ScanArgs a;
+    rc = prepare_rows(c, d_row_off, n_bases, n_rows, sp->k, st, &a, d_seq);
+    if (rc) return rc;
+    launch_partition(c->di, a, plan, (unsigned long long*)d_send_fill, d_send_recs, nullptr, st);
+    mark(c, st, "minimizer_partition");
+    resolve_bad_row_kernel<<<1, 1, 0, st>>>(c->d_status, d_row_off, n_rows);
+    c->launches += 2;
+    CU(cudaGetLastError(), "shard partition launch");
+    return KMER_OK;
+}
+
+extern "C" int kmer_cuda_dev_shard_count(kmer_cuda_ctx* c, const kmer_shard_plan* sp, const void* d_recv_recs,
+                                         const uint64_t* d_recv_fill, kmer_count_pair* d_pairs, uint64_t pairs_capacity,
+                                         void* stream) {
+    if (!c || !sp) return KMER_ERR_BAD_ARGUMENT;
+    cudaStream_t st = pick_stream(c, stream);
+    int rc = begin_op(c, st);
+    if (rc) return rc;
+    c->pending = OP_SHARD_COUNT;
+    c->last_overflow = 0;
+    c->last_tier2 = 0;
+    const int k = sp->k;
+    PartitionPlan plan = to_partition_plan(sp, sp->buckets_per_rank);
+    rc = ws(c, c->failed, (size_t)plan.n_buckets * 4);
+    if (rc) return rc;
+    launch_bucket_count(c->di, plan, k, (int)sp->n_ranks, (const unsigned long long*)d_recv_fill, d_recv_recs,
+                        (uint32_t*)c->failed.p, d_pairs, pairs_capacity, c->d_status, st);
+    mark(c, st, "bucket_count");
+    c->launches++;
+    CU(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, st), "D2H status");
+    CU(cudaStreamSynchronize(st), "stream sync");
+    const DevStatus hs = *c->h_status;
+    if (hs.n_failed) {   // tier 2: buckets that did not fit on chip (all their segments are here)
+        uint64_t n_slots = next_pow2(std::max<uint64_t>(1024, hs.failed_kmers * 2));
+        rc = ws(c, c->table, n_slots * sizeof(kmer_count_pair));
+        if (rc) return rc;
+        launch_hash_clear((kmer_count_pair*)c->table.p, n_slots, st);
+        launch_partition_tier2(c->di, plan, k, (int)sp->n_ranks, (const unsigned long long*)d_recv_fill, d_recv_recs, nullptr,
+                               (const uint32_t*)c->failed.p, (kmer_count_pair*)c->table.p, n_slots, c->d_status, st);
+        mark(c, st, "tier2_insert");
+        launch_hash_compact(c->di, (const kmer_count_pair*)c->table.p, n_slots, k, d_pairs, pairs_capacity, c->d_status, st);
+        mark(c, st, "tier2_compact");
+        c->launches += 2;
+        c->last_tier2 = hs.failed_kmers;
+    } else {
+        launch_append_special(d_pairs, pairs_capacity, c->d_status, st);
+        c->launches++;
+    }
+    CU(cudaGetLastError(), "shard count launch");
+    return KMER_OK;
+}
+
+extern "C" int kmer_cuda_dev_dense_table(kmer_cuda_ctx* c, const char* d_seq, uint64_t n_bases, const uint64_t* d_row_off,
+                                         uint64_t n_rows, int k, uint64_t* d_table, void* stream) {
+    if (!c) return KMER_ERR_BAD_ARGUMENT;
+    cudaStream_t st = pick_stream(c, stream);
+    int rc = begin_op(c, st);
+    if (rc) return rc;
+    c->pending = OP_DENSE_TABLE;
+    c->p_n_bases = n_bases; c->p_n_rows = n_rows; c->p_k = k;
+    c->p_expected_kmers = kmer_cuda_max_kmers(n_bases, n_rows, k);
+    if (n_rows && (k < 1 || k > 13)) {
+        if (k < 1 || k > KMER_CUDA_MAX_K) return ref_error(&c->err, KMER_ERR_INVALID_K, 0);
+        return bad_arg(c, "dense counting needs k <= 13");
+    }
+    if (n_rows == 0 || n_bases == 0) {
+        if (n_rows) return ref_error(&c->err, KMER_ERR_INVALID_K, 0);
+        if (k >= 1 && k <= 13) CU(cudaMemsetAsync(d_table, 0, (size_t)8 << (2 * k), st), "memset table");
+        return KMER_OK;
+    }
+    ScanArgs a;
+    rc = prepare_rows(c, d_row_off, n_bases, n_rows, k, st, &a, d_seq);
+    if (rc) return rc;
+    launch_dense_table(c->di, a, (unsigned long long*)d_table, st);
+    mark(c, st, "count_dense");
+    resolve_bad_row_kernel<<<1, 1, 0, st>>>(c->d_status, d_row_off, n_rows);
+    c->launches += 2;
+    CU(cudaGetLastError(), "dense table launch");
+    return KMER_OK;
+}
+
+extern "C" int kmer_cuda_dev_dense_emit(kmer_cuda_ctx* c, const uint64_t* d_table, int k, uint32_t rank, uint32_t n_ranks,
+                                        kmer_count_pair* d_pairs, uint64_t pairs_capacity, void* stream) {
+    if (!c) return KMER_ERR_BAD_ARGUMENT;
+    cudaStream_t st = pick_stream(c, stream);
+    int rc = begin_op(c, st);
+    if (rc) return rc;
+    c->pending = OP_SHARD_COUNT;
+    c->last_overflow = 0;
+    c->last_tier2 = 0;
+    if (k < 1 || k > 13 || n_ranks < 1 || rank >= n_ranks) return bad_arg(c, "dense emit: k in 1..13, rank < n_ranks");
+    launch_dense_emit(c->di, (const unsigned long long*)d_table, k, rank, n_ranks, d_pairs, pairs_capacity, c->d_status, st);
+    mark(c, st, "dense_emit");
+    c->launches++;
+    CU(cudaGetLastError(), "dense emit launch");
     return KMER_OK;
 }
 

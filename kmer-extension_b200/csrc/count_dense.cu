@@ -43,13 +43,14 @@ __global__ void __launch_bounds__(NT) count_dense_global_kernel(ScanArgs a, unsi
 
 // non-zero bins -> (code,count) pairs, warp-aggregated append
 __global__ void dense_compact_kernel(const unsigned long long* __restrict__ table, uint64_t nbins,
-                                     kmer_count_pair* __restrict__ out, uint64_t capacity, DevStatus* status) {
+                                     kmer_count_pair* __restrict__ out, uint64_t capacity, DevStatus* status,
+                                     uint32_t rank, uint32_t n_ranks) {
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     uint64_t nb32 = (nbins + 31) & ~31ull;
     unsigned long long total = 0;
     const int lane = threadIdx.x & 31;
     for (uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b < nb32; b += stride) {
-        unsigned long long c = b < nbins ? table[b] : 0;
+        unsigned long long c = (b < nbins && (n_ranks <= 1 || b % n_ranks == rank)) ? table[b] : 0;
         uint32_t m = __ballot_sync(0xffffffffu, c != 0);
         if (!m) continue;
         unsigned long long base = 0;
@@ -66,8 +67,7 @@ __global__ void dense_compact_kernel(const unsigned long long* __restrict__ tabl
     if (lane == 0 && total) atomicAdd(&status->n_kmers, total);
 }
 
-void launch_count_dense(const DeviceInfo& di, const ScanArgs& a, unsigned long long* d_table, kmer_count_pair* d_pairs,
-                        uint64_t capacity, cudaStream_t st) {
+void launch_dense_table(const DeviceInfo& di, const ScanArgs& a, unsigned long long* d_table, cudaStream_t st) {
     uint64_t nbins = 1ull << (2 * a.k);
     cudaMemsetAsync(d_table, 0, nbins * sizeof(unsigned long long), st);
     uint64_t n_tiles = (a.n_bases + TILE - 1) / TILE;
@@ -77,10 +77,21 @@ void launch_count_dense(const DeviceInfo& di, const ScanArgs& a, unsigned long l
         if (a.k <= kSmemDenseMaxK) count_dense_smem_kernel<<<(unsigned)grid, NT, 0, st>>>(a, d_table);
         else count_dense_global_kernel<<<(unsigned)grid, NT, 0, st>>>(a, d_table);
     }
+}
+
+void launch_dense_emit(const DeviceInfo& di, const unsigned long long* d_table, int k, uint32_t rank, uint32_t n_ranks,
+                       kmer_count_pair* d_pairs, uint64_t capacity, DevStatus* d_status, cudaStream_t st) {
+    uint64_t nbins = 1ull << (2 * k);
     uint64_t blocks = (nbins + 255) / 256;
     uint64_t maxb = (uint64_t)di.sm_count * 8;
     if (blocks > maxb) blocks = maxb;
-    dense_compact_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_table, nbins, d_pairs, capacity, a.status);
+    dense_compact_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_table, nbins, d_pairs, capacity, d_status, rank, n_ranks);
+}
+
+void launch_count_dense(const DeviceInfo& di, const ScanArgs& a, unsigned long long* d_table, kmer_count_pair* d_pairs,
+                        uint64_t capacity, cudaStream_t st) {
+    launch_dense_table(di, a, d_table, st);
+    launch_dense_emit(di, d_table, a.k, 0, 1, d_pairs, capacity, a.status, st);
 }
 
 }  // namespace kmer

@@ -22,6 +22,8 @@
 //           kernel counts exactly those buckets' records in a global hash table and appends them;
 //   tier 3  if even the spill list overflows, DevStatus::n_overflow is set and the caller recounts
 //           the whole batch with the global-hash-table path (count_hash.cu).
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace kmer {
@@ -156,7 +158,9 @@ __global__ void __launch_bounds__(NT) partition_kernel(ScanArgs a, PartitionPlan
             }
 #pragma unroll
             for (int q = 0; q < 4; q++)
-                oldq[q] = act[q] ? atomicAdd(&fill[(uint32_t)(d[q] >> 32)], ((d[q] & 0xff0000ull) << 16) | 1ull) : 0ull;
+                oldq[q] = !act[q] ? 0ull
+                          : (plan.debug & 2) ? (unsigned long long)((mix32((uint32_t)d[q] + (uint32_t)sc.tile) >> 8) % plan.cap)
+                                             : atomicAdd(&fill[(uint32_t)(d[q] >> 32)], ((d[q] & 0xff0000ull) << 16) | 1ull);
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 if (!act[q]) continue;
@@ -175,7 +179,7 @@ __global__ void __launch_bounds__(NT) partition_kernel(ScanArgs a, PartitionPlan
                     if (si < plan.spill_cap) dst = spill + si;
                     else overflow_kmers += L;
                 }
-                if (dst) {
+                if (dst && !(plan.debug & 1)) {
                     if (RECW == 1) {
                         uint64_t v = ((uint64_t)r0w << 32) | r1w;
                         v &= ~0ull << (64 - 2 * nb);                       // nb <= 30
@@ -274,7 +278,10 @@ __global__ void __launch_bounds__(LEAF_THREADS) bucket_count_kernel(PartitionPla
                                                                     const unsigned long long* __restrict__ fill,
                                                                     const Rec<RECW>* __restrict__ recs,
                                                                     kmer_count_pair* __restrict__ out, uint64_t capacity,
-                                                                    uint32_t* __restrict__ failed_ids, DevStatus* status) {
+                                                                    uint32_t* __restrict__ failed_ids, DevStatus* status,
+                                                                    int n_src) {
+    // n_src > 1 (sharded counting): bucket b's records arrive as n_src segments, one per source GPU:
+    // segment s is recs[(s * n_buckets + b) * cap ..] with fill[s * n_buckets + b].
     extern __shared__ __align__(16) unsigned char leaf_dyn[];
     // layout: tbl u64[SLOTS] | keys u64[KEYS_CAP] | cnt u32[SLOTS] | slot_of u16[KEYS_CAP]
     const uint32_t tbl_s = smem_u32(leaf_dyn);
@@ -292,10 +299,16 @@ __global__ void __launch_bounds__(LEAF_THREADS) bucket_count_kernel(PartitionPla
     uint32_t par = 0;
 
     for (uint32_t b = blockIdx.x; b < plan.n_buckets; b += gridDim.x) {
-        const unsigned long long f = fill[b];
-        const uint32_t nrec_all = (uint32_t)f, nk = (uint32_t)(f >> 32);
+        uint32_t nrec_all = 0, nk = 0;
+        bool seg_overflow = false;
+        for (int sI = 0; sI < n_src; sI++) {
+            const unsigned long long f = fill[(uint64_t)sI * plan.n_buckets + b];
+            nrec_all += (uint32_t)f;
+            nk += (uint32_t)(f >> 32);
+            seg_overflow |= (uint32_t)f > plan.cap;
+        }
         if (nrec_all == 0) continue;                                    // uniform across the CTA
-        if (nrec_all > plan.cap || nk > KEYS_CAP) {                     // region overflowed / too many k-mers: tier 2
+        if (seg_overflow || nk > KEYS_CAP) {                            // region overflowed / too many k-mers: tier 2
             if (t == 0) {
                 uint32_t idx = (uint32_t)atomicAdd(&status->n_failed, 1ull);
                 failed_ids[idx] = b;
@@ -308,9 +321,11 @@ __global__ void __launch_bounds__(LEAF_THREADS) bucket_count_kernel(PartitionPla
         // table := empty, counters := 0 (16-byte stores); overlaps with the expansion
         for (int i = t; i < LEAF_SLOTS / 2; i += LEAF_THREADS) sts128(tbl_s + 16 * i, ~0u, ~0u, ~0u, ~0u);
         for (int i = t; i < LEAF_SLOTS / 4; i += LEAF_THREADS) sts128(cnt_s + 16 * i, 0u, 0u, 0u, 0u);
-        const Rec<RECW>* base = recs + (uint64_t)b * plan.cap;
         // ---- expand
-        for (uint32_t r = t; r < nrec_all; r += LEAF_THREADS) {
+        for (int sI = 0; sI < n_src; sI++) {
+        const uint32_t nrec_seg = n_src == 1 ? nrec_all : (uint32_t)fill[(uint64_t)sI * plan.n_buckets + b];
+        const Rec<RECW>* base = recs + ((uint64_t)sI * plan.n_buckets + b) * plan.cap;
+        for (uint32_t r = t; r < nrec_seg; r += LEAF_THREADS) {
             uint64_t hi, lo = 0;
             int L;
             if (RECW == 1) {
@@ -327,6 +342,7 @@ __global__ void __launch_bounds__(LEAF_THREADS) bucket_count_kernel(PartitionPla
                 uint64_t win = (RECW == 1 || o == 0) ? (hi << (2 * o)) : ((hi << (2 * o)) | (lo >> (64 - 2 * o)));
                 sts64(a, win >> kshift);
             }
+        }
         }
         __syncthreads();                                                // (A)
         if (t == 0) {                                                   // the other counter set is idle now: reset it
@@ -466,16 +482,18 @@ template <int RECW>
 __global__ void __launch_bounds__(256) tier2_insert_kernel(PartitionPlan plan, int k, const unsigned long long* __restrict__ fill,
                                                            const Rec<RECW>* __restrict__ recs, const uint32_t* __restrict__ failed_ids,
                                                            const Rec<RECW>* __restrict__ spill, kmer_count_pair* __restrict__ slots,
-                                                           uint64_t mask, DevStatus* status) {
+                                                           uint64_t mask, DevStatus* status, int n_src) {
     const int kshift = 64 - 2 * k;
     const uint32_t n_failed = (uint32_t)status->n_failed;
     for (uint32_t fi = blockIdx.x; fi < n_failed; fi += gridDim.x) {
         const uint32_t b = failed_ids[fi];
-        const uint32_t nrec = min((uint32_t)fill[b], plan.cap);
-        const Rec<RECW>* base = recs + (uint64_t)b * plan.cap;
-        for (uint32_t r0 = 0; r0 < nrec; r0 += blockDim.x) {
-            uint32_t r = r0 + threadIdx.x;
-            tier2_add_record<RECW>(base + min(r, nrec - 1), kshift, slots, mask, status, r < nrec);
+        for (int sI = 0; sI < n_src; sI++) {
+            const uint32_t nrec = min((uint32_t)fill[(uint64_t)sI * plan.n_buckets + b], plan.cap);
+            const Rec<RECW>* base = recs + ((uint64_t)sI * plan.n_buckets + b) * plan.cap;
+            for (uint32_t r0 = 0; r0 < nrec; r0 += blockDim.x) {
+                uint32_t r = r0 + threadIdx.x;
+                tier2_add_record<RECW>(base + min(r, nrec - 1), kshift, slots, mask, status, r < nrec);
+            }
         }
     }
     const uint64_t n_spill = min((uint64_t)status->n_spill, (uint64_t)plan.spill_cap);
@@ -513,53 +531,67 @@ PartitionPlan make_partition_plan(uint64_t n_kmers, int k) {
     p.cap = p.recw == 1 ? 1280u : 896u;
     uint64_t sc = (uint64_t)p.n_buckets * p.cap / 8;          // spill list: 1/8 of the bucket regions
     p.spill_cap = sc < 4096 ? 4096 : sc;
+    const char* dbg = getenv("KMER_CUDA_DEBUG_PARTITION");   // profiling experiments only (bit0: no record stores, bit1: no slot atomics)
+    p.debug = dbg ? atoi(dbg) : 0;
     return p;
 }
 
 size_t partition_record_bytes(const PartitionPlan& p) { return (size_t)p.n_buckets * p.cap * (p.recw == 1 ? 8 : 16); }
 size_t partition_spill_bytes(const PartitionPlan& p) { return (size_t)p.spill_cap * (p.recw == 1 ? 8 : 16); }
 
-void launch_count_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPlan& p, unsigned long long* d_fill,
-                            void* d_recs, void* d_spill, uint32_t* d_failed_ids, kmer_count_pair* d_pairs, uint64_t capacity,
-                            cudaStream_t st, void (*mark)(void*, const char*), void* mark_arg) {
+void launch_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPlan& p, unsigned long long* d_fill,
+                      void* d_recs, void* d_spill, cudaStream_t st) {
     cudaMemsetAsync(d_fill, 0, (size_t)p.n_buckets * sizeof(unsigned long long), st);
     uint64_t n_tiles = (a.n_bases + TILE - 1) / TILE;
-    uint64_t grid = (uint64_t)di.sm_count * 6;
+    uint64_t grid = (uint64_t)di.sm_count * 5;
     if (grid > n_tiles) grid = n_tiles;
-    if (n_tiles) {
-        if (p.w == 4) partition_kernel<4, 1><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill);
-        else if (p.w == 8) partition_kernel<8, 1><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill);
-        else partition_kernel<16, 2><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<2>*)d_recs, (Rec<2>*)d_spill);
-    }
-    if (mark) mark(mark_arg, "minimizer_partition");
+    if (!n_tiles) return;
+    if (p.w == 4) partition_kernel<4, 1><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill);
+    else if (p.w == 8) partition_kernel<8, 1><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill);
+    else partition_kernel<16, 2><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<2>*)d_recs, (Rec<2>*)d_spill);
+}
+
+// p.n_buckets = buckets counted HERE (all of them on one GPU, the owned range when sharded)
+void launch_bucket_count(const DeviceInfo& di, const PartitionPlan& p, int k, int n_src, const unsigned long long* d_fill,
+                         const void* d_recs, uint32_t* d_failed_ids, kmer_count_pair* d_pairs, uint64_t capacity,
+                         DevStatus* d_status, cudaStream_t st) {
     const size_t leaf_smem = LEAF_SLOTS * (8 + 4) + KEYS_CAP * (8 + 2);   // 32 + 16 + 32 + 8 = 88 KB
     uint64_t lgrid = (uint64_t)di.sm_count * 2;
     if (lgrid > p.n_buckets) lgrid = p.n_buckets;
+    if (!lgrid) return;
     if (p.recw == 1) {
         cudaFuncSetAttribute(bucket_count_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leaf_smem);
         cudaFuncSetAttribute(bucket_count_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        bucket_count_kernel<1><<<(unsigned)lgrid, LEAF_THREADS, leaf_smem, st>>>(p, a.k, d_fill, (const Rec<1>*)d_recs, d_pairs,
-                                                                                capacity, d_failed_ids, a.status);
+        bucket_count_kernel<1><<<(unsigned)lgrid, LEAF_THREADS, leaf_smem, st>>>(p, k, d_fill, (const Rec<1>*)d_recs, d_pairs,
+                                                                                capacity, d_failed_ids, d_status, n_src);
     } else {
         cudaFuncSetAttribute(bucket_count_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leaf_smem);
         cudaFuncSetAttribute(bucket_count_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        bucket_count_kernel<2><<<(unsigned)lgrid, LEAF_THREADS, leaf_smem, st>>>(p, a.k, d_fill, (const Rec<2>*)d_recs, d_pairs,
-                                                                                capacity, d_failed_ids, a.status);
+        bucket_count_kernel<2><<<(unsigned)lgrid, LEAF_THREADS, leaf_smem, st>>>(p, k, d_fill, (const Rec<2>*)d_recs, d_pairs,
+                                                                                capacity, d_failed_ids, d_status, n_src);
     }
+}
+
+void launch_count_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPlan& p, unsigned long long* d_fill,
+                            void* d_recs, void* d_spill, uint32_t* d_failed_ids, kmer_count_pair* d_pairs, uint64_t capacity,
+                            cudaStream_t st, void (*mark)(void*, const char*), void* mark_arg) {
+    launch_partition(di, a, p, d_fill, d_recs, d_spill, st);
+    if (mark) mark(mark_arg, "minimizer_partition");
+    launch_bucket_count(di, p, a.k, 1, d_fill, d_recs, d_failed_ids, d_pairs, capacity, a.status, st);
     if (mark) mark(mark_arg, "bucket_count");
 }
 
 // tier 2 (only when the host saw n_failed or n_spill): slots must be cleared to 0xFF (launch_hash_clear)
-void launch_partition_tier2(const DeviceInfo& di, const PartitionPlan& p, int k, const unsigned long long* d_fill,
+void launch_partition_tier2(const DeviceInfo& di, const PartitionPlan& p, int k, int n_src, const unsigned long long* d_fill,
                             const void* d_recs, const void* d_spill, const uint32_t* d_failed_ids, kmer_count_pair* d_slots,
                             uint64_t n_slots, DevStatus* d_status, cudaStream_t st) {
     unsigned grid = (unsigned)di.sm_count * 8;
     if (p.recw == 1)
         tier2_insert_kernel<1><<<grid, 256, 0, st>>>(p, k, d_fill, (const Rec<1>*)d_recs, d_failed_ids, (const Rec<1>*)d_spill,
-                                                     d_slots, n_slots - 1, d_status);
+                                                     d_slots, n_slots - 1, d_status, n_src);
     else
         tier2_insert_kernel<2><<<grid, 256, 0, st>>>(p, k, d_fill, (const Rec<2>*)d_recs, d_failed_ids, (const Rec<2>*)d_spill,
-                                                     d_slots, n_slots - 1, d_status);
+                                                     d_slots, n_slots - 1, d_status, n_src);
 }
 
 void launch_append_special(kmer_count_pair* d_pairs, uint64_t capacity, DevStatus* d_status, cudaStream_t st) {

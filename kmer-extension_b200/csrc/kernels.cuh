@@ -29,6 +29,10 @@ void launch_extract(const DeviceInfo& di, const ScanArgs& a, const uint32_t* d_t
 void launch_count_dense(const DeviceInfo& di, const ScanArgs& a, unsigned long long* d_table,
                         kmer_count_pair* d_pairs, uint64_t capacity, cudaStream_t st);
 
+void launch_dense_table(const DeviceInfo& di, const ScanArgs& a, unsigned long long* d_table, cudaStream_t st);
+void launch_dense_emit(const DeviceInfo& di, const unsigned long long* d_table, int k, uint32_t rank, uint32_t n_ranks,
+                       kmer_count_pair* d_pairs, uint64_t capacity, DevStatus* d_status, cudaStream_t st);
+
 // count_hash.cu ---------------------------------------------------------------------------------
 // open-addressing table of (code,count) slots in HBM; slots must be filled with 0xFF bytes
 void launch_hash_clear(kmer_count_pair* d_slots, uint64_t n_slots, cudaStream_t st);
@@ -47,6 +51,7 @@ struct PartitionPlan {
     int recw;             // 64-bit words per super-k-mer record (1: k <= 26, 2: k >= 27)
     int rmax;             // max k-mers per record
     uint64_t spill_cap;   // records the spill list holds
+    int debug;            // profiling experiments only (env KMER_CUDA_DEBUG_PARTITION)
 };
 PartitionPlan make_partition_plan(uint64_t n_kmers, int k);
 size_t partition_record_bytes(const PartitionPlan& p);
@@ -56,7 +61,12 @@ size_t partition_spill_bytes(const PartitionPlan& p);
 void launch_count_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPlan& p, unsigned long long* d_fill,
                             void* d_recs, void* d_spill, uint32_t* d_failed_ids, kmer_count_pair* d_pairs, uint64_t capacity,
                             cudaStream_t st, void (*mark)(void*, const char*), void* mark_arg);
-void launch_partition_tier2(const DeviceInfo& di, const PartitionPlan& p, int k, const unsigned long long* d_fill,
+void launch_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPlan& p, unsigned long long* d_fill,
+                      void* d_recs, void* d_spill, cudaStream_t st);
+void launch_bucket_count(const DeviceInfo& di, const PartitionPlan& p, int k, int n_src, const unsigned long long* d_fill,
+                         const void* d_recs, uint32_t* d_failed_ids, kmer_count_pair* d_pairs, uint64_t capacity,
+                         DevStatus* d_status, cudaStream_t st);
+void launch_partition_tier2(const DeviceInfo& di, const PartitionPlan& p, int k, int n_src, const unsigned long long* d_fill,
                             const void* d_recs, const void* d_spill, const uint32_t* d_failed_ids, kmer_count_pair* d_slots,
                             uint64_t n_slots, DevStatus* d_status, cudaStream_t st);
 void launch_append_special(kmer_count_pair* d_pairs, uint64_t capacity, DevStatus* d_status, cudaStream_t st);

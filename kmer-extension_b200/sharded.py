@@ -1,0 +1,136 @@
+"""Sharded k-mer counting: one process per GPU, rows split across ranks, one all-to-all.
+
+The reference has no distributed path (its only parallelism is PostgreSQL's parallel query); this is
+the multi-GPU form of `SELECT kmer, count(*) ... GROUP BY kmer` over generate_kmers (kmer.c:289-351):
+
+  1. every rank partitions ITS rows' k-mers into the same global minimizer buckets
+     (kmer_cuda_dev_shard_partition),
+  2. bucket b is owned by rank b // buckets_per_rank; ONE all-to-all (equal splits) moves every
+     (bucket, source) segment of super-k-mer records to its owner, a second small one the fill counts,
+  3. every owner counts its buckets on chip (kmer_cuda_dev_shard_count).
+
+Identical k-mers share a minimizer, hence a bucket, hence an owner, so the per-rank results are
+disjoint and the GROUP BY result is their concatenation.  k <= 13 uses the dense 4^k table instead:
+all-reduce(sum) of the per-rank tables, every rank emits the bins it owns.
+
+`torch.distributed` is the transport (NCCL on GPUs; gloo in the CPU plumbing tests, where the engine is
+a stand-in).  The library itself never communicates.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+class ShardedCounter:
+    def __init__(self, engine, group=None, device=None):
+        self.eng = engine
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._bufs = {}
+        self.last_plan = None
+        self.last_exchange_bytes = 0
+        self.last_phases = []      # (name, ms) of the last count when the engine's profiling is on
+
+    # ------------------------------------------------------------------ helpers
+    def _buf(self, name, nbytes, dtype=torch.uint8):
+        item = torch.empty((), dtype=dtype).element_size()
+        n = (nbytes + item - 1) // item
+        t = self._bufs.get(name)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            self._bufs[name] = t
+        return t[:n]
+
+    def _allreduce_int(self, value: int, op=dist.ReduceOp.SUM) -> int:
+        if self.world == 1:
+            return int(value)
+        t = torch.tensor([int(value)], dtype=torch.int64, device=self.device)
+        dist.all_reduce(t, op=op, group=self.group)
+        return int(t.item())
+
+    def _phases(self):
+        return list(self.eng.phases()) if hasattr(self.eng, "phases") else []
+
+    def _agree(self, exc):
+        """All ranks raise if any rank failed (the lowest failing rank's error text wins on that rank only)."""
+        bad = self._allreduce_int(0 if exc is None else 1, dist.ReduceOp.MAX)
+        if exc is not None:
+            raise exc
+        if bad:
+            raise RuntimeError("sharded count aborted: another rank reported an input error")
+
+    # ------------------------------------------------------------------ the operation
+    def count(self, d_seq, n_bases: int, d_off, n_rows: int, k: int, d_pairs, total_kmers: int | None = None):
+        """Counts this rank's rows together with all other ranks' rows.
+
+        d_pairs: int64 [capacity, 2] on this rank; returns (n_distinct_here, n_kmers_counted_here, info dict).
+        Collective: every rank of the group must call it with the same k."""
+        eng = self.eng
+        local_kmers = eng.max_kmers(n_bases, n_rows, k)
+        if total_kmers is None:
+            total_kmers = self._allreduce_int(local_kmers)
+        if k <= 13:
+            return self._count_dense(d_seq, n_bases, d_off, n_rows, k, d_pairs, total_kmers)
+        plan = eng.shard_plan(max(total_kmers, 1), k, self.world)
+        self.last_plan = plan
+        recs_bytes = plan.recs_bytes_per_peer * self.world
+        fill_words = plan.buckets_per_rank * self.world
+        send_recs = self._buf("send_recs", recs_bytes)
+        send_fill = self._buf("send_fill", fill_words * 8, torch.int64)
+        exc = None
+        phases = []
+        try:
+            eng.dev_shard_partition(d_seq, n_bases, d_off, n_rows, plan, send_recs, send_fill)
+            eng.dev_finish()
+            phases += self._phases()
+        except Exception as e:  # input error or segment overflow on this rank
+            exc = e
+        self._agree(exc)
+        if self.world > 1:
+            recv_recs = self._buf("recv_recs", recs_bytes)
+            recv_fill = self._buf("recv_fill", fill_words * 8, torch.int64)
+            timed = self.device.type == "cuda"
+            if timed:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            dist.all_to_all_single(recv_fill, send_fill, group=self.group)
+            dist.all_to_all_single(recv_recs, send_recs, group=self.group)
+            if timed:
+                e1.record()
+                e1.synchronize()
+                phases.append(("all_to_all", e0.elapsed_time(e1)))
+            self.last_exchange_bytes = int(recs_bytes + fill_words * 8) * (self.world - 1) // self.world
+        else:
+            recv_recs, recv_fill = send_recs, send_fill
+            self.last_exchange_bytes = 0
+        eng.dev_shard_count(plan, recv_recs, recv_fill, d_pairs)
+        r = eng.dev_finish()
+        phases += self._phases()
+        self.last_phases = phases
+        counted = self._allreduce_int(int(r.n_kmers))
+        if counted != total_kmers:
+            raise RuntimeError(f"sharded count lost k-mers: counted {counted}, expected {total_kmers}")
+        return int(r.n_distinct), int(r.n_kmers), {"tier2_kmers": int(r.n_tier2), "plan": plan}
+
+    def _count_dense(self, d_seq, n_bases, d_off, n_rows, k, d_pairs, total_kmers):
+        eng = self.eng
+        table = self._buf("dense", 8 << (2 * k), torch.int64)
+        exc = None
+        try:
+            eng.dev_dense_table(d_seq, n_bases, d_off, n_rows, k, table)
+            eng.dev_finish()
+        except Exception as e:
+            exc = e
+        self._agree(exc)
+        if self.world > 1:
+            dist.all_reduce(table, op=dist.ReduceOp.SUM, group=self.group)
+            self.last_exchange_bytes = int(table.numel() * 8)
+        eng.dev_dense_emit(table, k, self.rank, self.world, d_pairs)
+        r = eng.dev_finish()
+        counted = self._allreduce_int(int(r.n_kmers))
+        if counted != total_kmers:
+            raise RuntimeError(f"sharded dense count lost k-mers: counted {counted}, expected {total_kmers}")
+        return int(r.n_distinct), int(r.n_kmers), {"tier2_kmers": 0, "plan": None}
