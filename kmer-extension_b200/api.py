@@ -155,6 +155,7 @@ class KmerCuda:
         return int(self.lib.kmer_cuda_launch_count(self.ctx))
 
     def set_profiling(self, on: bool):
+        self.profiling = bool(on)
         self.lib.kmer_cuda_set_profiling(self.ctx, int(on))
 
     def phases(self) -> list[tuple[str, float]]:

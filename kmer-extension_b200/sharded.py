@@ -92,7 +92,7 @@ class ShardedCounter:
         if self.world > 1:
             recv_recs = self._buf("recv_recs", recs_bytes)
             recv_fill = self._buf("recv_fill", fill_words * 8, torch.int64)
-            timed = self.device.type == "cuda"
+            timed = self.device.type == "cuda" and getattr(eng, "profiling", False)
             if timed:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
