@@ -1,0 +1,155 @@
+/*
+ * kmer_gpu.c -- C glue a maintainer adds NEXT TO the reference's kmer.c (same MODULE_big), binding
+ * libkmer_cuda.so through include/kmer_cuda.h.  The existing SQL surface (kmer--1.0.0.sql) is not
+ * touched; these functions are additive.  Compiles against PostgreSQL's headers, and -- for the
+ * compile check in this repository, which has no PostgreSQL -- against oracle/pgshim.
+ *
+ *   kmer_gpu_count_datums()  : GROUP BY kmer / count(*) over generate_kmers(dna, k) for a batch of `dna`
+ *                              datums, replacing one generate_kmers SRF scan per row (kmer.c:289-351) and
+ *                              the HashAggregate over kmer_hash / kmer_equals (kmer.c:226-245,353-365).
+ *   kmer_gpu_match_datums()  : equals / starts_with / contains over a batch of `kmer` datums against one
+ *                              constant, replacing per-row kmer_equals / kmer_starts_with / kmer_contains
+ *                              calls (kmer.c:226-285).
+ *
+ * Results are palloc'ed in the caller's memory context, exactly like the reference's functions
+ * (kmer.c:92,124,341); `kmer` results carry the 1-byte short varlena header generate_kmers writes
+ * (SET_VARSIZE_SHORT, kmer.c:341-342).  Errors are re-raised with the reference's own SQLSTATE and
+ * text (kmer.c:33-36,117-119,151-153,179-181,311-313).
+ *
+ * CUDA must not be initialised in the postmaster: the context is created lazily, on first use, in
+ * the backend (or parallel worker) process, i.e. after fork().
+ */
+#include "postgres.h"
+#include "fmgr.h"
+#include "kmer_cuda.h"
+
+
+static kmer_cuda_ctx *gpu_ctx = NULL; /* one per backend process */
+
+static void
+kmer_gpu_raise(const kmer_cuda_error *e)
+{
+	int code;
+
+	switch (e->status)
+	{
+	case KMER_ERR_INVALID_DNA:
+	case KMER_ERR_INVALID_QKMER:
+		code = ERRCODE_INVALID_TEXT_REPRESENTATION; /* 22P02 */
+		break;
+	case KMER_ERR_KMER_TOO_LONG:
+	case KMER_ERR_QKMER_TOO_LONG:
+		code = ERRCODE_STRING_DATA_RIGHT_TRUNCATION; /* 22001 */
+		break;
+	case KMER_ERR_INVALID_K:
+		code = ERRCODE_INVALID_PARAMETER_VALUE; /* 22023 */
+		break;
+	case KMER_ERR_OOM:
+		code = ERRCODE_OUT_OF_MEMORY;
+		break;
+	default:
+		code = ERRCODE_INTERNAL_ERROR;
+	}
+	if (e->detail[0])
+		ereport(ERROR, (errcode(code), errmsg("%s", e->message), errdetail("%s", e->detail)));
+	else
+		ereport(ERROR, (errcode(code), errmsg("%s", e->message)));
+}
+
+static kmer_cuda_ctx *
+kmer_gpu_context(void)
+{
+	if (gpu_ctx == NULL)
+	{
+		if (kmer_cuda_init(&gpu_ctx, 0) != KMER_OK) /* device choice: a GUC in a real build */
+			kmer_gpu_raise(kmer_cuda_last_error(NULL));
+	}
+	return gpu_ctx;
+}
+
+/*
+ * dnas[0..n) are detoasted `dna` datums (PG_DETOAST_DATUM in the caller).  On return *kmers is an array
+ * of *n_groups `kmer` datums (short-header varlenas) and *counts their bigint counts.
+ */
+void
+kmer_gpu_count_datums(struct varlena **dnas, uint64_t n, int k, struct varlena ***kmers, int64_t **counts,
+					  uint64_t *n_groups)
+{
+	kmer_cuda_ctx *ctx = kmer_gpu_context();
+	uint64_t *off = (uint64_t *) palloc((n + 1) * sizeof(uint64_t));
+	uint64_t total = 0, i, n_kmers = 0, d = 0;
+	char *flat, *text = NULL;
+	kmer_count_pair *pairs = NULL;
+	uint64_t *codes;
+
+	off[0] = 0;
+	for (i = 0; i < n; i++)
+	{
+		total += (uint64_t) VARSIZE_ANY_EXHDR(dnas[i]);
+		off[i + 1] = total;
+	}
+	flat = (char *) palloc(total + 16);
+	for (i = 0; i < n; i++)
+		memcpy(flat + off[i], VARDATA_ANY(dnas[i]), (size_t) (off[i + 1] - off[i]));
+
+	if (kmer_cuda_submit_count(ctx, flat, off, n, k, &pairs, &d, &n_kmers) != KMER_OK)
+		kmer_gpu_raise(kmer_cuda_last_error(ctx));
+
+	/* text of the groups with the short varlena header already in place: d * (k+1) bytes */
+	codes = (uint64_t *) palloc((d ? d : 1) * sizeof(uint64_t));
+	*counts = (int64_t *) palloc((d ? d : 1) * sizeof(int64_t));
+	for (i = 0; i < d; i++)
+	{
+		codes[i] = pairs[i].code;
+		(*counts)[i] = (int64_t) pairs[i].count;
+	}
+	kmer_cuda_release(ctx, pairs);
+	if (kmer_cuda_submit_decode(ctx, codes, d, k, 1, &text) != KMER_OK)
+		kmer_gpu_raise(kmer_cuda_last_error(ctx));
+
+	*kmers = (struct varlena **) palloc((d ? d : 1) * sizeof(struct varlena *));
+	for (i = 0; i < d; i++)
+	{
+		struct varlena *v = (struct varlena *) palloc((Size) k + VARHDRSZ_SHORT);
+
+		memcpy(v, text + i * (uint64_t) (k + 1), (size_t) k + 1); /* header byte + k lower-case bases */
+		(*kmers)[i] = v;
+	}
+	kmer_cuda_release(ctx, text);
+	*n_groups = d;
+}
+
+/*
+ * op: KMER_OP_EQUALS (kmer = const), KMER_OP_STARTS_WITH (kmer ^@ const), KMER_OP_CONTAINS (const::qkmer @> kmer).
+ * kmers[0..n) are `kmer` datums of any lengths 0..32; result[i] is the boolean the reference returns.
+ */
+void
+kmer_gpu_match_datums(int op, struct varlena **kmers, uint64_t n, const char *constant, bool *result)
+{
+	kmer_cuda_ctx *ctx = kmer_gpu_context();
+	char *text = (char *) palloc((n ? n : 1) * KMER_CUDA_MAX_K);
+	uint8_t *lens = (uint8_t *) palloc(n ? n : 1);
+	uint64_t *codes = NULL, *hits = NULL, wpr = 0, i;
+	uint32_t *bits = NULL;
+	const char *consts[1];
+
+	memset(text, 'a', (n ? n : 1) * KMER_CUDA_MAX_K);
+	for (i = 0; i < n; i++)
+	{
+		lens[i] = (uint8_t) VARSIZE_ANY_EXHDR(kmers[i]);
+		memcpy(text + i * KMER_CUDA_MAX_K, VARDATA_ANY(kmers[i]), lens[i]);
+	}
+	if (kmer_cuda_submit_encode(ctx, text, lens, n, KMER_CUDA_MAX_K, &codes) != KMER_OK)
+		kmer_gpu_raise(kmer_cuda_last_error(ctx));
+	consts[0] = constant;
+	if (kmer_cuda_submit_match(ctx, op, NULL, codes, lens, n, 0, consts, 1, &bits, &wpr, &hits) != KMER_OK)
+	{
+		kmer_cuda_release(ctx, codes);
+		kmer_gpu_raise(kmer_cuda_last_error(ctx));
+	}
+	for (i = 0; i < n; i++)
+		result[i] = (bits[i >> 5] >> (i & 31)) & 1u;
+	kmer_cuda_release(ctx, codes);
+	kmer_cuda_release(ctx, bits);
+	kmer_cuda_release(ctx, hits);
+}

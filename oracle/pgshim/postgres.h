@@ -69,6 +69,8 @@ static inline MemoryContext MemoryContextSwitchTo(MemoryContext c) { return c; }
 #define ERRCODE_INVALID_TEXT_REPRESENTATION 0x22503 /* "22P02" tag, value only compared for identity */
 #define ERRCODE_STRING_DATA_RIGHT_TRUNCATION 0x22001
 #define ERRCODE_INVALID_PARAMETER_VALUE 0x22023
+#define ERRCODE_INTERNAL_ERROR 0x99000 /* XX000 */
+#define ERRCODE_OUT_OF_MEMORY 0x53200
 
 typedef struct PgShimError
 {
