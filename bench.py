@@ -156,6 +156,82 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_secondary(args):
+    """Secondary single-GPU measurements of the other rows of the path (not the headline line):
+       extract  : generate_kmers over 1 GB, k=21              B_alg = N + 8*n_kmers
+       match_c5 : equals + starts_with in ONE pass over M 32-mers (configs[4])   B_alg = 8*M + 2*M/8
+       match_c4 : contains, 1000 IUPAC patterns (k=12) x M k-mers (configs[3])   B_alg = 8*M + 16*P + P*M/8"""
+    import torch
+    g, api, datagen = load_pkg()
+    torch.cuda.set_device(0)
+    eng = api.KmerCuda(0)
+    peak, peak_src = measured_peaks()
+    stream = torch.cuda.current_stream()
+
+    def timed(fn):
+        for _ in range(args.warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / args.steps
+
+    if args.workload == "extract":
+        n_rows = args.reads
+        flat, off = datagen.synth_reads(2, n_rows, READ_LEN)
+        n_bases = int(off[-1])
+        d_seq = torch.from_numpy(np.concatenate([flat, np.zeros(64, np.uint8)])).cuda()
+        d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+        n_k = eng.max_kmers(n_bases, n_rows, K)
+        d_codes = torch.empty(n_k, dtype=torch.int64, device="cuda")
+
+        def fn():
+            eng.dev_extract(d_seq, n_bases, d_off, n_rows, K, d_codes, stream=stream)
+            eng.dev_finish(stream)
+        ms = timed(fn)
+        alg = n_bases + 8 * n_k
+        units, unit, metric = n_k, "k-mers/s", "kmers_extracted_per_sec_k21"
+        wl = f"generate_kmers over {n_bases / 1e9:.3g} GB ({n_rows} reads x {READ_LEN}), k={K}"
+    else:
+        if args.workload == "match_c5":
+            m, k, P = args.match_m or 1_000_000_000, 32, 2
+            col = datagen.synth_kmer_codes(5, m, k)
+            txt = "".join("acgt"[(int(col[0]) >> (2 * (31 - j))) & 3] for j in range(32))
+            consts, ops = [txt, txt[:8]], [api.OP_EQUALS, api.OP_STARTS_WITH]
+            alg = 8 * m + 2 * ((m + 7) // 8)
+            wl = f"configs[4]: equals + starts_with(8-base prefix) in one pass over {m:.3g} 32-mers"
+        else:
+            m, k, P = args.match_m or 100_000_000, 12, 1000
+            col = datagen.synth_kmer_codes(4, m, k)
+            consts, ops = datagen.synth_qkmers(4, P, k, with_n=True), None
+            alg = 8 * m + 16 * P + P * ((m + 7) // 8)
+            wl = f"configs[3]: contains, {P} IUPAC patterns (k=12, 15-letter alphabet incl. N) x {m:.3g} k-mers, full bit matrix"
+        d_col = torch.from_numpy(col.view(np.int64)).cuda()
+        wpr = (m + 31) // 32
+        d_bits = torch.empty(P * wpr, dtype=torch.int32, device="cuda")
+        d_hits = torch.empty(P, dtype=torch.int64, device="cuda")
+        op = api.OP_CONTAINS if args.workload == "match_c4" else api.OP_EQUALS
+
+        def fn():
+            eng.dev_match(op, d_col, m, k, consts, d_bits, d_hits, ops=ops, stream=stream)
+            eng.dev_finish(stream)
+        ms = timed(fn)
+        units, unit, metric = m * P, "pair-tests/s", f"{args.workload}_pair_tests_per_sec"
+    ach = alg / (ms * 1e-3) / 1e9
+    line = {"metric": metric, "value": units / (ms * 1e-3), "unit": unit, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": wl, "secondary": True},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "alg_bytes_per_launch": alg, "peak_source": peak_src},
+            "gpu_launches": int(eng.launches)}
+    print(json.dumps(line), flush=True)
+    eng.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -166,6 +242,9 @@ def main():
     ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 dense, 2 hash, 3 minimizer partition")
     ap.add_argument("--ref-reads", type=int, default=4000, help="sample size of the reference arm per step")
     ap.add_argument("--cpu-reads", type=int, default=20000, help="sample size of the cpu_baseline leg")
+    ap.add_argument("--workload", default="count", choices=["count", "extract", "match_c4", "match_c5"],
+                    help="count = the headline (configs[1]); the others are secondary parity-config measurements")
+    ap.add_argument("--match-m", type=int, default=0, help="k-mers in the match workloads (default: the config's size)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -173,6 +252,8 @@ def main():
         print(f"note: warmup {args.warmup} < 3 is below the timing rule", file=sys.stderr)
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload != "count":
+        return run_secondary(args)
 
     import torch
     import torch.distributed as dist

@@ -203,25 +203,21 @@ __global__ void __launch_bounds__(NT) partition_kernel(ScanArgs a, PartitionPlan
 // ---------------------------------------------------------------------------------------------
 // per-bucket counting
 //
-// One CTA per bucket, in passes of at most KEYS_CAP k-mers (one pass for any ordinary bucket):
-//   expand  : every record is unpacked into the shared key array (a shared atomicAdd per RECORD
-//             reserves its range), so the next phase sees one k-mer per array slot whatever the
-//             record lengths were;
-//   probe   : PERSISTENT-LANE probing -- thread t walks keys t, t+256, ...; each loop iteration is
-//             one 64-bit shared atomicCAS, and a thread whose key is placed (or found) moves straight
-//             on to its next key, so nobody waits for the longest probe sequence of a warp.  A thread
-//             that claims an empty slot notes the slot index beside its key (slot_of[i]);
-//   compact : the noted slots are gathered into the bucket's winner list (ballot + one shared
-//             atomicAdd per warp iteration).
-// Emission walks the winner list -- exactly one entry per distinct k-mer -- and writes fully coalesced
-// 16-byte (k-mer, count) pairs after ONE global atomicAdd per bucket; the table is never scanned.
-// Shared memory is addressed through explicit 32-bit shared addresses (ld/st/atom.shared PTX), which
-// keeps the inner loop free of generic-address arithmetic.
-// A bucket whose distinct keys do not fit the table, or whose region overflowed in the partition
-// pass, is appended to the failed list and emits nothing (its k-mers are counted by the tier-2 kernel).
-
-constexpr int KEYS_CAP = 4096;                       // k-mers expanded per pass
-constexpr uint32_t NO_SLOT = 0xffffu;
+// One CTA (256 threads, 48 KB of shared memory -> 4 CTAs per SM) per bucket, two block barriers per
+// bucket, no intermediate key array:
+//   probe : thread t owns records t, t+256, ... of the bucket (up to four are fetched into registers
+//           up front, so the global-load latency is paid once per bucket, not inside the loop) and
+//           walks their k-mers with PERSISTENT-LANE probing: every loop iteration is one 64-bit
+//           shared atomicCAS (double hashing); a thread whose key is placed, or found (then a shared
+//           red.add bumps its counter), moves straight on to its next k-mer / next record, so nobody
+//           waits for the longest probe sequence of a warp.  The last warp to finish reserves the
+//           bucket's output range with ONE global atomicAdd.
+//   emit  : the 4096-slot table is scanned two slots per lane (16-byte loads); occupied slots are
+//           written as coalesced 16-byte (k-mer, count) pairs and reset on the spot, so the table is
+//           clean for the next bucket without a separate initialisation pass.
+// Shared memory is addressed through explicit 32-bit shared addresses (ld/st/atom.shared PTX).
+// A bucket whose distinct keys overflow the table, or whose region overflowed in the partition pass,
+// is appended to the failed list and emits nothing (its k-mers are counted by the tier-2 kernel).
 
 __device__ __forceinline__ unsigned long long atoms_cas64(uint32_t a, unsigned long long cmp, unsigned long long val) {
     unsigned long long old;
@@ -236,26 +232,19 @@ __device__ __forceinline__ uint32_t atoms_add32(uint32_t a, uint32_t v) {
 __device__ __forceinline__ void reds_add32(uint32_t a, uint32_t v) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
-__device__ __forceinline__ unsigned long long lds64(uint32_t a) {
-    unsigned long long v;
-    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
-    return v;
-}
-__device__ __forceinline__ void sts64(uint32_t a, unsigned long long v) {
-    asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
-}
 __device__ __forceinline__ uint32_t lds32(uint32_t a) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
     return v;
 }
-__device__ __forceinline__ uint32_t lds16(uint32_t a) {
-    unsigned short v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
-    return v;
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
-__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
-    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
+__device__ __forceinline__ void lds128(uint32_t a, unsigned long long& x, unsigned long long& y) {
+    asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(x), "=l"(y) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t a, unsigned long long v) {
+    asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
 }
 __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
@@ -270,8 +259,38 @@ __device__ __forceinline__ uint32_t leaf_hash(uint64_t key) {
 }
 
 struct LeafCounters {
-    uint32_t nkeys, nwin, arrived, failed, special, pad;
+    uint32_t nwin, arrived, failed, special, cursor, pad;
 };
+
+template <int RECW>
+struct RecRegs {
+    uint64_t hi, lo;
+};
+
+// record g of bucket b in the flattened (segment-major) order; n_src == 1 is the single-GPU layout
+template <int RECW>
+__device__ __forceinline__ void load_record(const Rec<RECW>* __restrict__ recs, const unsigned long long* __restrict__ fill,
+                                            const PartitionPlan& plan, int n_src, uint32_t b, uint32_t g, uint64_t& hi,
+                                            uint64_t& lo) {
+    uint32_t seg = 0;
+    if (n_src > 1) {
+        for (;;) {   // g is below the bucket's total, so this terminates inside the segments
+            uint32_t n = (uint32_t)fill[(uint64_t)seg * plan.n_buckets + b];
+            if (g < n) break;
+            g -= n;
+            seg++;
+        }
+    }
+    const Rec<RECW>* p = recs + ((uint64_t)seg * plan.n_buckets + b) * plan.cap + g;
+    if (RECW == 1) {
+        hi = ld_nc_u64(reinterpret_cast<const uint64_t*>(p));
+        lo = 0;
+    } else {
+        uint4 raw = ld_nc_u128(p);
+        hi = ((uint64_t)raw.y << 32) | raw.x;
+        lo = ((uint64_t)raw.w << 32) | raw.z;
+    }
+}
 
 template <int RECW>
 __global__ void __launch_bounds__(LEAF_THREADS) bucket_count_kernel(PartitionPlan plan, int k,
@@ -283,18 +302,17 @@ __global__ void __launch_bounds__(LEAF_THREADS) bucket_count_kernel(PartitionPla
     // n_src > 1 (sharded counting): bucket b's records arrive as n_src segments, one per source GPU:
     // segment s is recs[(s * n_buckets + b) * cap ..] with fill[s * n_buckets + b].
     extern __shared__ __align__(16) unsigned char leaf_dyn[];
-    // layout: tbl u64[SLOTS] | keys u64[KEYS_CAP] | cnt u32[SLOTS] | slot_of u16[KEYS_CAP]
-    const uint32_t tbl_s = smem_u32(leaf_dyn);
-    const uint32_t keys_s = tbl_s + LEAF_SLOTS * 8;
-    const uint32_t cnt_s = keys_s + KEYS_CAP * 8;
-    const uint32_t slot_s = cnt_s + LEAF_SLOTS * 4;
+    const uint32_t tbl_s = smem_u32(leaf_dyn);                 // u64[LEAF_SLOTS]
+    const uint32_t cnt_s = tbl_s + LEAF_SLOTS * 8;             // u32[LEAF_SLOTS]
     __shared__ unsigned long long s_base[2];
     __shared__ LeafCounters s_ctr[2];          // double-buffered by bucket parity: reset while the other set is live
     const int t = threadIdx.x, lane = t & 31;
     const uint32_t lane_lt = (1u << lane) - 1u;
     const int kshift = 64 - 2 * k;
     unsigned long long special_total = 0, kmers_total = 0;
-    if (t < 2) { s_ctr[t].nkeys = 0; s_ctr[t].nwin = 0; s_ctr[t].arrived = 0; s_ctr[t].failed = 0; s_ctr[t].special = 0; }
+    for (int i = t; i < LEAF_SLOTS / 2; i += LEAF_THREADS) sts128(tbl_s + 16 * i, ~0u, ~0u, ~0u, ~0u);
+    for (int i = t; i < LEAF_SLOTS / 4; i += LEAF_THREADS) sts128(cnt_s + 16 * i, 0u, 0u, 0u, 0u);
+    if (t < 2) { s_ctr[t].nwin = 0; s_ctr[t].arrived = 0; s_ctr[t].failed = 0; s_ctr[t].special = 0; s_ctr[t].cursor = 0; }
     __syncthreads();
     uint32_t par = 0;
 
@@ -308,7 +326,7 @@ __global__ void __launch_bounds__(LEAF_THREADS) bucket_count_kernel(PartitionPla
             seg_overflow |= (uint32_t)f > plan.cap;
         }
         if (nrec_all == 0) continue;                                    // uniform across the CTA
-        if (seg_overflow || nk > KEYS_CAP) {                            // region overflowed / too many k-mers: tier 2
+        if (seg_overflow) {                                             // region overflowed in the partition pass: tier 2
             if (t == 0) {
                 uint32_t idx = (uint32_t)atomicAdd(&status->n_failed, 1ull);
                 failed_ids[idx] = b;
@@ -317,84 +335,64 @@ __global__ void __launch_bounds__(LEAF_THREADS) bucket_count_kernel(PartitionPla
             continue;
         }
         LeafCounters& C = s_ctr[par];
-        const uint32_t nkeys_s = smem_u32(&C.nkeys), nwin_s = smem_u32(&C.nwin), arrived_s = smem_u32(&C.arrived);
-        // table := empty, counters := 0 (16-byte stores); overlaps with the expansion
-        for (int i = t; i < LEAF_SLOTS / 2; i += LEAF_THREADS) sts128(tbl_s + 16 * i, ~0u, ~0u, ~0u, ~0u);
-        for (int i = t; i < LEAF_SLOTS / 4; i += LEAF_THREADS) sts128(cnt_s + 16 * i, 0u, 0u, 0u, 0u);
-        // ---- expand
-        for (int sI = 0; sI < n_src; sI++) {
-        const uint32_t nrec_seg = n_src == 1 ? nrec_all : (uint32_t)fill[(uint64_t)sI * plan.n_buckets + b];
-        const Rec<RECW>* base = recs + ((uint64_t)sI * plan.n_buckets + b) * plan.cap;
-        for (uint32_t r = t; r < nrec_seg; r += LEAF_THREADS) {
-            uint64_t hi, lo = 0;
-            int L;
-            if (RECW == 1) {
-                hi = ld_nc_u64(reinterpret_cast<const uint64_t*>(base) + r);
-                L = (int)(hi & 15u) + 1;
-            } else {
-                uint4 raw = ld_nc_u128(base + r);
-                hi = ((uint64_t)raw.y << 32) | raw.x;
-                lo = ((uint64_t)raw.w << 32) | raw.z;
-                L = (int)(lo & 63u) + 1;
-            }
-            uint32_t a = keys_s + 8 * atoms_add32(nkeys_s, (uint32_t)L);
-            for (int o = 0; o < L; o++, a += 8) {
-                uint64_t win = (RECW == 1 || o == 0) ? (hi << (2 * o)) : ((hi << (2 * o)) | (lo >> (64 - 2 * o)));
-                sts64(a, win >> kshift);
-            }
-        }
-        }
-        __syncthreads();                                                // (A)
-        if (t == 0) {                                                   // the other counter set is idle now: reset it
-            LeafCounters& N = s_ctr[par ^ 1];
-            N.nkeys = 0; N.nwin = 0; N.arrived = 0; N.failed = 0; N.special = 0;
-        }
-        const uint32_t n_keys = C.nkeys;
-        // ---- probe: one CAS per iteration, a finished thread moves on to its next key at once
+        const uint32_t nwin_s = smem_u32(&C.nwin), arrived_s = smem_u32(&C.arrived), cursor_s = smem_u32(&C.cursor);
+        // ---- probe
         uint32_t own = 0, special = 0;
-        {
-            uint32_t i = t;
-            if (i < n_keys) {
-                uint64_t key = lds64(keys_s + 8 * i);
-                uint32_t hf = leaf_hash(key);
-                uint32_t h = hf & (LEAF_SLOTS - 1), step = ((hf >> 12) | 1u) & (LEAF_SLOTS - 1), tries = 0;
-                for (;;) {
-                    uint32_t res = NO_SLOT;                             // slot claimed, or NO_SLOT
-                    bool done = true;
-                    if (key == kEmpty) special++;                       // k == 32, 't'*32: kept out of the table
+        for (uint32_t g0 = t; g0 < nrec_all; g0 += 4 * LEAF_THREADS) {
+            // up to four records of this thread in registers (one global-load latency for all of them)
+            uint64_t rh[4], rl[4];
+            int nrec = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                rh[q] = 0; rl[q] = 0;
+                const uint32_t g = g0 + q * LEAF_THREADS;
+                if (g < nrec_all) { load_record<RECW>(recs, fill, plan, n_src, b, g, rh[q], rl[q]); nrec = q + 1; }
+            }
+            int q = 0, o = 0;
+            uint64_t hi = rh[0], lo = rl[0];
+            int L = (RECW == 1) ? (int)(hi & 15u) + 1 : (int)(lo & 63u) + 1;
+            uint64_t key = hi >> kshift;
+            uint32_t hf = leaf_hash(key);
+            uint32_t h = hf & (LEAF_SLOTS - 1), step = ((hf >> 12) | 1u) & (LEAF_SLOTS - 1), tries = 0;
+            for (;;) {
+                bool done = true;
+                if (key == kEmpty) special++;                           // k == 32, 't'*32: kept out of the table
+                else {
+                    unsigned long long old = atoms_cas64(tbl_s + 8 * h, kEmpty, key);
+                    if (old == kEmpty) own++;
+                    else if (old == key) reds_add32(cnt_s + 4 * h, 1u);
                     else {
-                        unsigned long long old = atoms_cas64(tbl_s + 8 * h, kEmpty, key);
-                        if (old == kEmpty) { res = h; own++; }
-                        else if (old == key) reds_add32(cnt_s + 4 * h, 1u);
-                        else {
-                            h = (h + step) & (LEAF_SLOTS - 1);          // double hashing: odd step visits every slot
-                            done = false;
-                            if (++tries >= LEAF_SLOTS) { C.failed = 1; done = true; }   // table full
-                        }
+                        h = (h + step) & (LEAF_SLOTS - 1);              // double hashing: odd step visits every slot
+                        done = false;
+                        if (++tries >= LEAF_SLOTS) { C.failed = 1; done = true; }   // table full
                     }
-                    if (done) {
-                        sts16(slot_s + 2 * i, res);
-                        i += LEAF_THREADS;
-                        if (i >= n_keys) break;
-                        key = lds64(keys_s + 8 * i);
-                        hf = leaf_hash(key);
-                        h = hf & (LEAF_SLOTS - 1);
-                        step = ((hf >> 12) | 1u) & (LEAF_SLOTS - 1);
-                        tries = 0;
+                }
+                if (done) {
+                    if (++o >= L) {                                     // next record of this thread
+                        if (++q >= nrec) break;
+                        hi = q == 1 ? rh[1] : (q == 2 ? rh[2] : rh[3]);
+                        lo = q == 1 ? rl[1] : (q == 2 ? rl[2] : rl[3]);
+                        L = (RECW == 1) ? (int)(hi & 15u) + 1 : (int)(lo & 63u) + 1;
+                        o = 0;
                     }
+                    const uint64_t win = (RECW == 1 || o == 0) ? (hi << (2 * o)) : ((hi << (2 * o)) | (lo >> (64 - 2 * o)));
+                    key = win >> kshift;
+                    hf = leaf_hash(key);
+                    h = hf & (LEAF_SLOTS - 1);
+                    step = ((hf >> 12) | 1u) & (LEAF_SLOTS - 1);
+                    tries = 0;
                 }
             }
         }
-        // ---- per-warp offsets; the last warp to arrive reserves the bucket's output range
+        // ---- the last warp to arrive reserves the bucket's output range
         __syncwarp();
         for (int d = 16; d; d >>= 1) {
             own += __shfl_xor_sync(0xffffffffu, own, d);
             special += __shfl_xor_sync(0xffffffffu, special, d);
         }
-        uint32_t woff = 0;
         if (lane == 0) {
             if (special) atomicAdd(&C.special, special);
-            woff = atoms_add32(nwin_s, own);
+            atoms_add32(nwin_s, own);
             __threadfence_block();
             if (atoms_add32(arrived_s, 1u) == LEAF_THREADS / 32 - 1) {
                 const uint32_t total = lds32(nwin_s);
@@ -402,35 +400,54 @@ __global__ void __launch_bounds__(LEAF_THREADS) bucket_count_kernel(PartitionPla
                 s_base[par] = (!failed && total) ? atomicAdd(&status->n_distinct, (unsigned long long)total) : 0ull;
             }
         }
-        woff = __shfl_sync(0xffffffffu, woff, 0);
         __syncthreads();                                                // (B)
+        if (t == 0) {                                                   // the other counter set is idle now: reset it
+            LeafCounters& N = s_ctr[par ^ 1];
+            N.nwin = 0; N.arrived = 0; N.failed = 0; N.special = 0; N.cursor = 0;
+        }
         const bool failed = C.failed != 0;
-        if (failed) {
-            if (t == 0) {
+        if (t == 0) {
+            if (failed) {
                 uint32_t idx = (uint32_t)atomicAdd(&status->n_failed, 1ull);
                 failed_ids[idx] = b;
                 atomicAdd(&status->failed_kmers, (unsigned long long)nk);
+            } else {
+                special_total += C.special;
+                kmers_total += nk - C.special;
             }
-        } else {
-            // ---- emit: every warp writes the k-mers its own lanes claimed
-            uint64_t obase = s_base[par] + woff;
-            for (uint32_t i0 = 0; i0 < n_keys; i0 += LEAF_THREADS) {
-                const uint32_t i = i0 + t;
-                const uint32_t sl = i < n_keys ? lds16(slot_s + 2 * i) : NO_SLOT;
-                const bool wv = sl != NO_SLOT;
-                const uint32_t mk = __ballot_sync(0xffffffffu, wv);
-                if (wv) {
-                    const uint64_t idx = obase + __popc(mk & lane_lt);
-                    if (idx < capacity) {
-                        ulonglong2 o; o.x = lds64(tbl_s + 8 * sl); o.y = 1ull + lds32(cnt_s + 4 * sl);
-                        reinterpret_cast<ulonglong2*>(out)[idx] = o;
-                    } else status->out_overflow = 1;
-                }
-                obase += __popc(mk);
-            }
-            if (t == 0) { special_total += C.special; kmers_total += nk - C.special; }
         }
-        __syncthreads();                                                // (D) table and key array are reused by the next bucket
+        // ---- emit + reset: two slots per lane per iteration
+        const unsigned long long obase = s_base[par];
+        for (int i = t; i < LEAF_SLOTS / 2; i += LEAF_THREADS) {
+            unsigned long long k0, k1;
+            lds128(tbl_s + 16 * i, k0, k1);
+            const bool o0 = k0 != kEmpty, o1 = k1 != kEmpty;
+            const uint32_t m0 = __ballot_sync(0xffffffffu, o0), m1 = __ballot_sync(0xffffffffu, o1);
+            if (!(m0 | m1)) continue;
+            uint32_t pos = 0;
+            if (lane == 0) pos = atoms_add32(cursor_s, (uint32_t)(__popc(m0) + __popc(m1)));
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            if (o0 | o1) sts128(tbl_s + 16 * i, ~0u, ~0u, ~0u, ~0u);
+            if (o0) {
+                const uint32_t c = lds32(cnt_s + 8 * i);
+                if (c) sts32(cnt_s + 8 * i, 0u);
+                const uint64_t idx = obase + pos + __popc(m0 & lane_lt);
+                if (!failed) {
+                    if (idx < capacity) { ulonglong2 v; v.x = k0; v.y = 1ull + c; reinterpret_cast<ulonglong2*>(out)[idx] = v; }
+                    else status->out_overflow = 1;
+                }
+            }
+            if (o1) {
+                const uint32_t c = lds32(cnt_s + 8 * i + 4);
+                if (c) sts32(cnt_s + 8 * i + 4, 0u);
+                const uint64_t idx = obase + pos + __popc(m0) + __popc(m1 & lane_lt);
+                if (!failed) {
+                    if (idx < capacity) { ulonglong2 v; v.x = k1; v.y = 1ull + c; reinterpret_cast<ulonglong2*>(out)[idx] = v; }
+                    else status->out_overflow = 1;
+                }
+            }
+        }
+        __syncthreads();                                                // (D) the table is clean again
         par ^= 1;
     }
     if (t == 0) {
@@ -555,8 +572,8 @@ void launch_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPl
 void launch_bucket_count(const DeviceInfo& di, const PartitionPlan& p, int k, int n_src, const unsigned long long* d_fill,
                          const void* d_recs, uint32_t* d_failed_ids, kmer_count_pair* d_pairs, uint64_t capacity,
                          DevStatus* d_status, cudaStream_t st) {
-    const size_t leaf_smem = LEAF_SLOTS * (8 + 4) + KEYS_CAP * (8 + 2);   // 32 + 16 + 32 + 8 = 88 KB
-    uint64_t lgrid = (uint64_t)di.sm_count * 2;
+    const size_t leaf_smem = LEAF_SLOTS * (8 + 4);   // 32 + 16 = 48 KB -> 4 CTAs per SM
+    uint64_t lgrid = (uint64_t)di.sm_count * 4;
     if (lgrid > p.n_buckets) lgrid = p.n_buckets;
     if (!lgrid) return;
     if (p.recw == 1) {
