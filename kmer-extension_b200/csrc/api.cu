@@ -692,7 +692,7 @@ extern "C" int kmer_cuda_dev_finish(kmer_cuda_ctx* c, void* stream, kmer_dev_res
 // sharded counting (the caller owns the exchange)
 
 extern "C" int kmer_cuda_shard_plan(uint64_t total_kmers, int k, uint32_t n_ranks, kmer_shard_plan* plan) {
-    if (!plan || n_ranks < 1 || k < 14 || k > KMER_CUDA_MAX_K) return KMER_ERR_BAD_ARGUMENT;
+    if (!plan || n_ranks < 1 || n_ranks > 16 || k < 14 || k > KMER_CUDA_MAX_K) return KMER_ERR_BAD_ARGUMENT;
     PartitionPlan p = make_partition_plan(total_kmers, k);
     memset(plan, 0, sizeof(*plan));
     plan->n_ranks = n_ranks;
@@ -708,7 +708,7 @@ extern "C" int kmer_cuda_shard_plan(uint64_t total_kmers, int k, uint32_t n_rank
         double rpk = 2.0 / (p.w + 1) + 1.0 / 16.0 + (p.rmax < p.w ? 1.0 / p.rmax : 0.0);
         double mean = kmers_per_bucket * rpk / n_ranks;
         double cap = 1.35 * mean + 6.0 * sqrt(2.0 * mean) + 16.0;
-        plan->cap = (uint32_t)cap;
+        plan->cap = ((uint32_t)cap + 1u) & ~1u;   // even: every (bucket, source) segment starts 16-byte aligned
     }
     plan->recs_bytes_per_peer = (uint64_t)plan->buckets_per_rank * plan->cap * plan->rec_bytes;
     plan->fill_bytes_per_peer = (uint64_t)plan->buckets_per_rank * 8;

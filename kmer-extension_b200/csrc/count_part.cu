@@ -203,21 +203,28 @@ __global__ void __launch_bounds__(NT) partition_kernel(ScanArgs a, PartitionPlan
 // ---------------------------------------------------------------------------------------------
 // per-bucket counting
 //
-// One CTA (256 threads, 48 KB of shared memory -> 4 CTAs per SM) per bucket, two block barriers per
-// bucket, no intermediate key array:
-//   probe : thread t owns records t, t+256, ... of the bucket (up to four are fetched into registers
-//           up front, so the global-load latency is paid once per bucket, not inside the loop) and
-//           walks their k-mers with PERSISTENT-LANE probing: every loop iteration is one 64-bit
-//           shared atomicCAS (double hashing); a thread whose key is placed, or found (then a shared
-//           red.add bumps its counter), moves straight on to its next k-mer / next record, so nobody
-//           waits for the longest probe sequence of a warp.  The last warp to finish reserves the
-//           bucket's output range with ONE global atomicAdd.
-//   emit  : the 4096-slot table is scanned two slots per lane (16-byte loads); occupied slots are
-//           written as coalesced 16-byte (k-mer, count) pairs and reset on the spot, so the table is
-//           clean for the next bucket without a separate initialisation pass.
+// One CTA (256 threads) per bucket, two block barriers per bucket:
+//   stage : the bucket's record region (contiguous in HBM) is brought to shared memory by the TMA
+//           engine (cp.async.bulk + mbarrier).  The copy for bucket i+1 is issued as soon as the probe
+//           phase of bucket i is over, so it lands behind the emit phase.
+//   probe : warp w owns the records [w*chunk, (w+1)*chunk) of the bucket and hands them to its lanes
+//           DYNAMICALLY: whenever a lane has finished the k-mers of its record it takes the warp's next
+//           record (a ballot + popc on a warp-uniform register cursor: no atomics, no idle lanes while
+//           records remain).  Every loop iteration is one 64-bit shared atomicCAS per lane (double
+//           hashing); a lane whose key is placed or found moves straight on to its next k-mer.
+//           k <= 26: the count lives in the 12 spare top bits of the key word (a bucket holds at most
+//           LEAF_MAX_KMERS < 4096 k-mers), so a duplicate is one 64-bit shared add on the same word.
+//           k >= 27: a separate 32-bit counter array.
+//           A bucket holds fewer k-mers than the table has slots, so a probe sequence (odd step) always
+//           terminates; buckets above LEAF_MAX_KMERS, or whose region overflowed, go to tier 2 up front.
+//   emit  : the table is scanned two slots per lane (16-byte loads); occupied slots are written as
+//           coalesced 16-byte (k-mer, count) pairs and reset on the spot.  The last warp to finish the
+//           probe phase reserves the bucket's output range with ONE global atomicAdd.
 // Shared memory is addressed through explicit 32-bit shared addresses (ld/st/atom.shared PTX).
-// A bucket whose distinct keys overflow the table, or whose region overflowed in the partition pass,
-// is appended to the failed list and emits nothing (its k-mers are counted by the tier-2 kernel).
+
+constexpr uint32_t LEAF_MAX_KMERS = 3840;
+constexpr int LEAF_WARPS = LEAF_THREADS / 32;
+constexpr int MAX_SRC = 16;           // source GPUs a sharded bucket may be assembled from
 
 __device__ __forceinline__ unsigned long long atoms_cas64(uint32_t a, unsigned long long cmp, unsigned long long val) {
     unsigned long long old;
@@ -232,9 +239,17 @@ __device__ __forceinline__ uint32_t atoms_add32(uint32_t a, uint32_t v) {
 __device__ __forceinline__ void reds_add32(uint32_t a, uint32_t v) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
+__device__ __forceinline__ void reds_add64(uint32_t a, unsigned long long v) {
+    asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t lds32(uint32_t a) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long lds64(uint32_t a) {
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
     return v;
 }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
@@ -243,11 +258,19 @@ __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
 __device__ __forceinline__ void lds128(uint32_t a, unsigned long long& x, unsigned long long& y) {
     asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(x), "=l"(y) : "r"(a) : "memory");
 }
-__device__ __forceinline__ void sts64(uint32_t a, unsigned long long v) {
-    asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
-}
 __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LEAF_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LEAF_DONE;\n"
+        "bra LEAF_WAIT;\n"
+        "LEAF_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
 __device__ __forceinline__ uint32_t leaf_hash(uint64_t key) {
@@ -259,162 +282,200 @@ __device__ __forceinline__ uint32_t leaf_hash(uint64_t key) {
 }
 
 struct LeafCounters {
-    uint32_t nwin, arrived, failed, special, cursor, pad;
+    uint32_t nwin, arrived, special, cursor;
 };
 
-template <int RECW>
-struct RecRegs {
-    uint64_t hi, lo;
+struct BucketInfo {
+    uint32_t nrec, nk;
+    bool overflow;
+    __device__ __forceinline__ bool usable() const { return nrec != 0 && !overflow && nk <= LEAF_MAX_KMERS; }
 };
 
-// record g of bucket b in the flattened (segment-major) order; n_src == 1 is the single-GPU layout
-template <int RECW>
-__device__ __forceinline__ void load_record(const Rec<RECW>* __restrict__ recs, const unsigned long long* __restrict__ fill,
-                                            const PartitionPlan& plan, int n_src, uint32_t b, uint32_t g, uint64_t& hi,
-                                            uint64_t& lo) {
-    uint32_t seg = 0;
-    if (n_src > 1) {
-        for (;;) {   // g is below the bucket's total, so this terminates inside the segments
-            uint32_t n = (uint32_t)fill[(uint64_t)seg * plan.n_buckets + b];
-            if (g < n) break;
-            g -= n;
-            seg++;
-        }
+// sharded counting (n_src > 1): bucket b's records arrive as n_src segments, one per source GPU:
+// segment s is recs[(s * n_buckets + b) * cap ..] with fill[s * n_buckets + b].
+template <bool MULTI>
+__device__ __forceinline__ BucketInfo bucket_info(const unsigned long long* __restrict__ fill, const PartitionPlan& plan,
+                                                  int n_src_, uint32_t b) {
+    BucketInfo bi;
+    bi.nrec = 0; bi.nk = 0; bi.overflow = false;
+    const int n_src = MULTI ? n_src_ : 1;
+#pragma unroll 1
+    for (int sI = 0; sI < n_src; sI++) {
+        const unsigned long long f = fill[(uint64_t)sI * plan.n_buckets + b];
+        bi.nrec += (uint32_t)f;
+        bi.nk += (uint32_t)(f >> 32);
+        bi.overflow |= (uint32_t)f > plan.cap;
     }
-    const Rec<RECW>* p = recs + ((uint64_t)seg * plan.n_buckets + b) * plan.cap + g;
-    if (RECW == 1) {
-        hi = ld_nc_u64(reinterpret_cast<const uint64_t*>(p));
-        lo = 0;
-    } else {
-        uint4 raw = ld_nc_u128(p);
-        hi = ((uint64_t)raw.y << 32) | raw.x;
-        lo = ((uint64_t)raw.w << 32) | raw.z;
-    }
+    return bi;
 }
 
-template <int RECW>
-__global__ void __launch_bounds__(LEAF_THREADS) bucket_count_kernel(PartitionPlan plan, int k,
-                                                                    const unsigned long long* __restrict__ fill,
-                                                                    const Rec<RECW>* __restrict__ recs,
-                                                                    kmer_count_pair* __restrict__ out, uint64_t capacity,
-                                                                    uint32_t* __restrict__ failed_ids, DevStatus* status,
-                                                                    int n_src) {
-    // n_src > 1 (sharded counting): bucket b's records arrive as n_src segments, one per source GPU:
-    // segment s is recs[(s * n_buckets + b) * cap ..] with fill[s * n_buckets + b].
+template <int RECW, bool MULTI>
+__global__ void __launch_bounds__(LEAF_THREADS, 4) bucket_count_kernel(PartitionPlan plan, int k,
+                                                                       const unsigned long long* __restrict__ fill,
+                                                                       const Rec<RECW>* __restrict__ recs,
+                                                                       kmer_count_pair* __restrict__ out, uint64_t capacity,
+                                                                       uint32_t* __restrict__ failed_ids, DevStatus* status,
+                                                                       int n_src_) {
+    const int n_src = MULTI ? n_src_ : 1;                     // MULTI: sharded counting, one segment per source GPU
+    constexpr bool PACKED = RECW == 1;                        // count in bits 63..52 of the key word (k <= 26)
+    constexpr uint32_t RECB = RECW * 8;
+    constexpr uint64_t KEYMASK = PACKED ? ((1ull << 52) - 1ull) : ~0ull;
     extern __shared__ __align__(16) unsigned char leaf_dyn[];
-    const uint32_t tbl_s = smem_u32(leaf_dyn);                 // u64[LEAF_SLOTS]
-    const uint32_t cnt_s = tbl_s + LEAF_SLOTS * 8;             // u32[LEAF_SLOTS]
+    uint32_t tbl_s = smem_u32(leaf_dyn);                                       // u64[LEAF_SLOTS]
+    asm volatile("" : "+r"(tbl_s));                                            // keep it in a register (no rematerialisation)
+    const uint32_t cnt_s = tbl_s + LEAF_SLOTS * 8;                             // u32[LEAF_SLOTS]   (k >= 27 only)
+    const uint32_t rec_s = cnt_s + (PACKED ? 0 : LEAF_SLOTS * 4);             // staged records
+    __shared__ __align__(8) uint64_t s_mbar;
     __shared__ unsigned long long s_base[2];
     __shared__ LeafCounters s_ctr[2];          // double-buffered by bucket parity: reset while the other set is live
-    const int t = threadIdx.x, lane = t & 31;
+    __shared__ uint32_t s_seg_cum[MAX_SRC + 1], s_seg_off[MAX_SRC + 1];        // n_src > 1: record prefix / staged offset
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint32_t lane_lt = (1u << lane) - 1u;
     const int kshift = 64 - 2 * k;
+    const uint32_t mbar_s = smem_u32(&s_mbar);
     unsigned long long special_total = 0, kmers_total = 0;
     for (int i = t; i < LEAF_SLOTS / 2; i += LEAF_THREADS) sts128(tbl_s + 16 * i, ~0u, ~0u, ~0u, ~0u);
-    for (int i = t; i < LEAF_SLOTS / 4; i += LEAF_THREADS) sts128(cnt_s + 16 * i, 0u, 0u, 0u, 0u);
-    if (t < 2) { s_ctr[t].nwin = 0; s_ctr[t].arrived = 0; s_ctr[t].failed = 0; s_ctr[t].special = 0; s_ctr[t].cursor = 0; }
+    if (!PACKED)
+        for (int i = t; i < LEAF_SLOTS / 4; i += LEAF_THREADS) sts128(cnt_s + 16 * i, 0u, 0u, 0u, 0u);
+    if (t < 2) { s_ctr[t].nwin = 0; s_ctr[t].arrived = 0; s_ctr[t].special = 0; s_ctr[t].cursor = 0; }
+    if (t == 0) { mbar_init(&s_mbar, 1); mbar_fence_init(); }
     __syncthreads();
-    uint32_t par = 0;
+
+    // thread 0: start the bulk copies of bucket b's records (every segment padded to 16 bytes)
+    auto issue = [&](uint32_t b) {
+        uint32_t off = 0, cum = 0, bytes = 0;
+#pragma unroll 1
+        for (int sI = 0; sI < n_src; sI++) {
+            const uint32_t n = (uint32_t)fill[(uint64_t)sI * plan.n_buckets + b];
+            if (MULTI) { s_seg_cum[sI] = cum; s_seg_off[sI] = off; }
+            cum += n;
+            const uint32_t nb = (n * RECB + 15u) & ~15u;
+            off += nb / RECB;
+            bytes += nb;
+        }
+        if (MULTI) s_seg_cum[n_src] = cum;
+        mbar_arrive_expect_tx(&s_mbar, bytes);
+        off = 0;
+#pragma unroll 1
+        for (int sI = 0; sI < n_src; sI++) {
+            const uint32_t n = (uint32_t)fill[(uint64_t)sI * plan.n_buckets + b];
+            const uint32_t nb = (n * RECB + 15u) & ~15u;
+            if (nb) {
+                const Rec<RECW>* src = recs + ((uint64_t)sI * plan.n_buckets + b) * plan.cap;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 rec_s + off * RECB),
+                             "l"(src), "r"(nb), "r"(mbar_s)
+                             : "memory");
+            }
+            off += nb / RECB;
+        }
+    };
+
+    uint32_t par = 0, phase = 0;
+    BucketInfo cur;
+    cur.nrec = 0; cur.nk = 0; cur.overflow = false;
+    if (blockIdx.x < plan.n_buckets) cur = bucket_info<MULTI>(fill, plan, n_src, blockIdx.x);
+    if (t == 0 && cur.usable()) issue(blockIdx.x);
 
     for (uint32_t b = blockIdx.x; b < plan.n_buckets; b += gridDim.x) {
-        uint32_t nrec_all = 0, nk = 0;
-        bool seg_overflow = false;
-        for (int sI = 0; sI < n_src; sI++) {
-            const unsigned long long f = fill[(uint64_t)sI * plan.n_buckets + b];
-            nrec_all += (uint32_t)f;
-            nk += (uint32_t)(f >> 32);
-            seg_overflow |= (uint32_t)f > plan.cap;
-        }
-        if (nrec_all == 0) continue;                                    // uniform across the CTA
-        if (seg_overflow) {                                             // region overflowed in the partition pass: tier 2
+        const uint32_t b_next = b + gridDim.x;
+        BucketInfo nxt;
+        nxt.nrec = 0; nxt.nk = 0; nxt.overflow = false;
+        if (b_next < plan.n_buckets) nxt = bucket_info<MULTI>(fill, plan, n_src, b_next);   // in flight during the probe phase
+        if (!cur.usable()) {                                            // uniform across the CTA
             if (t == 0) {
-                uint32_t idx = (uint32_t)atomicAdd(&status->n_failed, 1ull);
-                failed_ids[idx] = b;
-                atomicAdd(&status->failed_kmers, (unsigned long long)nk);
+                if (cur.nrec) {                                         // does not fit on chip: tier 2
+                    uint32_t idx = (uint32_t)atomicAdd(&status->n_failed, 1ull);
+                    failed_ids[idx] = b;
+                    atomicAdd(&status->failed_kmers, (unsigned long long)cur.nk);
+                }
+                if (nxt.usable()) issue(b_next);
             }
+            cur = nxt;
             continue;
         }
         LeafCounters& C = s_ctr[par];
         const uint32_t nwin_s = smem_u32(&C.nwin), arrived_s = smem_u32(&C.arrived), cursor_s = smem_u32(&C.cursor);
+        mbar_wait_s(mbar_s, phase);
+        phase ^= 1u;
         // ---- probe
-        uint32_t own = 0, special = 0;
-        for (uint32_t g0 = t; g0 < nrec_all; g0 += 4 * LEAF_THREADS) {
-            // up to four records of this thread in registers (one global-load latency for all of them)
-            uint64_t rh[4], rl[4];
-            int nrec = 0;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                rh[q] = 0; rl[q] = 0;
-                const uint32_t g = g0 + q * LEAF_THREADS;
-                if (g < nrec_all) { load_record<RECW>(recs, fill, plan, n_src, b, g, rh[q], rl[q]); nrec = q + 1; }
-            }
-            int q = 0, o = 0;
-            uint64_t hi = rh[0], lo = rl[0];
-            int L = (RECW == 1) ? (int)(hi & 15u) + 1 : (int)(lo & 63u) + 1;
-            uint64_t key = hi >> kshift;
-            uint32_t hf = leaf_hash(key);
-            uint32_t h = hf & (LEAF_SLOTS - 1), step = ((hf >> 12) | 1u) & (LEAF_SLOTS - 1), tries = 0;
-            for (;;) {
-                bool done = true;
-                if (key == kEmpty) special++;                           // k == 32, 't'*32: kept out of the table
-                else {
-                    unsigned long long old = atoms_cas64(tbl_s + 8 * h, kEmpty, key);
-                    if (old == kEmpty) own++;
-                    else if (old == key) reds_add32(cnt_s + 4 * h, 1u);
-                    else {
-                        h = (h + step) & (LEAF_SLOTS - 1);              // double hashing: odd step visits every slot
-                        done = false;
-                        if (++tries >= LEAF_SLOTS) { C.failed = 1; done = true; }   // table full
+        const uint32_t nrec = cur.nrec;
+        const uint32_t chunk = (nrec + LEAF_WARPS - 1) / LEAF_WARPS;
+        uint32_t next = warp * chunk;
+        const uint32_t end = min(next + chunk, nrec);
+        uint32_t rem = 0, tries = 0, own = 0, special = 0;             // rem: k-mers left in this lane's record
+        unsigned long long hi = 0, lo = 0;                              // the record, shifted so the current window is on top
+        for (;;) {
+            const uint32_t m = __ballot_sync(0xffffffffu, rem == 0);
+            if (m) {                                                    // hand the warp's next records to the idle lanes
+                uint32_t idx = next + __popc(m & lane_lt);
+                next += __popc(m);
+                if (rem == 0 && idx < end) {
+                    if (MULTI) {
+                        int sI = 0;
+                        while (idx >= s_seg_cum[sI + 1]) sI++;
+                        idx = idx - s_seg_cum[sI] + s_seg_off[sI];
                     }
-                }
-                if (done) {
-                    if (++o >= L) {                                     // next record of this thread
-                        if (++q >= nrec) break;
-                        hi = q == 1 ? rh[1] : (q == 2 ? rh[2] : rh[3]);
-                        lo = q == 1 ? rl[1] : (q == 2 ? rl[2] : rl[3]);
-                        L = (RECW == 1) ? (int)(hi & 15u) + 1 : (int)(lo & 63u) + 1;
-                        o = 0;
+                    if (RECW == 1) {
+                        hi = lds64(rec_s + 8 * idx);
+                        rem = (uint32_t)(hi & 15u) + 1;
+                    } else {
+                        lds128(rec_s + 16 * idx, hi, lo);
+                        rem = (uint32_t)(lo & 63u) + 1;
                     }
-                    const uint64_t win = (RECW == 1 || o == 0) ? (hi << (2 * o)) : ((hi << (2 * o)) | (lo >> (64 - 2 * o)));
-                    key = win >> kshift;
-                    hf = leaf_hash(key);
-                    h = hf & (LEAF_SLOTS - 1);
-                    step = ((hf >> 12) | 1u) & (LEAF_SLOTS - 1);
                     tries = 0;
                 }
             }
+            if (__all_sync(0xffffffffu, rem == 0)) break;               // the warp's records are exhausted
+            const uint64_t key = hi >> kshift;
+            const uint32_t x = (uint32_t)key * 0x9E3779B1u + (uint32_t)(key >> 32) * 0x85EBCA6Bu;
+            const uint32_t step = (x >> 7) | 1u;                        // double hashing: an odd step visits every slot
+            const uint32_t slot = tbl_s + 8 * (((x >> 20) + tries * step) & (LEAF_SLOTS - 1));
+            if (rem) {
+                bool adv;
+                if (RECW == 2 && key == kEmpty) {                       // k == 32, 't'*32: kept out of the table
+                    special++;
+                    adv = true;
+                } else {
+                    const unsigned long long old = atoms_cas64(slot, kEmpty, key);
+                    const bool won = old == kEmpty;
+                    const bool dup = (old & KEYMASK) == key;           // (never true together with won)
+                    own += won;
+                    if (dup) {
+                        if (PACKED) reds_add64(slot, 1ull << 52);
+                        else reds_add32(cnt_s + ((slot - tbl_s) >> 1), 1u);
+                    }
+                    adv = won | dup;
+                }
+                if (adv) {
+                    hi = (hi << 2) | (RECW == 2 ? (lo >> 62) : 0ull);
+                    if (RECW == 2) lo <<= 2;
+                    rem--;
+                    tries = 0;
+                } else tries++;
+            }
         }
         // ---- the last warp to arrive reserves the bucket's output range
-        __syncwarp();
         for (int d = 16; d; d >>= 1) {
             own += __shfl_xor_sync(0xffffffffu, own, d);
-            special += __shfl_xor_sync(0xffffffffu, special, d);
+            if (RECW == 2) special += __shfl_xor_sync(0xffffffffu, special, d);
         }
         if (lane == 0) {
-            if (special) atomicAdd(&C.special, special);
+            if (RECW == 2 && special) atomicAdd(&C.special, special);
             atoms_add32(nwin_s, own);
             __threadfence_block();
-            if (atoms_add32(arrived_s, 1u) == LEAF_THREADS / 32 - 1) {
+            if (atoms_add32(arrived_s, 1u) == LEAF_WARPS - 1) {
                 const uint32_t total = lds32(nwin_s);
-                const bool failed = *reinterpret_cast<volatile uint32_t*>(&C.failed) != 0;
-                s_base[par] = (!failed && total) ? atomicAdd(&status->n_distinct, (unsigned long long)total) : 0ull;
+                s_base[par] = total ? atomicAdd(&status->n_distinct, (unsigned long long)total) : 0ull;
             }
         }
-        __syncthreads();                                                // (B)
-        if (t == 0) {                                                   // the other counter set is idle now: reset it
-            LeafCounters& N = s_ctr[par ^ 1];
-            N.nwin = 0; N.arrived = 0; N.failed = 0; N.special = 0; N.cursor = 0;
-        }
-        const bool failed = C.failed != 0;
+        __syncthreads();                                                // (B) probing done: the record buffer is free
         if (t == 0) {
-            if (failed) {
-                uint32_t idx = (uint32_t)atomicAdd(&status->n_failed, 1ull);
-                failed_ids[idx] = b;
-                atomicAdd(&status->failed_kmers, (unsigned long long)nk);
-            } else {
-                special_total += C.special;
-                kmers_total += nk - C.special;
-            }
+            if (nxt.usable()) issue(b_next);
+            LeafCounters& N = s_ctr[par ^ 1];                           // the other counter set is idle now: reset it
+            N.nwin = 0; N.arrived = 0; N.special = 0; N.cursor = 0;
+            special_total += C.special;
+            kmers_total += cur.nk - C.special;
         }
         // ---- emit + reset: two slots per lane per iteration
         const unsigned long long obase = s_base[par];
@@ -429,26 +490,31 @@ __global__ void __launch_bounds__(LEAF_THREADS) bucket_count_kernel(PartitionPla
             pos = __shfl_sync(0xffffffffu, pos, 0);
             if (o0 | o1) sts128(tbl_s + 16 * i, ~0u, ~0u, ~0u, ~0u);
             if (o0) {
-                const uint32_t c = lds32(cnt_s + 8 * i);
-                if (c) sts32(cnt_s + 8 * i, 0u);
-                const uint64_t idx = obase + pos + __popc(m0 & lane_lt);
-                if (!failed) {
-                    if (idx < capacity) { ulonglong2 v; v.x = k0; v.y = 1ull + c; reinterpret_cast<ulonglong2*>(out)[idx] = v; }
-                    else status->out_overflow = 1;
+                uint64_t c;
+                if (PACKED) c = k0 >> 52;
+                else {
+                    c = lds32(cnt_s + 8 * i);
+                    if (c) sts32(cnt_s + 8 * i, 0u);
                 }
+                const uint64_t idx = obase + pos + __popc(m0 & lane_lt);
+                if (idx < capacity) { ulonglong2 v; v.x = k0 & KEYMASK; v.y = 1ull + c; reinterpret_cast<ulonglong2*>(out)[idx] = v; }
+                else status->out_overflow = 1;
             }
             if (o1) {
-                const uint32_t c = lds32(cnt_s + 8 * i + 4);
-                if (c) sts32(cnt_s + 8 * i + 4, 0u);
-                const uint64_t idx = obase + pos + __popc(m0) + __popc(m1 & lane_lt);
-                if (!failed) {
-                    if (idx < capacity) { ulonglong2 v; v.x = k1; v.y = 1ull + c; reinterpret_cast<ulonglong2*>(out)[idx] = v; }
-                    else status->out_overflow = 1;
+                uint64_t c;
+                if (PACKED) c = k1 >> 52;
+                else {
+                    c = lds32(cnt_s + 8 * i + 4);
+                    if (c) sts32(cnt_s + 8 * i + 4, 0u);
                 }
+                const uint64_t idx = obase + pos + __popc(m0) + __popc(m1 & lane_lt);
+                if (idx < capacity) { ulonglong2 v; v.x = k1 & KEYMASK; v.y = 1ull + c; reinterpret_cast<ulonglong2*>(out)[idx] = v; }
+                else status->out_overflow = 1;
             }
         }
         __syncthreads();                                                // (D) the table is clean again
         par ^= 1;
+        cur = nxt;
     }
     if (t == 0) {
         if (special_total) atomicAdd(&status->special_count, special_total);
@@ -569,24 +635,40 @@ void launch_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPl
 }
 
 // p.n_buckets = buckets counted HERE (all of them on one GPU, the owned range when sharded)
+size_t leaf_smem_bytes(const PartitionPlan& p, int n_src) {
+    const size_t recb = p.recw == 1 ? 8 : 16;
+    size_t table = (size_t)LEAF_SLOTS * 8 + (p.recw == 1 ? 0 : (size_t)LEAF_SLOTS * 4);
+    size_t staged = ((size_t)p.cap * n_src + 2 * (size_t)n_src) * recb;   // every segment padded to 16 bytes
+    return table + ((staged + 15) & ~(size_t)15);
+}
+
 void launch_bucket_count(const DeviceInfo& di, const PartitionPlan& p, int k, int n_src, const unsigned long long* d_fill,
                          const void* d_recs, uint32_t* d_failed_ids, kmer_count_pair* d_pairs, uint64_t capacity,
                          DevStatus* d_status, cudaStream_t st) {
-    const size_t leaf_smem = LEAF_SLOTS * (8 + 4);   // 32 + 16 = 48 KB -> 4 CTAs per SM
-    uint64_t lgrid = (uint64_t)di.sm_count * 4;
+    const size_t leaf_smem = leaf_smem_bytes(p, n_src);
+    int per_sm = (int)((size_t)227 * 1024 / (leaf_smem + 1024));
+    static const char* env_ctas = getenv("KMER_CUDA_LEAF_CTAS");   // profiling experiments only
+    int max_per_sm = env_ctas ? atoi(env_ctas) : 5;
+    if (per_sm > max_per_sm) per_sm = max_per_sm;
+    if (per_sm < 1) per_sm = 1;
+    uint64_t lgrid = (uint64_t)di.sm_count * per_sm;
     if (lgrid > p.n_buckets) lgrid = p.n_buckets;
     if (!lgrid) return;
+#define KMER_LEAF_LAUNCH(RW, MU)                                                                                              \
+    do {                                                                                                                      \
+        cudaFuncSetAttribute(bucket_count_kernel<RW, MU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leaf_smem);       \
+        cudaFuncSetAttribute(bucket_count_kernel<RW, MU>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);               \
+        bucket_count_kernel<RW, MU><<<(unsigned)lgrid, LEAF_THREADS, leaf_smem, st>>>(                                        \
+            p, k, d_fill, (const Rec<RW>*)d_recs, d_pairs, capacity, d_failed_ids, d_status, n_src);                          \
+    } while (0)
     if (p.recw == 1) {
-        cudaFuncSetAttribute(bucket_count_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leaf_smem);
-        cudaFuncSetAttribute(bucket_count_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        bucket_count_kernel<1><<<(unsigned)lgrid, LEAF_THREADS, leaf_smem, st>>>(p, k, d_fill, (const Rec<1>*)d_recs, d_pairs,
-                                                                                capacity, d_failed_ids, d_status, n_src);
+        if (n_src > 1) KMER_LEAF_LAUNCH(1, true);
+        else KMER_LEAF_LAUNCH(1, false);
     } else {
-        cudaFuncSetAttribute(bucket_count_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leaf_smem);
-        cudaFuncSetAttribute(bucket_count_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        bucket_count_kernel<2><<<(unsigned)lgrid, LEAF_THREADS, leaf_smem, st>>>(p, k, d_fill, (const Rec<2>*)d_recs, d_pairs,
-                                                                                capacity, d_failed_ids, d_status, n_src);
+        if (n_src > 1) KMER_LEAF_LAUNCH(2, true);
+        else KMER_LEAF_LAUNCH(2, false);
     }
+#undef KMER_LEAF_LAUNCH
 }
 
 void launch_count_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPlan& p, unsigned long long* d_fill,
