@@ -252,8 +252,19 @@ __device__ __forceinline__ unsigned long long lds64(uint32_t a) {
     asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
     return v;
 }
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory");
+}
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t a, unsigned long long v) {
+    asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
 }
 __device__ __forceinline__ void lds128(uint32_t a, unsigned long long& x, unsigned long long& y) {
     asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(x), "=l"(y) : "r"(a) : "memory");
@@ -280,10 +291,6 @@ __device__ __forceinline__ uint32_t leaf_hash(uint64_t key) {
     h ^= h >> 13;
     return h;
 }
-
-struct LeafCounters {
-    uint32_t nwin, arrived, special, cursor;
-};
 
 struct BucketInfo {
     uint32_t nrec, nk;
@@ -324,11 +331,11 @@ __global__ void __launch_bounds__(LEAF_THREADS, 4) bucket_count_kernel(Partition
     uint32_t tbl_s = smem_u32(leaf_dyn);                                       // u64[LEAF_SLOTS]
     asm volatile("" : "+r"(tbl_s));                                            // keep it in a register (no rematerialisation)
     const uint32_t cnt_s = tbl_s + LEAF_SLOTS * 8;                             // u32[LEAF_SLOTS]   (k >= 27 only)
-    const uint32_t rec_s = cnt_s + (PACKED ? 0 : LEAF_SLOTS * 4);             // staged records
+    const uint32_t desc_s = cnt_s + (PACKED ? 0 : LEAF_SLOTS * 4);            // u16[LEAF_MAX_KMERS] k-mer descriptors
+    const uint32_t rec_s = desc_s + LEAF_MAX_KMERS * 2;                        // staged records
     __shared__ __align__(8) uint64_t s_mbar;
-    __shared__ unsigned long long s_base[2];
-    __shared__ LeafCounters s_ctr[2];          // double-buffered by bucket parity: reset while the other set is live
     __shared__ uint32_t s_seg_cum[MAX_SRC + 1], s_seg_off[MAX_SRC + 1];        // n_src > 1: record prefix / staged offset
+    __shared__ uint32_t s_wtot[2][LEAF_WARPS];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint32_t lane_lt = (1u << lane) - 1u;
     const int kshift = 64 - 2 * k;
@@ -337,7 +344,6 @@ __global__ void __launch_bounds__(LEAF_THREADS, 4) bucket_count_kernel(Partition
     for (int i = t; i < LEAF_SLOTS / 2; i += LEAF_THREADS) sts128(tbl_s + 16 * i, ~0u, ~0u, ~0u, ~0u);
     if (!PACKED)
         for (int i = t; i < LEAF_SLOTS / 4; i += LEAF_THREADS) sts128(cnt_s + 16 * i, 0u, 0u, 0u, 0u);
-    if (t < 2) { s_ctr[t].nwin = 0; s_ctr[t].arrived = 0; s_ctr[t].special = 0; s_ctr[t].cursor = 0; }
     if (t == 0) { mbar_init(&s_mbar, 1); mbar_fence_init(); }
     __syncthreads();
 
@@ -394,132 +400,143 @@ __global__ void __launch_bounds__(LEAF_THREADS, 4) bucket_count_kernel(Partition
             cur = nxt;
             continue;
         }
-        LeafCounters& C = s_ctr[par];
-        const uint32_t nwin_s = smem_u32(&C.nwin), arrived_s = smem_u32(&C.arrived), cursor_s = smem_u32(&C.cursor);
         mbar_wait_s(mbar_s, phase);
         phase ^= 1u;
-        // ---- probe
+        // ---- expand: k-mer j of the bucket -> descriptor (staged record << 4 | window), so that the probe phase can
+        //      hand out single k-mers (records hold 1..16 of them; handing out whole records leaves most lanes idle
+        //      while the longest records finish).  Thread t lists the k-mers of records t, t+256, ...
         const uint32_t nrec = cur.nrec;
-        const uint32_t chunk = (nrec + LEAF_WARPS - 1) / LEAF_WARPS;
-        uint32_t next = warp * chunk;
-        const uint32_t end = min(next + chunk, nrec);
-        uint32_t rem = 0, tries = 0, own = 0, special = 0;             // rem: k-mers left in this lane's record
-        unsigned long long hi = 0, lo = 0;                              // the record, shifted so the current window is on top
+        uint32_t mysum = 0;
+        for (uint32_t r = t; r < nrec; r += LEAF_THREADS) {
+            uint32_t pos = r;
+            if (MULTI) {
+                int sI = 0;
+                while (r >= s_seg_cum[sI + 1]) sI++;
+                pos = r - s_seg_cum[sI] + s_seg_off[sI];
+            }
+            mysum += (RECW == 1 ? (lds32(rec_s + 8 * pos) & 15u) : (lds32(rec_s + 16 * pos + 8) & 63u)) + 1;
+        }
+        uint32_t incl = mysum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += n;
+        }
+        if (lane == 31) s_wtot[par][warp] = incl;
+        __syncthreads();                                                // (S) also: the previous bucket's table reset is complete
+        uint32_t kbase = incl - mysum, nk = 0;
+#pragma unroll
+        for (int q = 0; q < LEAF_WARPS; q++) {
+            const uint32_t v = s_wtot[par][q];
+            if (q < warp) kbase += v;
+            nk += v;
+        }
+        for (uint32_t r = t; r < nrec; r += LEAF_THREADS) {
+            uint32_t pos = r;
+            if (MULTI) {
+                int sI = 0;
+                while (r >= s_seg_cum[sI + 1]) sI++;
+                pos = r - s_seg_cum[sI] + s_seg_off[sI];
+            }
+            const uint32_t L = (RECW == 1 ? (lds32(rec_s + 8 * pos) & 15u) : (lds32(rec_s + 16 * pos + 8) & 63u)) + 1;
+            for (uint32_t o = 0; o < L; o++) sts16(desc_s + 2 * (kbase + o), (pos << 4) | o);
+            kbase += L;
+        }
+        __syncthreads();                                                // (E) descriptors complete
+        // ---- probe: warp w owns k-mers [w*nk/8, (w+1)*nk/8) and hands them to its lanes one at a time: a lane whose key
+        //      is placed (or found) takes the warp's next k-mer (ballot + popc on a warp-uniform cursor, no atomics)
+        const uint32_t kb = (nk * warp) / LEAF_WARPS;
+        uint32_t next = kb;
+        const uint32_t end = (nk * (warp + 1)) / LEAF_WARPS;
+        uint32_t x = 0, tries = 0, special = 0;
+        uint32_t nwin = 0;                                              // warp-uniform: slots this warp has claimed so far
+        uint64_t key = 0;
+        bool active = false;
         for (;;) {
-            const uint32_t m = __ballot_sync(0xffffffffu, rem == 0);
-            if (m) {                                                    // hand the warp's next records to the idle lanes
-                uint32_t idx = next + __popc(m & lane_lt);
+            const uint32_t m = __ballot_sync(0xffffffffu, !active);
+            if (m) {
+                const uint32_t idx = next + __popc(m & lane_lt);
                 next += __popc(m);
-                if (rem == 0 && idx < end) {
-                    if (MULTI) {
-                        int sI = 0;
-                        while (idx >= s_seg_cum[sI + 1]) sI++;
-                        idx = idx - s_seg_cum[sI] + s_seg_off[sI];
+                if (!active && idx < end) {
+                    const uint32_t d = lds16(desc_s + 2 * idx);
+                    const uint32_t o2 = 2 * (d & 15u);
+                    if (RECW == 1) key = (lds64(rec_s + 8 * (d >> 4)) << o2) >> kshift;
+                    else {
+                        unsigned long long hi, lo;
+                        lds128(rec_s + 16 * (d >> 4), hi, lo);
+                        key = (o2 ? ((hi << o2) | (lo >> (64 - o2))) : hi) >> kshift;
                     }
-                    if (RECW == 1) {
-                        hi = lds64(rec_s + 8 * idx);
-                        rem = (uint32_t)(hi & 15u) + 1;
-                    } else {
-                        lds128(rec_s + 16 * idx, hi, lo);
-                        rem = (uint32_t)(lo & 63u) + 1;
-                    }
+                    x = (uint32_t)key * 0x9E3779B1u + (uint32_t)(key >> 32) * 0x85EBCA6Bu;
                     tries = 0;
+                    active = true;
+                    if (RECW == 2 && key == kEmpty) {                   // k == 32, 't'*32: kept out of the table
+                        special++;
+                        active = false;
+                    }
                 }
             }
-            if (__all_sync(0xffffffffu, rem == 0)) break;               // the warp's records are exhausted
-            const uint64_t key = hi >> kshift;
-            const uint32_t x = (uint32_t)key * 0x9E3779B1u + (uint32_t)(key >> 32) * 0x85EBCA6Bu;
+            if (__all_sync(0xffffffffu, !active)) {
+                if (next >= end) break;                                 // the warp's k-mers are exhausted
+                continue;                                               // (k == 32: a whole round of 't'*32)
+            }
             const uint32_t step = (x >> 7) | 1u;                        // double hashing: an odd step visits every slot
-            const uint32_t slot = tbl_s + 8 * (((x >> 20) + tries * step) & (LEAF_SLOTS - 1));
-            if (rem) {
-                bool adv;
-                if (RECW == 2 && key == kEmpty) {                       // k == 32, 't'*32: kept out of the table
-                    special++;
-                    adv = true;
-                } else {
-                    const unsigned long long old = atoms_cas64(slot, kEmpty, key);
-                    const bool won = old == kEmpty;
-                    const bool dup = (old & KEYMASK) == key;           // (never true together with won)
-                    own += won;
-                    if (dup) {
-                        if (PACKED) reds_add64(slot, 1ull << 52);
-                        else reds_add32(cnt_s + ((slot - tbl_s) >> 1), 1u);
-                    }
-                    adv = won | dup;
+            const uint32_t h = ((x >> 20) + tries * step) & (LEAF_SLOTS - 1);
+            const uint32_t slot = tbl_s + 8 * h;
+            bool won = false;
+            if (active) {
+                const unsigned long long old = atoms_cas64(slot, kEmpty, key);
+                won = old == kEmpty;
+                const bool dup = (old & KEYMASK) == key;               // (never true together with won)
+                if (dup) {
+                    if (PACKED) reds_add64(slot, 1ull << 52);
+                    else reds_add32(cnt_s + 4 * h, 1u);
                 }
-                if (adv) {
-                    hi = (hi << 2) | (RECW == 2 ? (lo >> 62) : 0ull);
-                    if (RECW == 2) lo <<= 2;
-                    rem--;
-                    tries = 0;
-                } else tries++;
+                active = !(won | dup);
+                tries++;
             }
+            // the claimed slots are listed in place of the warp's consumed descriptors (nwin < next - kb always holds:
+            // every claim follows the fetch of its k-mer, and all descriptors below `next` have been read)
+            const uint32_t wm = __ballot_sync(0xffffffffu, won);
+            if (won) sts16(desc_s + 2 * (kb + nwin + __popc(wm & lane_lt)), h);
+            nwin += __popc(wm);
         }
-        // ---- the last warp to arrive reserves the bucket's output range
-        for (int d = 16; d; d >>= 1) {
-            own += __shfl_xor_sync(0xffffffffu, own, d);
-            if (RECW == 2) special += __shfl_xor_sync(0xffffffffu, special, d);
-        }
-        if (lane == 0) {
-            if (RECW == 2 && special) atomicAdd(&C.special, special);
-            atoms_add32(nwin_s, own);
-            __threadfence_block();
-            if (atoms_add32(arrived_s, 1u) == LEAF_WARPS - 1) {
-                const uint32_t total = lds32(nwin_s);
-                s_base[par] = total ? atomicAdd(&status->n_distinct, (unsigned long long)total) : 0ull;
-            }
-        }
-        __syncthreads();                                                // (B) probing done: the record buffer is free
+        // ---- every warp reserves the output range of the slots it claimed (the latency hides behind the barrier)
+        unsigned long long obase = 0;
+        if (lane == 0 && nwin) obase = atomicAdd(&status->n_distinct, (unsigned long long)nwin);
+        if (RECW == 2) special_total += special;
+        __syncthreads();                                                // (B) all counts final; the record buffer is free
         if (t == 0) {
             if (nxt.usable()) issue(b_next);
-            LeafCounters& N = s_ctr[par ^ 1];                           // the other counter set is idle now: reset it
-            N.nwin = 0; N.arrived = 0; N.special = 0; N.cursor = 0;
-            special_total += C.special;
-            kmers_total += cur.nk - C.special;
+            kmers_total += cur.nk;
         }
-        // ---- emit + reset: two slots per lane per iteration
-        const unsigned long long obase = s_base[par];
-        for (int i = t; i < LEAF_SLOTS / 2; i += LEAF_THREADS) {
-            unsigned long long k0, k1;
-            lds128(tbl_s + 16 * i, k0, k1);
-            const bool o0 = k0 != kEmpty, o1 = k1 != kEmpty;
-            const uint32_t m0 = __ballot_sync(0xffffffffu, o0), m1 = __ballot_sync(0xffffffffu, o1);
-            if (!(m0 | m1)) continue;
-            uint32_t pos = 0;
-            if (lane == 0) pos = atoms_add32(cursor_s, (uint32_t)(__popc(m0) + __popc(m1)));
-            pos = __shfl_sync(0xffffffffu, pos, 0);
-            if (o0 | o1) sts128(tbl_s + 16 * i, ~0u, ~0u, ~0u, ~0u);
-            if (o0) {
-                uint64_t c;
-                if (PACKED) c = k0 >> 52;
-                else {
-                    c = lds32(cnt_s + 8 * i);
-                    if (c) sts32(cnt_s + 8 * i, 0u);
-                }
-                const uint64_t idx = obase + pos + __popc(m0 & lane_lt);
-                if (idx < capacity) { ulonglong2 v; v.x = k0 & KEYMASK; v.y = 1ull + c; reinterpret_cast<ulonglong2*>(out)[idx] = v; }
-                else status->out_overflow = 1;
+        // ---- emit + reset: the warp walks its own list of claimed slots, coalesced 16-byte (k-mer, count) stores
+        obase = __shfl_sync(0xffffffffu, obase, 0);
+        for (uint32_t i = lane; i < nwin; i += 32) {
+            const uint32_t h = lds16(desc_s + 2 * (kb + i));
+            const unsigned long long v = lds64(tbl_s + 8 * h);
+            sts64(tbl_s + 8 * h, kEmpty);
+            unsigned long long c;
+            if (PACKED) c = v >> 52;
+            else {
+                c = lds32(cnt_s + 4 * h);
+                if (c) sts32(cnt_s + 4 * h, 0u);
             }
-            if (o1) {
-                uint64_t c;
-                if (PACKED) c = k1 >> 52;
-                else {
-                    c = lds32(cnt_s + 8 * i + 4);
-                    if (c) sts32(cnt_s + 8 * i + 4, 0u);
-                }
-                const uint64_t idx = obase + pos + __popc(m0) + __popc(m1 & lane_lt);
-                if (idx < capacity) { ulonglong2 v; v.x = k1 & KEYMASK; v.y = 1ull + c; reinterpret_cast<ulonglong2*>(out)[idx] = v; }
-                else status->out_overflow = 1;
-            }
+            const uint64_t idx = obase + i;
+            if (idx < capacity) { ulonglong2 o; o.x = v & KEYMASK; o.y = 1ull + c; reinterpret_cast<ulonglong2*>(out)[idx] = o; }
+            else status->out_overflow = 1;
         }
-        __syncthreads();                                                // (D) the table is clean again
-        par ^= 1;
+        par ^= 1;                                                       // (the next bucket's barrier (S) covers the table reset)
         cur = nxt;
     }
-    if (t == 0) {
-        if (special_total) atomicAdd(&status->special_count, special_total);
-        if (kmers_total) atomicAdd(&status->n_kmers, kmers_total);
+    // n_kmers counts what went through the tables; the k == 32 special key is added back by append_special_kernel
+    if (RECW == 2) {
+        for (int d = 16; d; d >>= 1) special_total += __shfl_xor_sync(0xffffffffu, special_total, d);
+        if (lane == 0 && special_total) {
+            atomicAdd(&status->special_count, special_total);
+            atomicAdd(&status->n_kmers, 0ull - special_total);
+        }
     }
+    if (t == 0 && kmers_total) atomicAdd(&status->n_kmers, kmers_total);
 }
 
 // tier 2: every k-mer of the failed buckets (their in-region records) and of the spill list goes into
@@ -637,7 +654,7 @@ void launch_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPl
 // p.n_buckets = buckets counted HERE (all of them on one GPU, the owned range when sharded)
 size_t leaf_smem_bytes(const PartitionPlan& p, int n_src) {
     const size_t recb = p.recw == 1 ? 8 : 16;
-    size_t table = (size_t)LEAF_SLOTS * 8 + (p.recw == 1 ? 0 : (size_t)LEAF_SLOTS * 4);
+    size_t table = (size_t)LEAF_SLOTS * 8 + (p.recw == 1 ? 0 : (size_t)LEAF_SLOTS * 4) + (size_t)LEAF_MAX_KMERS * 2;
     size_t staged = ((size_t)p.cap * n_src + 2 * (size_t)n_src) * recb;   // every segment padded to 16 bytes
     return table + ((staged + 15) & ~(size_t)15);
 }
