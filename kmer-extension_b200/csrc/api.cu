@@ -764,6 +764,8 @@ extern "C" int kmer_cuda_dev_shard_count(kmer_cuda_ctx* c, const kmer_shard_plan
     c->last_tier2 = 0;
     const int k = sp->k;
     PartitionPlan plan = to_partition_plan(sp, sp->buckets_per_rank);
+    if ((uint64_t)sp->cap * sp->n_ranks + 2ull * sp->n_ranks > 4096 || (sp->cap & 1u))
+        return bad_arg(c, "shard plan: cap must be even and cap * n_ranks must stay below 4096 staged records");
     rc = ws(c, c->failed, (size_t)plan.n_buckets * 4);
     if (rc) return rc;
     launch_bucket_count(c->di, plan, k, (int)sp->n_ranks, (const unsigned long long*)d_recv_fill, d_recv_recs,

@@ -22,15 +22,16 @@
 //           kernel counts exactly those buckets' records in a global hash table and appends them;
 //   tier 3  if even the spill list overflows, DevStatus::n_overflow is set and the caller recounts
 //           the whole batch with the global-hash-table path (count_hash.cu).
+#include <cmath>
 #include <cstdlib>
 
 #include "kernels.cuh"
 
 namespace kmer {
 
-constexpr int LEAF_SLOTS = 4096;          // shared-memory table slots per bucket
+constexpr int LEAF_SLOTS = 2048;          // shared-memory table slots per bucket
 constexpr int LEAF_THREADS = 256;
-constexpr uint32_t TARGET_KMERS_PER_BUCKET = 2000;   // mean load 0.49 of the table; the tail is handled by tier 2
+constexpr uint32_t TARGET_KMERS_PER_BUCKET = 1000;   // about half of what a bucket may hold; the tail is handled by tier 2
 
 // ---------------------------------------------------------------------------------------------
 // record formats
@@ -203,27 +204,36 @@ __global__ void __launch_bounds__(NT) partition_kernel(ScanArgs a, PartitionPlan
 // ---------------------------------------------------------------------------------------------
 // per-bucket counting
 //
-// One CTA (256 threads) per bucket, two block barriers per bucket:
-//   stage : the bucket's record region (contiguous in HBM) is brought to shared memory by the TMA
-//           engine (cp.async.bulk + mbarrier).  The copy for bucket i+1 is issued as soon as the probe
-//           phase of bucket i is over, so it lands behind the emit phase.
-//   probe : warp w owns the records [w*chunk, (w+1)*chunk) of the bucket and hands them to its lanes
-//           DYNAMICALLY: whenever a lane has finished the k-mers of its record it takes the warp's next
-//           record (a ballot + popc on a warp-uniform register cursor: no atomics, no idle lanes while
-//           records remain).  Every loop iteration is one 64-bit shared atomicCAS per lane (double
-//           hashing); a lane whose key is placed or found moves straight on to its next k-mer.
-//           k <= 26: the count lives in the 12 spare top bits of the key word (a bucket holds at most
-//           LEAF_MAX_KMERS < 4096 k-mers), so a duplicate is one 64-bit shared add on the same word.
-//           k >= 27: a separate 32-bit counter array.
-//           A bucket holds fewer k-mers than the table has slots, so a probe sequence (odd step) always
-//           terminates; buckets above LEAF_MAX_KMERS, or whose region overflowed, go to tier 2 up front.
-//   emit  : the table is scanned two slots per lane (16-byte loads); occupied slots are written as
-//           coalesced 16-byte (k-mer, count) pairs and reset on the spot.  The last warp to finish the
-//           probe phase reserves the bucket's output range with ONE global atomicAdd.
+// One CTA (256 threads) per bucket (about 1000 k-mers, at most 2047).  Most k-mers of a bucket occur once; proving
+// that is much cheaper than inserting them into an exact table, so the table only sees the rest:
+//   stage  : the bucket's record region (contiguous in HBM) is brought to shared memory by the TMA engine
+//            (cp.async.bulk + mbarrier); the copy for bucket i+1 is issued while bucket i is being emitted.
+//   expand : k-mer j of the bucket -> 16-bit descriptor (staged record << 4 | window) via a block-wide prefix sum of
+//            the record lengths, so that every later phase works on single k-mers, 8 per thread, all lanes busy.
+//   mark   : every k-mer sets bit hash(k-mer) of bitmap A (atom.or with return); whoever finds the bit already set
+//            sets the same bit of bitmap B.                                                        -- barrier --
+//   sort   : a k-mer whose B bit is clear is the ONLY k-mer of the bucket in its cell: it is unique, count 1.
+//            The others (true repeats and the ~3 % that merely share a cell) are listed in a compact "slow list"
+//            (which reuses bitmap A's storage: A is dead after the barrier).                        -- barrier --
+//   count  : the slow list is spread evenly over the warps and counted exactly in a 2048-slot open-addressing
+//            table: one 64-bit shared atomicCAS per lane per iteration (double hashing); a lane whose key is placed
+//            or found takes the warp's next k-mer (ballot + popc on a warp-uniform cursor: no atomics, no idle
+//            lanes).  k <= 26: the count lives in the 12 spare top bits of the key word; k >= 27: separate 32-bit
+//            counters.  The slots a warp claims are listed in place of its consumed slow-list entries.
+//                                                                                                   -- barrier --
+//   emit   : unique k-mers are written straight from their descriptors, table entries from the claimed-slot lists
+//            (which also resets the table); both as coalesced 16-byte (k-mer, count) pairs.  Output ranges: one
+//            global atomicAdd per bucket for the unique k-mers, one per warp that claimed table slots.
+// A bucket holds fewer k-mers than the table has slots, so a probe sequence (odd step) always terminates; buckets
+// above LEAF_MAX_KMERS, or whose region overflowed in the partition pass, go to tier 2 up front.
 // Shared memory is addressed through explicit 32-bit shared addresses (ld/st/atom.shared PTX).
 
-constexpr uint32_t LEAF_MAX_KMERS = 3840;
+constexpr int LEAF_KPT = 8;                                          // k-mers per thread
+constexpr uint32_t LEAF_MAX_KMERS = LEAF_KPT * LEAF_THREADS - 1;    // 2047 < LEAF_SLOTS: the table can never fill up
+constexpr int LEAF_CELLS = 32768;                                    // bits per filter bitmap
 constexpr int LEAF_WARPS = LEAF_THREADS / 32;
+static_assert(LEAF_MAX_KMERS < LEAF_SLOTS, "a probe sequence must always find a free slot");
+static_assert(LEAF_CELLS / 8 >= 2 * (LEAF_MAX_KMERS + 1), "the slow list lives in bitmap A");
 constexpr int MAX_SRC = 16;           // source GPUs a sharded bucket may be assembled from
 
 __device__ __forceinline__ unsigned long long atoms_cas64(uint32_t a, unsigned long long cmp, unsigned long long val) {
@@ -235,6 +245,14 @@ __device__ __forceinline__ uint32_t atoms_add32(uint32_t a, uint32_t v) {
     uint32_t old;
     asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
     return old;
+}
+__device__ __forceinline__ uint32_t atoms_or32(uint32_t a, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void reds_or32(uint32_t a, uint32_t v) {
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 __device__ __forceinline__ void reds_add32(uint32_t a, uint32_t v) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
@@ -317,7 +335,7 @@ __device__ __forceinline__ BucketInfo bucket_info(const unsigned long long* __re
 }
 
 template <int RECW, bool MULTI>
-__global__ void __launch_bounds__(LEAF_THREADS, 4) bucket_count_kernel(PartitionPlan plan, int k,
+__global__ void __launch_bounds__(LEAF_THREADS, 5) bucket_count_kernel(PartitionPlan plan, int k,
                                                                        const unsigned long long* __restrict__ fill,
                                                                        const Rec<RECW>* __restrict__ recs,
                                                                        kmer_count_pair* __restrict__ out, uint64_t capacity,
@@ -331,11 +349,16 @@ __global__ void __launch_bounds__(LEAF_THREADS, 4) bucket_count_kernel(Partition
     uint32_t tbl_s = smem_u32(leaf_dyn);                                       // u64[LEAF_SLOTS]
     asm volatile("" : "+r"(tbl_s));                                            // keep it in a register (no rematerialisation)
     const uint32_t cnt_s = tbl_s + LEAF_SLOTS * 8;                             // u32[LEAF_SLOTS]   (k >= 27 only)
-    const uint32_t desc_s = cnt_s + (PACKED ? 0 : LEAF_SLOTS * 4);            // u16[LEAF_MAX_KMERS] k-mer descriptors
-    const uint32_t rec_s = desc_s + LEAF_MAX_KMERS * 2;                        // staged records
+    const uint32_t bma_s = cnt_s + (PACKED ? 0 : LEAF_SLOTS * 4);             // bitmap A / slow list (u16 k-mer indices)
+    const uint32_t bmb_s = bma_s + LEAF_CELLS / 8;                             // bitmap B
+    const uint32_t desc_s = bmb_s + LEAF_CELLS / 8;                            // u16[LEAF_MAX_KMERS + 1] k-mer descriptors
+    const uint32_t rec0_s = desc_s + (LEAF_MAX_KMERS + 1) * 2;                 // staged records, two buffers
+    const uint32_t rec_stride = (((uint32_t)plan.cap * n_src + 2u * n_src) * RECB + 15u) & ~15u;
     __shared__ __align__(8) uint64_t s_mbar;
-    __shared__ uint32_t s_seg_cum[MAX_SRC + 1], s_seg_off[MAX_SRC + 1];        // n_src > 1: record prefix / staged offset
+    __shared__ uint32_t s_seg_cum[2][MAX_SRC + 1], s_seg_off[2][MAX_SRC + 1];  // n_src > 1: record prefix / staged offset
     __shared__ uint32_t s_wtot[2][LEAF_WARPS];
+    __shared__ uint32_t s_nuniq[2], s_nslow[2];                                // per bucket parity
+    __shared__ unsigned long long s_obase[2];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint32_t lane_lt = (1u << lane) - 1u;
     const int kshift = 64 - 2 * k;
@@ -344,22 +367,25 @@ __global__ void __launch_bounds__(LEAF_THREADS, 4) bucket_count_kernel(Partition
     for (int i = t; i < LEAF_SLOTS / 2; i += LEAF_THREADS) sts128(tbl_s + 16 * i, ~0u, ~0u, ~0u, ~0u);
     if (!PACKED)
         for (int i = t; i < LEAF_SLOTS / 4; i += LEAF_THREADS) sts128(cnt_s + 16 * i, 0u, 0u, 0u, 0u);
+    for (int i = t; i < 2 * LEAF_CELLS / 128; i += LEAF_THREADS) sts128(bma_s + 16 * i, 0u, 0u, 0u, 0u);   // A and B
+    if (t < 2) { s_nuniq[t] = 0; s_nslow[t] = 0; }
     if (t == 0) { mbar_init(&s_mbar, 1); mbar_fence_init(); }
     __syncthreads();
 
     // thread 0: start the bulk copies of bucket b's records (every segment padded to 16 bytes)
-    auto issue = [&](uint32_t b) {
+    auto issue = [&](uint32_t b, uint32_t buf) {
+        const uint32_t rec_s = rec0_s + buf * rec_stride;
         uint32_t off = 0, cum = 0, bytes = 0;
 #pragma unroll 1
         for (int sI = 0; sI < n_src; sI++) {
             const uint32_t n = (uint32_t)fill[(uint64_t)sI * plan.n_buckets + b];
-            if (MULTI) { s_seg_cum[sI] = cum; s_seg_off[sI] = off; }
+            if (MULTI) { s_seg_cum[buf][sI] = cum; s_seg_off[buf][sI] = off; }
             cum += n;
             const uint32_t nb = (n * RECB + 15u) & ~15u;
             off += nb / RECB;
             bytes += nb;
         }
-        if (MULTI) s_seg_cum[n_src] = cum;
+        if (MULTI) s_seg_cum[buf][n_src] = cum;
         mbar_arrive_expect_tx(&s_mbar, bytes);
         off = 0;
 #pragma unroll 1
@@ -377,11 +403,11 @@ __global__ void __launch_bounds__(LEAF_THREADS, 4) bucket_count_kernel(Partition
         }
     };
 
-    uint32_t par = 0, phase = 0;
+    uint32_t par = 0, phase = 0, rb = 0;                                // bucket parity, mbarrier phase, record buffer
     BucketInfo cur;
     cur.nrec = 0; cur.nk = 0; cur.overflow = false;
     if (blockIdx.x < plan.n_buckets) cur = bucket_info<MULTI>(fill, plan, n_src, blockIdx.x);
-    if (t == 0 && cur.usable()) issue(blockIdx.x);
+    if (t == 0 && cur.usable()) issue(blockIdx.x, 0);
 
     for (uint32_t b = blockIdx.x; b < plan.n_buckets; b += gridDim.x) {
         const uint32_t b_next = b + gridDim.x;
@@ -395,24 +421,24 @@ __global__ void __launch_bounds__(LEAF_THREADS, 4) bucket_count_kernel(Partition
                     failed_ids[idx] = b;
                     atomicAdd(&status->failed_kmers, (unsigned long long)cur.nk);
                 }
-                if (nxt.usable()) issue(b_next);
+                if (nxt.usable()) issue(b_next, rb);                    // nothing is staged for this bucket
             }
             cur = nxt;
             continue;
         }
         mbar_wait_s(mbar_s, phase);
         phase ^= 1u;
-        // ---- expand: k-mer j of the bucket -> descriptor (staged record << 4 | window), so that the probe phase can
-        //      hand out single k-mers (records hold 1..16 of them; handing out whole records leaves most lanes idle
-        //      while the longest records finish).  Thread t lists the k-mers of records t, t+256, ...
+        const uint32_t rec_s = rec0_s + rb * rec_stride;
+        // ---- expand: k-mer j of the bucket -> descriptor (staged record << 4 | window).  Thread t lists the k-mers of
+        //      records t, t+256, ...; the block-wide prefix sum of the record lengths gives their positions.
         const uint32_t nrec = cur.nrec;
         uint32_t mysum = 0;
         for (uint32_t r = t; r < nrec; r += LEAF_THREADS) {
             uint32_t pos = r;
             if (MULTI) {
                 int sI = 0;
-                while (r >= s_seg_cum[sI + 1]) sI++;
-                pos = r - s_seg_cum[sI] + s_seg_off[sI];
+                while (r >= s_seg_cum[rb][sI + 1]) sI++;
+                pos = r - s_seg_cum[rb][sI] + s_seg_off[rb][sI];
             }
             mysum += (RECW == 1 ? (lds32(rec_s + 8 * pos) & 15u) : (lds32(rec_s + 16 * pos + 8) & 63u)) + 1;
         }
@@ -423,7 +449,11 @@ __global__ void __launch_bounds__(LEAF_THREADS, 4) bucket_count_kernel(Partition
             if (lane >= d) incl += n;
         }
         if (lane == 31) s_wtot[par][warp] = incl;
-        __syncthreads();                                                // (S) also: the previous bucket's table reset is complete
+        __syncthreads();                                                // (S) also: the previous bucket is fully emitted
+        // bitmap A doubled as the previous bucket's slow list / claimed-slot lists: clear it now; the other record
+        // buffer is free as well: start the next bucket's copy
+        sts128(bma_s + 16 * t, 0u, 0u, 0u, 0u);
+        if (t == 0 && nxt.usable()) issue(b_next, rb ^ 1u);
         uint32_t kbase = incl - mysum, nk = 0;
 #pragma unroll
         for (int q = 0; q < LEAF_WARPS; q++) {
@@ -435,84 +465,163 @@ __global__ void __launch_bounds__(LEAF_THREADS, 4) bucket_count_kernel(Partition
             uint32_t pos = r;
             if (MULTI) {
                 int sI = 0;
-                while (r >= s_seg_cum[sI + 1]) sI++;
-                pos = r - s_seg_cum[sI] + s_seg_off[sI];
+                while (r >= s_seg_cum[rb][sI + 1]) sI++;
+                pos = r - s_seg_cum[rb][sI] + s_seg_off[rb][sI];
             }
             const uint32_t L = (RECW == 1 ? (lds32(rec_s + 8 * pos) & 15u) : (lds32(rec_s + 16 * pos + 8) & 63u)) + 1;
             for (uint32_t o = 0; o < L; o++) sts16(desc_s + 2 * (kbase + o), (pos << 4) | o);
             kbase += L;
         }
-        __syncthreads();                                                // (E) descriptors complete
-        // ---- probe: warp w owns k-mers [w*nk/8, (w+1)*nk/8) and hands them to its lanes one at a time: a lane whose key
-        //      is placed (or found) takes the warp's next k-mer (ballot + popc on a warp-uniform cursor, no atomics)
-        const uint32_t kb = (nk * warp) / LEAF_WARPS;
-        uint32_t next = kb;
-        const uint32_t end = (nk * (warp + 1)) / LEAF_WARPS;
-        uint32_t x = 0, tries = 0, special = 0;
-        uint32_t nwin = 0;                                              // warp-uniform: slots this warp has claimed so far
-        uint64_t key = 0;
-        bool active = false;
-        for (;;) {
-            const uint32_t m = __ballot_sync(0xffffffffu, !active);
-            if (m) {
-                const uint32_t idx = next + __popc(m & lane_lt);
-                next += __popc(m);
-                if (!active && idx < end) {
-                    const uint32_t d = lds16(desc_s + 2 * idx);
-                    const uint32_t o2 = 2 * (d & 15u);
-                    if (RECW == 1) key = (lds64(rec_s + 8 * (d >> 4)) << o2) >> kshift;
-                    else {
-                        unsigned long long hi, lo;
-                        lds128(rec_s + 16 * (d >> 4), hi, lo);
-                        key = (o2 ? ((hi << o2) | (lo >> (64 - o2))) : hi) >> kshift;
-                    }
-                    x = (uint32_t)key * 0x9E3779B1u + (uint32_t)(key >> 32) * 0x85EBCA6Bu;
-                    tries = 0;
-                    active = true;
-                    if (RECW == 2 && key == kEmpty) {                   // k == 32, 't'*32: kept out of the table
-                        special++;
-                        active = false;
+        __syncthreads();                                                // (E) descriptors complete, bitmap A clear
+        auto key_at = [&](uint32_t j) -> uint64_t {                     // k-mer j of the bucket
+            const uint32_t d = lds16(desc_s + 2 * j);
+            const uint32_t o2 = 2 * (d & 15u);
+            if (RECW == 1) return (lds64(rec_s + 8 * (d >> 4)) << o2) >> kshift;
+            unsigned long long hi, lo;
+            lds128(rec_s + 16 * (d >> 4), hi, lo);
+            return (o2 ? ((hi << o2) | (lo >> (64 - o2))) : hi) >> kshift;
+        };
+        // ---- mark: thread t owns k-mers t, t+256, ...
+        uint32_t valid = 0, multi = 0, special = 0;                     // bit i: k-mer t + 256 i exists / shares its cell
+        uint32_t cells[LEAF_KPT / 2];                                   // its 15-bit cell, two per register
+#pragma unroll
+        for (int i = 0; i < LEAF_KPT / 2; i++) cells[i] = 0;
+#pragma unroll
+        for (int i = 0; i < LEAF_KPT; i++) {
+            if (i * LEAF_THREADS >= nk) break;                          // uniform
+            const uint32_t j = t + i * LEAF_THREADS;
+            if (j < nk) {
+                const uint64_t key = key_at(j);
+                if (RECW == 2 && key == kEmpty) special++;              // k == 32, 't'*32: kept out of the tables
+                else {
+                    const uint32_t x = (uint32_t)key * 0x9E3779B1u + (uint32_t)(key >> 32) * 0x85EBCA6Bu;
+                    const uint32_t cell = x >> 17;
+                    cells[i >> 1] |= cell << (16 * (i & 1));
+                    const uint32_t bit = 1u << (cell & 31u), w = (cell >> 5) * 4;
+                    valid |= 1u << i;
+                    if (atoms_or32(bma_s + w, bit) & bit) {
+                        reds_or32(bmb_s + w, bit);
+                        multi |= 1u << i;
                     }
                 }
             }
-            if (__all_sync(0xffffffffu, !active)) {
-                if (next >= end) break;                                 // the warp's k-mers are exhausted
-                continue;                                               // (k == 32: a whole round of 't'*32)
-            }
-            const uint32_t step = (x >> 7) | 1u;                        // double hashing: an odd step visits every slot
-            const uint32_t h = ((x >> 20) + tries * step) & (LEAF_SLOTS - 1);
-            const uint32_t slot = tbl_s + 8 * h;
-            bool won = false;
-            if (active) {
-                const unsigned long long old = atoms_cas64(slot, kEmpty, key);
-                won = old == kEmpty;
-                const bool dup = (old & KEYMASK) == key;               // (never true together with won)
-                if (dup) {
-                    if (PACKED) reds_add64(slot, 1ull << 52);
-                    else reds_add32(cnt_s + 4 * h, 1u);
-                }
-                active = !(won | dup);
-                tries++;
-            }
-            // the claimed slots are listed in place of the warp's consumed descriptors (nwin < next - kb always holds:
-            // every claim follows the fetch of its k-mer, and all descriptors below `next` have been read)
-            const uint32_t wm = __ballot_sync(0xffffffffu, won);
-            if (won) sts16(desc_s + 2 * (kb + nwin + __popc(wm & lane_lt)), h);
-            nwin += __popc(wm);
         }
-        // ---- every warp reserves the output range of the slots it claimed (the latency hides behind the barrier)
-        unsigned long long obase = 0;
-        if (lane == 0 && nwin) obase = atomicAdd(&status->n_distinct, (unsigned long long)nwin);
-        if (RECW == 2) special_total += special;
-        __syncthreads();                                                // (B) all counts final; the record buffer is free
+        __syncthreads();                                                // (M) both bitmaps final; A is free from here on
+        // ---- sort: unique k-mers stay where they are, the others go to the slow list
+#pragma unroll
+        for (int i = 0; i < LEAF_KPT; i++) {
+            if (i * LEAF_THREADS >= nk) break;
+            if (((valid & ~multi) >> i) & 1u) {
+                const uint32_t cell = (cells[i >> 1] >> (16 * (i & 1))) & 0x7fffu;
+                if ((lds32(bmb_s + (cell >> 5) * 4) >> (cell & 31u)) & 1u) multi |= 1u << i;
+            }
+        }
+        const uint32_t uniq = valid & ~multi;
+        const uint32_t pk = __popc(uniq) | ((uint32_t)__popc(multi) << 16);   // per warp each half stays below 2^16
+        uint32_t pincl = pk;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, pincl, d);
+            if (lane >= d) pincl += n;
+        }
+        uint32_t woff = 0;                                              // the warp's offsets: unique (low) / slow (high)
+        if (lane == 31) {
+            const uint32_t u = (pincl & 0xffffu) ? atoms_add32(smem_u32(&s_nuniq[par]), pincl & 0xffffu) : 0u;
+            const uint32_t m = (pincl >> 16) ? atoms_add32(smem_u32(&s_nslow[par]), pincl >> 16) : 0u;
+            woff = u | (m << 16);
+        }
+        woff = __shfl_sync(0xffffffffu, woff, 31);
+        {
+            uint32_t sb = (woff >> 16) + (pincl >> 16) - __popc(multi);
+            uint32_t m2 = multi;
+            while (m2) {
+                const uint32_t i = __ffs(m2) - 1;
+                m2 &= m2 - 1;
+                sts16(bma_s + 2 * sb, t + i * LEAF_THREADS);
+                sb++;
+            }
+        }
+        __syncthreads();                                                // (L) slow list complete
+        const uint32_t ns = s_nslow[par];
+        unsigned long long ubase = 0;
         if (t == 0) {
-            if (nxt.usable()) issue(b_next);
-            kmers_total += cur.nk;
+            const uint32_t nu = s_nuniq[par];
+            if (nu) ubase = atomicAdd(&status->n_distinct, (unsigned long long)nu);   // consumed after the next barrier
         }
-        // ---- emit + reset: the warp walks its own list of claimed slots, coalesced 16-byte (k-mer, count) stores
-        obase = __shfl_sync(0xffffffffu, obase, 0);
+        // bitmap B is dead: clear it for the next bucket
+        sts128(bmb_s + 16 * t, 0u, 0u, 0u, 0u);
+        // ---- count: the slow list is cut into one slice per warp, but never thinner than 32 entries (a warp pays for
+        //      the probe loop whether 1 or 32 of its lanes are busy)
+        const uint32_t slice = max(32u, (ns + LEAF_WARPS - 1) / LEAF_WARPS);
+        const uint32_t kb = min(ns, warp * slice);
+        const uint32_t end = min(ns, kb + slice);
+        uint32_t nwin = 0;                                              // warp-uniform: slots this warp has claimed so far
+        if (kb < end) {
+            uint32_t next = kb, x = 0, tries = 0;
+            uint64_t key = 0;
+            bool active = false;
+            for (;;) {
+                const uint32_t m = __ballot_sync(0xffffffffu, !active);
+                if (m) {
+                    const uint32_t idx = next + __popc(m & lane_lt);
+                    next += __popc(m);
+                    if (!active && idx < end) {
+                        key = key_at(lds16(bma_s + 2 * idx));
+                        x = (uint32_t)key * 0x9E3779B1u + (uint32_t)(key >> 32) * 0x85EBCA6Bu;
+                        x *= 0x2C1B3C6Du;                               // decorrelate from the cell index
+                        tries = 0;
+                        active = true;
+                    }
+                }
+                if (__all_sync(0xffffffffu, !active)) break;            // the warp's share is exhausted
+                const uint32_t step = (x >> 6) | 1u;                    // double hashing: an odd step visits every slot
+                const uint32_t h = ((x >> 21) + tries * step) & (LEAF_SLOTS - 1);
+                const uint32_t slot = tbl_s + 8 * h;
+                bool won = false;
+                if (active) {
+                    const unsigned long long old = atoms_cas64(slot, kEmpty, key);
+                    won = old == kEmpty;
+                    const bool dup = (old & KEYMASK) == key;           // (never true together with won)
+                    if (dup) {
+                        if (PACKED) reds_add64(slot, 1ull << 52);
+                        else reds_add32(cnt_s + 4 * h, 1u);
+                    }
+                    active = !(won | dup);
+                    tries++;
+                }
+                // the claimed slots are listed in place of the warp's consumed slow-list entries (nwin < next - kb always
+                // holds: every claim follows the fetch of its k-mer, and all entries below `next` have been read)
+                const uint32_t wm = __ballot_sync(0xffffffffu, won);
+                if (won) sts16(bma_s + 2 * (kb + nwin + __popc(wm & lane_lt)), h);
+                nwin += __popc(wm);
+            }
+        }
+        unsigned long long wbase = 0;
+        if (lane == 0 && nwin) wbase = atomicAdd(&status->n_distinct, (unsigned long long)nwin);
+        if (t == 0) s_obase[par] = ubase;
+        if (RECW == 2) special_total += special;
+        __syncthreads();                                                // (B) all counts final
+        if (t == 0) { s_nuniq[par ^ 1] = 0; s_nslow[par ^ 1] = 0; }   // idle until the next bucket's sort phase
+        // ---- emit the unique k-mers: coalesced 16-byte (k-mer, 1) pairs, ranks by ballot
+        {
+            unsigned long long ob = s_obase[par] + (woff & 0xffffu);
+#pragma unroll
+            for (int i = 0; i < LEAF_KPT; i++) {
+                if (i * LEAF_THREADS >= nk) break;
+                const bool u = (uniq >> i) & 1u;
+                const uint32_t m = __ballot_sync(0xffffffffu, u);
+                if (u) {
+                    const uint64_t idx = ob + __popc(m & lane_lt);
+                    if (idx < capacity) { ulonglong2 o; o.x = key_at(t + i * LEAF_THREADS); o.y = 1ull; reinterpret_cast<ulonglong2*>(out)[idx] = o; }
+                    else status->out_overflow = 1;
+                }
+                ob += __popc(m);
+            }
+        }
+        // ---- emit + reset the table entries this warp claimed
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
         for (uint32_t i = lane; i < nwin; i += 32) {
-            const uint32_t h = lds16(desc_s + 2 * (kb + i));
+            const uint32_t h = lds16(bma_s + 2 * (kb + i));
             const unsigned long long v = lds64(tbl_s + 8 * h);
             sts64(tbl_s + 8 * h, kEmpty);
             unsigned long long c;
@@ -521,11 +630,13 @@ __global__ void __launch_bounds__(LEAF_THREADS, 4) bucket_count_kernel(Partition
                 c = lds32(cnt_s + 4 * h);
                 if (c) sts32(cnt_s + 4 * h, 0u);
             }
-            const uint64_t idx = obase + i;
+            const uint64_t idx = wbase + i;
             if (idx < capacity) { ulonglong2 o; o.x = v & KEYMASK; o.y = 1ull + c; reinterpret_cast<ulonglong2*>(out)[idx] = o; }
             else status->out_overflow = 1;
         }
-        par ^= 1;                                                       // (the next bucket's barrier (S) covers the table reset)
+        if (t == 0) kmers_total += cur.nk;
+        par ^= 1;
+        rb ^= 1u;
         cur = nxt;
     }
     // n_kmers counts what went through the tables; the k == 32 special key is added back by append_special_kernel
@@ -628,7 +739,11 @@ PartitionPlan make_partition_plan(uint64_t n_kmers, int k) {
     if (nb < 1) nb = 1;
     if (nb > 0x7fffffffull) nb = 0x7fffffffull;
     p.n_buckets = (uint32_t)nb;
-    p.cap = p.recw == 1 ? 1280u : 896u;
+    {   // records per bucket: about 2/(w+1) + 1/16 records per k-mer (runs also end at 16-window chunk borders)
+        const double rpk = 2.0 / (p.w + 1) + 1.0 / 16.0 + (p.rmax < p.w ? 1.0 / p.rmax : 0.0);
+        const double mean = TARGET_KMERS_PER_BUCKET * rpk;
+        p.cap = ((uint32_t)(1.25 * mean + 5.0 * sqrt(3.0 * mean) + 16.0) + 1u) & ~1u;
+    }
     uint64_t sc = (uint64_t)p.n_buckets * p.cap / 8;          // spill list: 1/8 of the bucket regions
     p.spill_cap = sc < 4096 ? 4096 : sc;
     const char* dbg = getenv("KMER_CUDA_DEBUG_PARTITION");   // profiling experiments only (bit0: no record stores, bit1: no slot atomics)
@@ -654,9 +769,10 @@ void launch_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPl
 // p.n_buckets = buckets counted HERE (all of them on one GPU, the owned range when sharded)
 size_t leaf_smem_bytes(const PartitionPlan& p, int n_src) {
     const size_t recb = p.recw == 1 ? 8 : 16;
-    size_t table = (size_t)LEAF_SLOTS * 8 + (p.recw == 1 ? 0 : (size_t)LEAF_SLOTS * 4) + (size_t)LEAF_MAX_KMERS * 2;
+    size_t table = (size_t)LEAF_SLOTS * 8 + (p.recw == 1 ? 0 : (size_t)LEAF_SLOTS * 4) + 2 * (size_t)LEAF_CELLS / 8 +
+                   ((size_t)LEAF_MAX_KMERS + 1) * 2;
     size_t staged = ((size_t)p.cap * n_src + 2 * (size_t)n_src) * recb;   // every segment padded to 16 bytes
-    return table + ((staged + 15) & ~(size_t)15);
+    return table + 2 * ((staged + 15) & ~(size_t)15);                    // two record buffers
 }
 
 void launch_bucket_count(const DeviceInfo& di, const PartitionPlan& p, int k, int n_src, const unsigned long long* d_fill,
@@ -665,7 +781,7 @@ void launch_bucket_count(const DeviceInfo& di, const PartitionPlan& p, int k, in
     const size_t leaf_smem = leaf_smem_bytes(p, n_src);
     int per_sm = (int)((size_t)227 * 1024 / (leaf_smem + 1024));
     static const char* env_ctas = getenv("KMER_CUDA_LEAF_CTAS");   // profiling experiments only
-    int max_per_sm = env_ctas ? atoi(env_ctas) : 5;
+    int max_per_sm = env_ctas ? atoi(env_ctas) : 6;
     if (per_sm > max_per_sm) per_sm = max_per_sm;
     if (per_sm < 1) per_sm = 1;
     uint64_t lgrid = (uint64_t)di.sm_count * per_sm;
