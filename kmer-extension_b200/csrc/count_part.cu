@@ -146,24 +146,25 @@ __global__ void __launch_bounds__(NT) partition_kernel(ScanArgs a, PartitionPlan
             }
         }
         __syncthreads();
-        // ---- flat emission: run r of the tile is handled by thread r % NT; four slot reservations
+        // ---- flat emission: run r of the tile is handled by thread r % NT; EMIT_Q slot reservations
         //      (64-bit atomicAdd with return) are in flight per thread before any of them is consumed
-        for (uint32_t r0 = 0; r0 < n_tile_runs; r0 += 4 * NT) {
-            unsigned long long d[4], oldq[4];
-            bool act[4];
+        constexpr int EMIT_Q = 6;
+        for (uint32_t r0 = 0; r0 < n_tile_runs; r0 += EMIT_Q * NT) {
+            unsigned long long d[EMIT_Q], oldq[EMIT_Q];
+            bool act[EMIT_Q];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
+            for (int q = 0; q < EMIT_Q; q++) {
                 const uint32_t r = r0 + q * NT + t;
                 act[q] = r < n_tile_runs;
                 d[q] = act[q] ? runs[r] : 0ull;
             }
 #pragma unroll
-            for (int q = 0; q < 4; q++)
+            for (int q = 0; q < EMIT_Q; q++)
                 oldq[q] = !act[q] ? 0ull
                           : (plan.debug & 2) ? (unsigned long long)((mix32((uint32_t)d[q] + (uint32_t)sc.tile) >> 8) % plan.cap)
                                              : atomicAdd(&fill[(uint32_t)(d[q] >> 32)], ((d[q] & 0xff0000ull) << 16) | 1ull);
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
+            for (int q = 0; q < EMIT_Q; q++) {
                 if (!act[q]) continue;
                 const uint32_t b = (uint32_t)(d[q] >> 32);
                 const int L = (int)((d[q] >> 16) & 0xffu);
