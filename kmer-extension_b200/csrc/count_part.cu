@@ -30,7 +30,10 @@
 namespace kmer {
 
 constexpr int LEAF_SLOTS = 2048;          // shared-memory table slots per bucket
-constexpr int LEAF_THREADS = 256;
+#ifndef LEAF_THREADS_N
+#define LEAF_THREADS_N 128
+#endif
+constexpr int LEAF_THREADS = LEAF_THREADS_N;
 constexpr uint32_t TARGET_KMERS_PER_BUCKET = 1000;   // about half of what a bucket may hold; the tail is handled by tier 2
 
 // ---------------------------------------------------------------------------------------------
@@ -53,73 +56,110 @@ struct alignas(16) Rec<2> {
 // ---------------------------------------------------------------------------------------------
 // partition
 
+#ifndef PART_MINB
+#define PART_MINB 4
+#endif
 template <int W, int RECW>
-__global__ void __launch_bounds__(NT) partition_kernel(ScanArgs a, PartitionPlan plan, unsigned long long* __restrict__ fill,
+__global__ void __launch_bounds__(NT, PART_MINB) partition_kernel(ScanArgs a, PartitionPlan plan, unsigned long long* __restrict__ fill,
                                                        Rec<RECW>* __restrict__ recs, Rec<RECW>* __restrict__ spill) {
     __shared__ ScanSmem s;
-    __shared__ unsigned long long runs[TILE];   // (bucket << 32) | (L << 16) | tile-relative start base
-    __shared__ uint32_t wtot[NT / 32];
+    __shared__ unsigned long long runs[TILE];   // (minimizer hash << 32) | (windows << 16) | tile-relative start base
+    __shared__ uint32_t bdm[TILE / 32 + 2];     // bit p: a run cannot continue through window p (run start or invalid window)
     TileScanner sc(a, s);
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int k = a.k;
     const int m = plan.m;
-    const int rmax = plan.rmax;
+    const uint32_t rmax = plan.rmax;
     const uint32_t mshift = 32 - 2 * m;
     unsigned long long overflow_kmers = 0;
+    if (t < 2) bdm[TILE / 32 + t] = 0xffffffffu;   // the tile end ends every run
+
+    // one super-k-mer record: L windows starting at tile-relative base p go to bucket b
+    auto put_record = [&](uint32_t b, uint32_t slot, int p, int L) {
+        const int c = p >> 4, sh = 2 * (p & 15);
+        const uint32_t w0 = s.packed[c], w1 = s.packed[c + 1], w2 = s.packed[c + 2], w3 = s.packed[c + 3];
+        const uint32_t r0w = __funnelshift_l(w1, w0, sh), r1w = __funnelshift_l(w2, w1, sh), r2w = __funnelshift_l(w3, w2, sh);
+        const int nb = L + k - 1;                                  // bases covered
+        Rec<RECW>* dst = nullptr;
+        if (slot < plan.cap) dst = recs + ((uint64_t)b * plan.cap + slot);
+        else {                                                      // region full: spill list (tier 2), else recount
+            unsigned long long si = atomicAdd(&a.status->n_spill, 1ull);
+            if (si < plan.spill_cap) dst = spill + si;
+            else overflow_kmers += L;
+        }
+        if (dst && !(plan.debug & 1)) {
+            if (RECW == 1) {
+                uint64_t v = ((uint64_t)r0w << 32) | r1w;
+                v &= ~0ull << (64 - 2 * nb);                       // nb <= 30
+                reinterpret_cast<uint64_t*>(dst)[0] = v | (uint64_t)(L - 1);
+            } else {
+                uint64_t hi = ((uint64_t)r0w << 32) | r1w;
+                uint64_t lo = (uint64_t)r2w << 32;                  // bases 32..47 (nb <= 47)
+                if (nb <= 32) { hi &= ~0ull << (64 - 2 * nb); lo = 0; }
+                else lo &= ~0ull << (128 - 2 * nb);
+                ulonglong2 o; o.x = hi; o.y = lo | (uint64_t)(L - 1);
+                reinterpret_cast<ulonglong2*>(dst)[0] = o;
+            }
+        }
+    };
 
     while (sc.next()) {
         const uint32_t* bnd = sc.bnd();
-        // this thread's 16 windows start at tile-relative bases 16t .. 16t+15 and need bases up to 16t+46
+        // this thread's 16 windows start at tile-relative bases 16t .. 16t+15 and need bases up to 16t+46;
+        // window 16t-1 (the previous thread's last) is looked at as well, so that runs continue across threads
         uint32_t w[3];
         w[0] = s.packed[t]; w[1] = s.packed[t + 1]; w[2] = s.packed[t + 2];
-        // validity of the 16 windows: no row start in (i, i+k-1], and inside the input
-        uint32_t vmask = 0;
+        const uint32_t wm1 = t ? s.packed[t - 1] : 0u;
+        // validity of the windows: no row start in (i, i+k-1], and inside the input
+        uint32_t vmask = 0;      // bit j+1: window j is valid (j = -1 .. 15)
         {
-            const int b0 = 16 * t + 1;
-            uint32_t lo = bits32(bnd, b0), hi = bits32(bnd, b0 + 32);
-            uint64_t bw = ((uint64_t)hi << 32) | lo;
-            uint64_t remaining = a.n_bases > sc.t0 + 16ull * t ? a.n_bases - (sc.t0 + 16ull * t) : 0;
+            const int b0 = 16 * t;                                   // bit q of bw: a row starts at base 16t + q
+            const uint32_t lo = bits32(bnd, b0), hi = bits32(bnd, b0 + 32);
+            const uint64_t bw = ((uint64_t)hi << 32) | lo;
+            const uint64_t remaining = a.n_bases > sc.t0 + 16ull * t ? a.n_bases - (sc.t0 + 16ull * t) : 0;
+            if (remaining >= 16 && ((bw >> 1) & ((1ull << (15 + k - 1)) - 1ull)) == 0) vmask = 0x1fffeu;   // the common case
+            else {
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-                bool ok = (((uint32_t)(bw >> j) & sc.kmask) == 0) && ((uint64_t)j < remaining);
-                vmask |= (uint32_t)ok << j;
+                for (int j = 0; j < 16; j++) {
+                    bool ok = (((uint32_t)(bw >> (j + 1)) & sc.kmask) == 0) && ((uint64_t)j < remaining);
+                    vmask |= (uint32_t)ok << (j + 1);
+                }
             }
+            if (t && remaining && (lo & sc.kmask) == 0) vmask |= 1u;  // window 16t-1: bits 16t .. 16t+k-2
         }
-        uint32_t starts = 0, stops = 0x10000u;
-        uint32_t bk[16];
-        if (vmask) {
-            // hashed m-mers at bases 0 .. 15+W-1 of this chunk
-            uint32_t h[16 + W - 1];
+        uint32_t starts = 0;
+        uint32_t h[17 + W - 1];                                       // h[j+1]: minimizer hash of window j
+        if (vmask >> 1) {
+            // hashed m-mers at bases -1 .. 15+W-1 of this chunk
 #pragma unroll
-            for (int j = 0; j < 16 + W - 1; j++) {
-                const int q = j >> 4, sh = (j & 15) * 2;
-                uint32_t top = __funnelshift_l(w[q + 1], w[q], sh);   // 16 bases starting at base j
+            for (int j = -1; j < 16 + W - 1; j++) {
+                uint32_t top;                                         // 16 bases starting at base j
+                if (j < 0) top = __funnelshift_l(w[0], wm1, 30);
+                else {
+                    const int q = j >> 4, sh = (j & 15) * 2;
+                    top = __funnelshift_l(w[q + 1], w[q], sh);
+                }
                 uint32_t mm = top >> mshift;
                 uint32_t x = mm * 0x9E3779B1u;
-                h[j] = x ^ (x >> 15);
+                h[j + 1] = x ^ (x >> 15);
             }
             // sliding minimum over W consecutive m-mers (log-step, W is a power of two)
 #pragma unroll
             for (int step = 1; step < W; step <<= 1) {
 #pragma unroll
-                for (int j = 0; j < 16 + W - 1 - step; j++) h[j] = min(h[j], h[j + step]);
+                for (int j = 0; j < 17 + W - 1 - step; j++) h[j] = min(h[j], h[j + step]);
             }
-            // bucket of every window; run starts
-            uint32_t prevb = 0;
-            int len = 0;
+            // a run starts where the minimizer changes (identical k-mers have identical minimizers, hence the same
+            // bucket = mix(minimizer hash); the bucket itself is only computed once per run, at emission)
 #pragma unroll
             for (int j = 0; j < 16; j++) {
-                uint32_t b = __umulhi(mix32(h[j]), plan.n_buckets);
-                bk[j] = b;
-                bool v = (vmask >> j) & 1u;
-                bool st = v && (len == 0 || b != prevb || len == rmax);
-                len = st ? 1 : (v ? len + 1 : 0);
-                starts |= (uint32_t)st << j;
-                prevb = b;
+                const bool v = (vmask >> (j + 1)) & 1u, pv = (vmask >> j) & 1u;
+                starts |= (uint32_t)(v && (!pv || h[j + 1] != h[j])) << j;
             }
-            stops = starts | ~vmask | 0x10000u;   // a run ends before the next start / invalid / chunk end
         }
-        // ---- the tile's runs, compacted into one list (block-wide exclusive scan of the per-thread run counts)
+        const uint32_t bd = (starts | ~(vmask >> 1)) & 0xffffu;
+        reinterpret_cast<uint16_t*>(bdm)[t] = (uint16_t)bd;
+        // ---- the warp's runs, compacted into the warp's own list (warp-wide exclusive scan of the run counts)
         const uint32_t nrun = __popc(starts);
         uint32_t incl = nrun;
 #pragma unroll
@@ -127,73 +167,55 @@ __global__ void __launch_bounds__(NT) partition_kernel(ScanArgs a, PartitionPlan
             uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += n;
         }
-        if (lane == 31) wtot[warp] = incl;
-        __syncthreads();
-        uint32_t rbase = incl - nrun, n_tile_runs = 0;
+        const uint32_t n_warp_runs = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned long long* wruns = runs + warp * 512;
+        if (starts) {
+            uint32_t rbase = incl - nrun;
 #pragma unroll
-        for (int q = 0; q < NT / 32; q++) {
-            uint32_t v = wtot[q];
-            if (q < warp) rbase += v;
-            n_tile_runs += v;
+            for (int j = 0; j < 16; j++)
+                if ((starts >> j) & 1u) wruns[rbase++] = ((unsigned long long)h[j + 1] << 32) | (uint32_t)(16 * t + j);
         }
-        if (vmask) {
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-                if ((starts >> j) & 1u) {
-                    const uint32_t L = __ffs(stops >> (j + 1));            // 1..16 windows
-                    runs[rbase++] = ((unsigned long long)bk[j] << 32) | (L << 16) | (uint32_t)(16 * t + j);
-                }
-            }
-        }
-        __syncthreads();
-        // ---- flat emission: run r of the tile is handled by thread r % NT; EMIT_Q slot reservations
-        //      (64-bit atomicAdd with return) are in flight per thread before any of them is consumed
+        __syncthreads();                                              // boundary bits of the whole tile are visible
+        // ---- emission: run i of the warp is handled by lane i % 32; EMIT_Q slot reservations (64-bit atomicAdd with
+        //      return) are in flight per lane before any of them is consumed
         constexpr int EMIT_Q = 6;
-        for (uint32_t r0 = 0; r0 < n_tile_runs; r0 += EMIT_Q * NT) {
-            unsigned long long d[EMIT_Q], oldq[EMIT_Q];
-            bool act[EMIT_Q];
+        for (uint32_t r0 = 0; r0 < n_warp_runs; r0 += EMIT_Q * 32) {
+            uint32_t pR[EMIT_Q], bq[EMIT_Q], slot[EMIT_Q];           // (windows << 16) | start base ; bucket ; region slot
 #pragma unroll
             for (int q = 0; q < EMIT_Q; q++) {
-                const uint32_t r = r0 + q * NT + t;
-                act[q] = r < n_tile_runs;
-                d[q] = act[q] ? runs[r] : 0ull;
+                const uint32_t r = r0 + q * 32 + lane;
+                pR[q] = 0; bq[q] = 0;
+                if (r < n_warp_runs) {
+                    const unsigned long long d = wruns[r];
+                    bq[q] = __umulhi(mix32((uint32_t)(d >> 32)), plan.n_buckets);
+                    // the run ends before the next boundary bit after its first window
+                    uint32_t p = (uint32_t)d + 1, R = 1;
+                    for (;;) {
+                        const uint32_t nb32 = bits32(bdm, p);
+                        if (nb32) { R += __ffs(nb32) - 1; break; }
+                        R += 32; p += 32;
+                    }
+                    pR[q] = (R << 16) | (uint32_t)d;
+                }
             }
 #pragma unroll
-            for (int q = 0; q < EMIT_Q; q++)
-                oldq[q] = !act[q] ? 0ull
-                          : (plan.debug & 2) ? (unsigned long long)((mix32((uint32_t)d[q] + (uint32_t)sc.tile) >> 8) % plan.cap)
-                                             : atomicAdd(&fill[(uint32_t)(d[q] >> 32)], ((d[q] & 0xff0000ull) << 16) | 1ull);
+            for (int q = 0; q < EMIT_Q; q++) {
+                const uint32_t R = pR[q] >> 16;
+                const unsigned long long L0 = R < rmax ? R : rmax;
+                slot[q] = !R ? 0u
+                          : (plan.debug & 2) ? ((mix32(pR[q] + (uint32_t)sc.tile) >> 8) % plan.cap)
+                                             : (uint32_t)atomicAdd(&fill[bq[q]], (L0 << 32) | 1ull);
+            }
 #pragma unroll
             for (int q = 0; q < EMIT_Q; q++) {
-                if (!act[q]) continue;
-                const uint32_t b = (uint32_t)(d[q] >> 32);
-                const int L = (int)((d[q] >> 16) & 0xffu);
-                const int p = (int)(d[q] & 0xffffu);
-                const int c = p >> 4, sh = 2 * (p & 15);
-                const uint32_t w0 = s.packed[c], w1 = s.packed[c + 1], w2 = s.packed[c + 2], w3 = s.packed[c + 3];
-                const uint32_t r0w = __funnelshift_l(w1, w0, sh), r1w = __funnelshift_l(w2, w1, sh), r2w = __funnelshift_l(w3, w2, sh);
-                const int nb = L + k - 1;                                  // bases covered
-                const uint32_t slot = (uint32_t)oldq[q];
-                Rec<RECW>* dst = nullptr;
-                if (slot < plan.cap) dst = recs + ((uint64_t)b * plan.cap + slot);
-                else {                                                      // region full: spill list (tier 2), else recount
-                    unsigned long long si = atomicAdd(&a.status->n_spill, 1ull);
-                    if (si < plan.spill_cap) dst = spill + si;
-                    else overflow_kmers += L;
-                }
-                if (dst && !(plan.debug & 1)) {
-                    if (RECW == 1) {
-                        uint64_t v = ((uint64_t)r0w << 32) | r1w;
-                        v &= ~0ull << (64 - 2 * nb);                       // nb <= 30
-                        reinterpret_cast<uint64_t*>(dst)[0] = v | (uint64_t)(L - 1);
-                    } else {
-                        uint64_t hi = ((uint64_t)r0w << 32) | r1w;
-                        uint64_t lo = (uint64_t)r2w << 32;                  // bases 32..47 (nb <= 47)
-                        if (nb <= 32) { hi &= ~0ull << (64 - 2 * nb); lo = 0; }
-                        else lo &= ~0ull << (128 - 2 * nb);
-                        ulonglong2 o; o.x = hi; o.y = lo | (uint64_t)(L - 1);
-                        reinterpret_cast<ulonglong2*>(dst)[0] = o;
-                    }
+                const uint32_t R = pR[q] >> 16;
+                if (!R) continue;
+                const int p = (int)(pR[q] & 0xffffu);
+                put_record(bq[q], slot[q], p, (int)(R < rmax ? R : rmax));
+                for (uint32_t off = rmax; off < R; off += rmax) {   // a run longer than one record holds (repetitive text)
+                    const uint32_t L = R - off < rmax ? R - off : rmax;
+                    const unsigned long long o2 = atomicAdd(&fill[bq[q]], ((unsigned long long)L << 32) | 1ull);
+                    put_record(bq[q], (uint32_t)o2, p + (int)off, (int)L);
                 }
             }
         }
@@ -229,7 +251,7 @@ __global__ void __launch_bounds__(NT) partition_kernel(ScanArgs a, PartitionPlan
 // above LEAF_MAX_KMERS, or whose region overflowed in the partition pass, go to tier 2 up front.
 // Shared memory is addressed through explicit 32-bit shared addresses (ld/st/atom.shared PTX).
 
-constexpr int LEAF_KPT = 8;                                          // k-mers per thread
+constexpr int LEAF_KPT = 2048 / LEAF_THREADS;                        // k-mers per thread
 constexpr uint32_t LEAF_MAX_KMERS = LEAF_KPT * LEAF_THREADS - 1;    // 2047 < LEAF_SLOTS: the table can never fill up
 constexpr int LEAF_CELLS = 32768;                                    // bits per filter bitmap
 constexpr int LEAF_WARPS = LEAF_THREADS / 32;
@@ -336,7 +358,7 @@ __device__ __forceinline__ BucketInfo bucket_info(const unsigned long long* __re
 }
 
 template <int RECW, bool MULTI>
-__global__ void __launch_bounds__(LEAF_THREADS, 5) bucket_count_kernel(PartitionPlan plan, int k,
+__global__ void __launch_bounds__(LEAF_THREADS, 1280 / LEAF_THREADS) bucket_count_kernel(PartitionPlan plan, int k,
                                                                        const unsigned long long* __restrict__ fill,
                                                                        const Rec<RECW>* __restrict__ recs,
                                                                        kmer_count_pair* __restrict__ out, uint64_t capacity,
@@ -453,7 +475,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, 5) bucket_count_kernel(Partition
         __syncthreads();                                                // (S) also: the previous bucket is fully emitted
         // bitmap A doubled as the previous bucket's slow list / claimed-slot lists: clear it now; the other record
         // buffer is free as well: start the next bucket's copy
-        sts128(bma_s + 16 * t, 0u, 0u, 0u, 0u);
+        for (int i = t; i < LEAF_CELLS / 128; i += LEAF_THREADS) sts128(bma_s + 16 * i, 0u, 0u, 0u, 0u);
         if (t == 0 && nxt.usable()) issue(b_next, rb ^ 1u);
         uint32_t kbase = incl - mysum, nk = 0;
 #pragma unroll
@@ -550,7 +572,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, 5) bucket_count_kernel(Partition
             if (nu) ubase = atomicAdd(&status->n_distinct, (unsigned long long)nu);   // consumed after the next barrier
         }
         // bitmap B is dead: clear it for the next bucket
-        sts128(bmb_s + 16 * t, 0u, 0u, 0u, 0u);
+        for (int i = t; i < LEAF_CELLS / 128; i += LEAF_THREADS) sts128(bmb_s + 16 * i, 0u, 0u, 0u, 0u);
         // ---- count: the slow list is cut into one slice per warp, but never thinner than 32 entries (a warp pays for
         //      the probe loop whether 1 or 32 of its lanes are busy)
         const uint32_t slice = max(32u, (ns + LEAF_WARPS - 1) / LEAF_WARPS);
@@ -740,8 +762,8 @@ PartitionPlan make_partition_plan(uint64_t n_kmers, int k) {
     if (nb < 1) nb = 1;
     if (nb > 0x7fffffffull) nb = 0x7fffffffull;
     p.n_buckets = (uint32_t)nb;
-    {   // records per bucket: about 2/(w+1) + 1/16 records per k-mer (runs also end at 16-window chunk borders)
-        const double rpk = 2.0 / (p.w + 1) + 1.0 / 16.0 + (p.rmax < p.w ? 1.0 / p.rmax : 0.0);
+    {   // records per bucket: about 2/(w+1) records per k-mer (runs end where the minimizer changes, and at tile borders)
+        const double rpk = 2.1 / (p.w + 1) + (p.rmax < p.w ? 1.0 / p.rmax : 0.0);
         const double mean = TARGET_KMERS_PER_BUCKET * rpk;
         p.cap = ((uint32_t)(1.25 * mean + 5.0 * sqrt(3.0 * mean) + 16.0) + 1u) & ~1u;
     }
@@ -759,7 +781,7 @@ void launch_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPl
                       void* d_recs, void* d_spill, cudaStream_t st) {
     cudaMemsetAsync(d_fill, 0, (size_t)p.n_buckets * sizeof(unsigned long long), st);
     uint64_t n_tiles = (a.n_bases + TILE - 1) / TILE;
-    uint64_t grid = (uint64_t)di.sm_count * 5;
+    uint64_t grid = (uint64_t)di.sm_count * PART_MINB;
     if (grid > n_tiles) grid = n_tiles;
     if (!n_tiles) return;
     if (p.w == 4) partition_kernel<4, 1><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill);
