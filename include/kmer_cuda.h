@@ -184,12 +184,14 @@ int kmer_cuda_dev_decode(kmer_cuda_ctx *ctx, const uint64_t *d_codes, uint64_t n
 int kmer_cuda_dev_finish(kmer_cuda_ctx *ctx, void *stream, kmer_dev_result *result);
 
 /* ---------------------------------------------------------------- sharded counting (one process per GPU)
- * Counting shards by row: every GPU partitions ITS rows' k-mers into the same global set of
- * minimizer buckets, bucket b is owned by GPU b / buckets_per_rank, one all-to-all moves every
- * bucket segment to its owner, and each owner counts its buckets.  Identical k-mers share a
- * minimizer, hence a bucket, hence an owner: the per-GPU results are disjoint and the GROUP BY
- * result is their concatenation.  The library does no communication itself; the caller runs the
- * exchange (NCCL all-to-all with equal splits in bench.py / sharded.py; ncclSend/ncclRecv from C):
+ * Counting shards by row.  Every GPU partitions ITS rows' k-mers (as super-k-mer records) into the same global
+ * set of coarse minimizer partitions; partition p is owned by GPU p / buckets_per_rank; one all-to-all moves
+ * every (partition, source) segment to its owner; the owner splits its partitions into 2^fine_shift fine buckets
+ * each and counts those on chip.  Identical k-mers share a minimizer, hence a partition, hence an owner: the
+ * per-GPU results are disjoint and the GROUP BY result is their concatenation.  The number of regions a source
+ * GPU scatters into (n_buckets) does not grow with the size of the job, only their size does.
+ * The library does no communication itself; the caller runs the exchange (NCCL all-to-all with equal splits in
+ * bench.py / sharded.py; ncclSend/ncclRecv from C):
  *
  *   kmer_cuda_shard_plan()            same arguments on every rank -> same plan
  *   kmer_cuda_dev_shard_partition()   rows -> send_recs [n_buckets][cap] records, send_fill [n_buckets]
@@ -200,14 +202,17 @@ int kmer_cuda_dev_finish(kmer_cuda_ctx *ctx, void *stream, kmer_dev_result *resu
 typedef struct kmer_shard_plan
 {
 	uint32_t n_ranks;
-	uint32_t n_buckets;		   /* global; = n_ranks * buckets_per_rank */
+	uint32_t n_buckets;		   /* coarse partitions, global; = n_ranks * buckets_per_rank */
 	uint32_t buckets_per_rank;
-	uint32_t cap;			   /* records per (bucket, source GPU) segment */
+	uint32_t cap;			   /* records per (partition, source GPU) segment; even */
 	int32_t k;
 	int32_t rec_bytes;		   /* 8 (k <= 26) or 16 */
 	uint64_t recs_bytes_per_peer; /* buckets_per_rank * cap * rec_bytes */
 	uint64_t fill_bytes_per_peer; /* buckets_per_rank * 8 */
 	int32_t w, m, recw, rmax;  /* minimizer window / m-mer length / record words / max k-mers per record */
+	uint32_t fine_shift;	   /* every partition is split into 2^fine_shift fine buckets by its owner */
+	uint32_t fine_cap;		   /* records per fine bucket region (owner side workspace) */
+	uint32_t reserved[2];
 } kmer_shard_plan;
 
 int kmer_cuda_shard_plan(uint64_t total_kmers_all_ranks, int k, uint32_t n_ranks, kmer_shard_plan *plan);

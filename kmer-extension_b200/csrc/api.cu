@@ -677,6 +677,9 @@ extern "C" int kmer_cuda_dev_finish(kmer_cuda_ctx* c, void* stream, kmer_dev_res
     } else if (op == OP_SHARD_COUNT) {
         if (s.out_overflow)
             return set_error(&c->err, KMER_ERR_CAPACITY, "XX000", "kmer_cuda: output buffer too small", "", -1);
+        if (c->last_overflow)
+            return set_error(&c->err, KMER_ERR_CAPACITY, "XX000",
+                             "kmer_cuda: the spill list overflowed (input too repetitive for the sharded partition path)", "", -1);
         if (result) {
             result->n_kmers = s.n_kmers;
             result->n_distinct = s.n_distinct;
@@ -693,34 +696,56 @@ extern "C" int kmer_cuda_dev_finish(kmer_cuda_ctx* c, void* stream, kmer_dev_res
 
 extern "C" int kmer_cuda_shard_plan(uint64_t total_kmers, int k, uint32_t n_ranks, kmer_shard_plan* plan) {
     if (!plan || n_ranks < 1 || n_ranks > 16 || k < 14 || k > KMER_CUDA_MAX_K) return KMER_ERR_BAD_ARGUMENT;
+    // fine buckets as on one GPU (about 1000 k-mers each), 2^fine_shift of them per coarse partition
     PartitionPlan p = make_partition_plan(total_kmers, k);
+    uint64_t fine_per_rank = ((uint64_t)p.n_buckets + n_ranks - 1) / n_ranks;
+    uint32_t fine_shift = 8;
+    while (fine_shift > 0 && (1ull << fine_shift) > fine_per_rank) fine_shift--;
+    uint64_t coarse_per_rank = (fine_per_rank + (1ull << fine_shift) - 1) >> fine_shift;
+    if (coarse_per_rank * n_ranks << fine_shift > 0x7fffffffull) return KMER_ERR_BAD_ARGUMENT;
     memset(plan, 0, sizeof(*plan));
     plan->n_ranks = n_ranks;
-    plan->buckets_per_rank = (p.n_buckets + n_ranks - 1) / n_ranks;
+    plan->buckets_per_rank = (uint32_t)coarse_per_rank;
     plan->n_buckets = plan->buckets_per_rank * n_ranks;
+    plan->fine_shift = fine_shift;
+    plan->fine_cap = p.cap;
     plan->k = k;
     plan->w = p.w; plan->m = p.m; plan->recw = p.recw; plan->rmax = p.rmax;
     plan->rec_bytes = p.recw == 1 ? 8 : 16;
-    if (n_ranks == 1) plan->cap = p.cap;
-    else {
-        // records per (bucket, source): about 2/(w+1) + 1/16 records per k-mer, 1/n_ranks of a bucket's k-mers
-        double kmers_per_bucket = (double)total_kmers / (double)plan->n_buckets;
-        double rpk = 2.0 / (p.w + 1) + 1.0 / 16.0 + (p.rmax < p.w ? 1.0 / p.rmax : 0.0);
-        double mean = kmers_per_bucket * rpk / n_ranks;
-        double cap = 1.35 * mean + 6.0 * sqrt(2.0 * mean) + 16.0;
-        plan->cap = ((uint32_t)cap + 1u) & ~1u;   // even: every (bucket, source) segment starts 16-byte aligned
+    {   // records per (coarse partition, source): 1/n_ranks of a partition's k-mers, about 2.1/(w+1) records per k-mer
+        double kmers_per_part = (double)total_kmers / (double)plan->n_buckets;
+        double rpk = 2.1 / (p.w + 1) + (p.rmax < p.w ? 1.0 / p.rmax : 0.0);
+        double mean = kmers_per_part * rpk / n_ranks;
+        double cap = 1.15 * mean + 6.0 * sqrt(3.0 * mean) + 64.0;
+        plan->cap = ((uint32_t)cap + 1u) & ~1u;   // even: every (partition, source) segment starts 16-byte aligned
     }
     plan->recs_bytes_per_peer = (uint64_t)plan->buckets_per_rank * plan->cap * plan->rec_bytes;
     plan->fill_bytes_per_peer = (uint64_t)plan->buckets_per_rank * 8;
     return KMER_OK;
 }
 
-static PartitionPlan to_partition_plan(const kmer_shard_plan* sp, uint32_t n_buckets) {
+// the source side scatters into coarse partitions; the hash range is the global number of fine buckets
+static PartitionPlan coarse_partition_plan(const kmer_shard_plan* sp) {
     PartitionPlan p{};
-    p.n_buckets = n_buckets;
+    p.n_buckets = sp->n_buckets;
+    p.hash_buckets = sp->n_buckets << sp->fine_shift;
+    p.fine_shift = (int)sp->fine_shift;
     p.cap = sp->cap;
     p.w = sp->w; p.m = sp->m; p.recw = sp->recw; p.rmax = sp->rmax;
-    p.spill_cap = 0;   // no spill list when sharded: a full segment is an error reported by finish()
+    p.spill_cap = 0;   // no spill list on the source side: a full segment is an error reported by finish()
+    p.debug = 0;
+    return p;
+}
+// the owner side: this GPU's fine buckets (local numbering), counted like a single-GPU batch
+static PartitionPlan fine_partition_plan(const kmer_shard_plan* sp) {
+    PartitionPlan p{};
+    p.n_buckets = sp->buckets_per_rank << sp->fine_shift;
+    p.hash_buckets = sp->n_buckets << sp->fine_shift;
+    p.fine_shift = (int)sp->fine_shift;
+    p.cap = sp->fine_cap;
+    p.w = sp->w; p.m = sp->m; p.recw = sp->recw; p.rmax = sp->rmax;
+    uint64_t sc = (uint64_t)p.n_buckets * p.cap / 8;
+    p.spill_cap = sc < 4096 ? 4096 : sc;
     p.debug = 0;
     return p;
 }
@@ -735,7 +760,7 @@ extern "C" int kmer_cuda_dev_shard_partition(kmer_cuda_ctx* c, const char* d_seq
     c->pending = OP_SHARD_PART;
     c->p_n_bases = n_bases; c->p_n_rows = n_rows; c->p_k = sp->k;
     c->p_expected_kmers = kmer_cuda_max_kmers(n_bases, n_rows, sp->k);
-    PartitionPlan plan = to_partition_plan(sp, sp->n_buckets);
+    PartitionPlan plan = coarse_partition_plan(sp);
     if (n_rows == 0 || n_bases == 0) {
         if (n_rows) return ref_error(&c->err, KMER_ERR_INVALID_K, 0);
         CU(cudaMemsetAsync(d_send_fill, 0, (size_t)sp->n_buckets * 8, st), "memset fill");
@@ -763,24 +788,32 @@ extern "C" int kmer_cuda_dev_shard_count(kmer_cuda_ctx* c, const kmer_shard_plan
     c->last_overflow = 0;
     c->last_tier2 = 0;
     const int k = sp->k;
-    PartitionPlan plan = to_partition_plan(sp, sp->buckets_per_rank);
-    if ((uint64_t)sp->cap * sp->n_ranks + 2ull * sp->n_ranks > 4096 || (sp->cap & 1u))
-        return bad_arg(c, "shard plan: cap must be even and cap * n_ranks must stay below 4096 staged records");
-    rc = ws(c, c->failed, (size_t)plan.n_buckets * 4);
+    if ((sp->cap & 1u) || sp->fine_shift > 12) return bad_arg(c, "shard plan: cap must be even, fine_shift <= 12");
+    // coarse partitions (one segment per source GPU) -> this GPU's fine buckets, then counted like a single-GPU batch
+    PartitionPlan plan = fine_partition_plan(sp);
+    rc = ws(c, c->fill, (size_t)plan.n_buckets * 8);
+    if (!rc) rc = ws(c, c->recs, partition_record_bytes(plan));
+    if (!rc) rc = ws(c, c->spill, partition_spill_bytes(plan));
+    if (!rc) rc = ws(c, c->failed, (size_t)plan.n_buckets * 4);
     if (rc) return rc;
-    launch_bucket_count(c->di, plan, k, (int)sp->n_ranks, (const unsigned long long*)d_recv_fill, d_recv_recs,
-                        (uint32_t*)c->failed.p, d_pairs, pairs_capacity, c->d_status, st);
+    launch_refine(c->di, plan, k, (int)sp->n_ranks, sp->buckets_per_rank, sp->cap, (const unsigned long long*)d_recv_fill,
+                  d_recv_recs, (unsigned long long*)c->fill.p, c->recs.p, c->spill.p, c->d_status, st);
+    mark(c, st, "refine");
+    launch_bucket_count(c->di, plan, k, 1, (const unsigned long long*)c->fill.p, c->recs.p, (uint32_t*)c->failed.p, d_pairs,
+                        pairs_capacity, c->d_status, st);
     mark(c, st, "bucket_count");
-    c->launches++;
+    c->launches += 2;
     CU(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, st), "D2H status");
     CU(cudaStreamSynchronize(st), "stream sync");
     const DevStatus hs = *c->h_status;
-    if (hs.n_failed) {   // tier 2: buckets that did not fit on chip (all their segments are here)
-        uint64_t n_slots = next_pow2(std::max<uint64_t>(1024, hs.failed_kmers * 2));
+    if (hs.n_overflow != 0) {
+        c->last_overflow = hs.n_overflow;   // even the spill list overflowed: reported by finish() as KMER_ERR_CAPACITY
+    } else if (hs.n_failed || hs.n_spill) {   // tier 2: only the buckets that did not fit on chip
+        uint64_t n_slots = next_pow2(std::max<uint64_t>(1024, (hs.failed_kmers + hs.n_spill * 16) * 2));
         rc = ws(c, c->table, n_slots * sizeof(kmer_count_pair));
         if (rc) return rc;
         launch_hash_clear((kmer_count_pair*)c->table.p, n_slots, st);
-        launch_partition_tier2(c->di, plan, k, (int)sp->n_ranks, (const unsigned long long*)d_recv_fill, d_recv_recs, nullptr,
+        launch_partition_tier2(c->di, plan, k, 1, (const unsigned long long*)c->fill.p, c->recs.p, c->spill.p,
                                (const uint32_t*)c->failed.p, (kmer_count_pair*)c->table.p, n_slots, c->d_status, st);
         mark(c, st, "tier2_insert");
         launch_hash_compact(c->di, (const kmer_count_pair*)c->table.p, n_slots, k, d_pairs, pairs_capacity, c->d_status, st);

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(NT, PART_MINB) partition_kernel(ScanArgs a, Pa
                 pR[q] = 0; bq[q] = 0;
                 if (r < n_warp_runs) {
                     const unsigned long long d = wruns[r];
-                    bq[q] = __umulhi(mix32((uint32_t)(d >> 32)), plan.n_buckets);
+                    bq[q] = __umulhi(mix32((uint32_t)(d >> 32)), plan.hash_buckets) >> plan.fine_shift;
                     // the run ends before the next boundary bit after its first window
                     uint32_t p = (uint32_t)d + 1, R = 1;
                     for (;;) {
@@ -673,6 +673,84 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1280 / LEAF_THREADS) bucket_coun
     if (t == 0 && kmers_total) atomicAdd(&status->n_kmers, kmers_total);
 }
 
+// ---------------------------------------------------------------------------------------------
+// sharded counting, owner side: coarse partitions -> fine buckets
+//
+// A source GPU scatters its records over few, large coarse partitions (n_ranks * n_coarse of them: the scatter cost
+// grows with the number of open regions, which must not grow with the size of the whole job).  After the exchange
+// the owner splits every coarse partition into its 2^fine_shift fine buckets: one CTA per coarse partition, slot
+// counters in shared memory (no global atomics), all stores of a CTA inside one small window of HBM.  The bucket of
+// a record is recomputed from its first window: it is the bucket of the run's minimizer, as in partition_kernel.
+template <int W, int RECW>
+__global__ void __launch_bounds__(256) refine_kernel(PartitionPlan plan, int k, int n_src, uint32_t n_coarse, uint32_t coarse_cap,
+                                                     const unsigned long long* __restrict__ recv_fill,
+                                                     const Rec<RECW>* __restrict__ recv_recs, unsigned long long* __restrict__ fill,
+                                                     Rec<RECW>* __restrict__ recs, Rec<RECW>* __restrict__ spill, DevStatus* status) {
+    extern __shared__ uint32_t refine_smem[];       // [F] records, [F] k-mers
+    const uint32_t F = 1u << plan.fine_shift;
+    uint32_t* s_nrec = refine_smem;
+    uint32_t* s_nk = refine_smem + F;
+    const int t = threadIdx.x;
+    const uint32_t mshift = 32 - 2 * plan.m;
+    unsigned long long overflow_kmers = 0;
+    for (uint32_t c = blockIdx.x; c < n_coarse; c += gridDim.x) {
+        for (uint32_t f = t; f < 2 * F; f += blockDim.x) refine_smem[f] = 0;
+        __syncthreads();
+        for (int sI = 0; sI < n_src; sI++) {
+            const uint32_t n = min((uint32_t)recv_fill[(uint64_t)sI * n_coarse + c], coarse_cap);
+            const Rec<RECW>* base = recv_recs + ((uint64_t)sI * n_coarse + c) * coarse_cap;
+            constexpr int RQ = 4;                                 // records in flight per thread
+            for (uint32_t i0 = t; i0 < n; i0 += RQ * blockDim.x) {
+                uint64_t hi[RQ], lo[RQ];
+#pragma unroll
+                for (int q = 0; q < RQ; q++) {
+                    const uint32_t i = i0 + q * blockDim.x;
+                    hi[q] = 0; lo[q] = 0;
+                    if (i < n) {
+                        if (RECW == 1) hi[q] = ld_nc_u64(reinterpret_cast<const uint64_t*>(base + i));
+                        else {
+                            const uint4 raw = ld_nc_u128(base + i);
+                            hi[q] = ((uint64_t)raw.y << 32) | raw.x;
+                            lo[q] = ((uint64_t)raw.w << 32) | raw.z;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < RQ; q++) {
+                    if (i0 + q * blockDim.x >= n) break;
+                    const uint32_t L = (RECW == 1 ? (uint32_t)(hi[q] & 15u) : (uint32_t)(lo[q] & 63u)) + 1;
+                    uint32_t hmin = 0xffffffffu;                  // minimizer hash of the record's first window
+#pragma unroll
+                    for (int j = 0; j < W; j++) {
+                        const uint32_t top = (uint32_t)((hi[q] << (2 * j)) >> 32);
+                        const uint32_t x = (top >> mshift) * 0x9E3779B1u;
+                        hmin = min(hmin, x ^ (x >> 15));
+                    }
+                    const uint32_t f = __umulhi(mix32(hmin), plan.hash_buckets) & (F - 1);
+                    const uint32_t slot = atomicAdd(&s_nrec[f], 1u);
+                    atomicAdd(&s_nk[f], L);
+                    Rec<RECW>* dst = nullptr;
+                    if (slot < plan.cap) dst = recs + ((uint64_t)c * F + f) * plan.cap + slot;
+                    else {                                        // region full: spill list (tier 2), else recount
+                        const unsigned long long si = atomicAdd(&status->n_spill, 1ull);
+                        if (si < plan.spill_cap) dst = spill + si;
+                        else overflow_kmers += L;
+                    }
+                    if (dst) {
+                        if (RECW == 1) reinterpret_cast<uint64_t*>(dst)[0] = hi[q];
+                        else { ulonglong2 o; o.x = hi[q]; o.y = lo[q]; reinterpret_cast<ulonglong2*>(dst)[0] = o; }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (uint32_t f = t; f < F; f += blockDim.x)
+            fill[(uint64_t)c * F + f] = ((unsigned long long)s_nk[f] << 32) | s_nrec[f];
+        __syncthreads();
+    }
+    if (overflow_kmers) atomicAdd(&status->n_overflow, overflow_kmers);
+}
+
 // tier 2: every k-mer of the failed buckets (their in-region records) and of the spill list goes into
 // a global open-addressing table (count_hash.cu layout); hash_compact then appends it to the result.
 // Failed buckets and spilled records hold k-mers of the same buckets only, so nothing here can also
@@ -762,6 +840,8 @@ PartitionPlan make_partition_plan(uint64_t n_kmers, int k) {
     if (nb < 1) nb = 1;
     if (nb > 0x7fffffffull) nb = 0x7fffffffull;
     p.n_buckets = (uint32_t)nb;
+    p.hash_buckets = p.n_buckets;
+    p.fine_shift = 0;
     {   // records per bucket: about 2/(w+1) records per k-mer (runs end where the minimizer changes, and at tile borders)
         const double rpk = 2.1 / (p.w + 1) + (p.rmax < p.w ? 1.0 / p.rmax : 0.0);
         const double mean = TARGET_KMERS_PER_BUCKET * rpk;
@@ -769,6 +849,11 @@ PartitionPlan make_partition_plan(uint64_t n_kmers, int k) {
     }
     uint64_t sc = (uint64_t)p.n_buckets * p.cap / 8;          // spill list: 1/8 of the bucket regions
     p.spill_cap = sc < 4096 ? 4096 : sc;
+    if (const char* nbs = getenv("KMER_CUDA_DEBUG_NBUCKETS")) {   // profiling experiment only: scatter to few, large regions
+        p.n_buckets = (uint32_t)atoi(nbs);
+        p.hash_buckets = p.n_buckets;
+        p.cap = (uint32_t)((double)n_kmers * 0.3 / p.n_buckets * 1.3 + 1024) & ~1u;
+    }
     const char* dbg = getenv("KMER_CUDA_DEBUG_PARTITION");   // profiling experiments only (bit0: no record stores, bit1: no slot atomics)
     p.debug = dbg ? atoi(dbg) : 0;
     return p;
@@ -817,13 +902,9 @@ void launch_bucket_count(const DeviceInfo& di, const PartitionPlan& p, int k, in
         bucket_count_kernel<RW, MU><<<(unsigned)lgrid, LEAF_THREADS, leaf_smem, st>>>(                                        \
             p, k, d_fill, (const Rec<RW>*)d_recs, d_pairs, capacity, d_failed_ids, d_status, n_src);                          \
     } while (0)
-    if (p.recw == 1) {
-        if (n_src > 1) KMER_LEAF_LAUNCH(1, true);
-        else KMER_LEAF_LAUNCH(1, false);
-    } else {
-        if (n_src > 1) KMER_LEAF_LAUNCH(2, true);
-        else KMER_LEAF_LAUNCH(2, false);
-    }
+    // (sharded counting merges the source segments in refine_kernel: the leaf always sees one segment per bucket)
+    if (p.recw == 1) KMER_LEAF_LAUNCH(1, false);
+    else KMER_LEAF_LAUNCH(2, false);
 #undef KMER_LEAF_LAUNCH
 }
 
@@ -847,6 +928,24 @@ void launch_partition_tier2(const DeviceInfo& di, const PartitionPlan& p, int k,
     else
         tier2_insert_kernel<2><<<grid, 256, 0, st>>>(p, k, d_fill, (const Rec<2>*)d_recs, d_failed_ids, (const Rec<2>*)d_spill,
                                                      d_slots, n_slots - 1, d_status, n_src);
+}
+
+void launch_refine(const DeviceInfo& di, const PartitionPlan& p, int k, int n_src, uint32_t n_coarse, uint32_t coarse_cap,
+                   const unsigned long long* d_recv_fill, const void* d_recv_recs, unsigned long long* d_fill,
+                   void* d_recs, void* d_spill, DevStatus* d_status, cudaStream_t st) {
+    if (!n_coarse) return;
+    unsigned grid = (unsigned)di.sm_count * 8;
+    if (grid > n_coarse) grid = n_coarse;
+    const size_t smem = (size_t)(2u << p.fine_shift) * sizeof(uint32_t);
+    if (p.w == 4)
+        refine_kernel<4, 1><<<grid, 256, smem, st>>>(p, k, n_src, n_coarse, coarse_cap, d_recv_fill, (const Rec<1>*)d_recv_recs,
+                                                     d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill, d_status);
+    else if (p.w == 8)
+        refine_kernel<8, 1><<<grid, 256, smem, st>>>(p, k, n_src, n_coarse, coarse_cap, d_recv_fill, (const Rec<1>*)d_recv_recs,
+                                                     d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill, d_status);
+    else
+        refine_kernel<16, 2><<<grid, 256, smem, st>>>(p, k, n_src, n_coarse, coarse_cap, d_recv_fill, (const Rec<2>*)d_recv_recs,
+                                                      d_fill, (Rec<2>*)d_recs, (Rec<2>*)d_spill, d_status);
 }
 
 void launch_append_special(kmer_count_pair* d_pairs, uint64_t capacity, DevStatus* d_status, cudaStream_t st) {

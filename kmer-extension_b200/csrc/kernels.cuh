@@ -51,6 +51,8 @@ struct PartitionPlan {
     int recw;             // 64-bit words per super-k-mer record (1: k <= 26, 2: k >= 27)
     int rmax;             // max k-mers per record
     uint64_t spill_cap;   // records the spill list holds
+    uint32_t hash_buckets; // range the minimizer hash is scaled to (== n_buckets unless partitioning coarsely)
+    int fine_shift;       // bucket = scaled hash >> fine_shift (sharded counting: coarse partitions of 2^fine_shift buckets)
     int debug;            // profiling experiments only (env KMER_CUDA_DEBUG_PARTITION)
 };
 PartitionPlan make_partition_plan(uint64_t n_kmers, int k);
@@ -69,6 +71,11 @@ void launch_bucket_count(const DeviceInfo& di, const PartitionPlan& p, int k, in
 void launch_partition_tier2(const DeviceInfo& di, const PartitionPlan& p, int k, int n_src, const unsigned long long* d_fill,
                             const void* d_recs, const void* d_spill, const uint32_t* d_failed_ids, kmer_count_pair* d_slots,
                             uint64_t n_slots, DevStatus* d_status, cudaStream_t st);
+// sharded counting, owner side: the coarse partitions received from every source GPU ([src][n_coarse][coarse_cap] records,
+// [src][n_coarse] fills) are split into this GPU's fine buckets (p: n_buckets = n_coarse << fine_shift, cap, spill list)
+void launch_refine(const DeviceInfo& di, const PartitionPlan& p, int k, int n_src, uint32_t n_coarse, uint32_t coarse_cap,
+                   const unsigned long long* d_recv_fill, const void* d_recv_recs, unsigned long long* d_fill,
+                   void* d_recs, void* d_spill, DevStatus* d_status, cudaStream_t st);
 void launch_append_special(kmer_count_pair* d_pairs, uint64_t capacity, DevStatus* d_status, cudaStream_t st);
 
 // match.cu --------------------------------------------------------------------------------------
