@@ -540,22 +540,14 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1280 / LEAF_THREADS) bucket_coun
             }
         }
         const uint32_t uniq = valid & ~multi;
-        const uint32_t pk = __popc(uniq) | ((uint32_t)__popc(multi) << 16);   // per warp each half stays below 2^16
-        uint32_t pincl = pk;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t n = __shfl_up_sync(0xffffffffu, pincl, d);
-            if (lane >= d) pincl += n;
-        }
-        uint32_t woff = 0;                                              // the warp's offsets: unique (low) / slow (high)
-        if (lane == 31) {
-            const uint32_t u = (pincl & 0xffffu) ? atoms_add32(smem_u32(&s_nuniq[par]), pincl & 0xffffu) : 0u;
-            const uint32_t m = (pincl >> 16) ? atoms_add32(smem_u32(&s_nslow[par]), pincl >> 16) : 0u;
-            woff = u | (m << 16);
-        }
-        woff = __shfl_sync(0xffffffffu, woff, 31);
-        {
-            uint32_t sb = (woff >> 16) + (pincl >> 16) - __popc(multi);
+        // the warp's unique k-mers get a contiguous share of the bucket's output; every lane that has slow k-mers
+        // takes its slow-list positions with one shared atomicAdd
+        const uint32_t wuniq = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(uniq));
+        uint32_t woff = 0;
+        if (lane == 0 && wuniq) woff = atoms_add32(smem_u32(&s_nuniq[par]), wuniq);
+        woff = __shfl_sync(0xffffffffu, woff, 0);
+        if (multi) {
+            uint32_t sb = atoms_add32(smem_u32(&s_nslow[par]), (uint32_t)__popc(multi));
             uint32_t m2 = multi;
             while (m2) {
                 const uint32_t i = __ffs(m2) - 1;
@@ -627,16 +619,19 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1280 / LEAF_THREADS) bucket_coun
         if (t == 0) { s_nuniq[par ^ 1] = 0; s_nslow[par ^ 1] = 0; }   // idle until the next bucket's sort phase
         // ---- emit the unique k-mers: coalesced 16-byte (k-mer, 1) pairs, ranks by ballot
         {
-            unsigned long long ob = s_obase[par] + (woff & 0xffffu);
+            unsigned long long ob = s_obase[par] + woff;
+            const bool fits = ob + wuniq <= capacity;                   // uniform per warp
+            if (!fits && lane == 0) status->out_overflow = 1;
 #pragma unroll
             for (int i = 0; i < LEAF_KPT; i++) {
                 if (i * LEAF_THREADS >= nk) break;
-                const bool u = (uniq >> i) & 1u;
+                const bool u = fits && ((uniq >> i) & 1u);
                 const uint32_t m = __ballot_sync(0xffffffffu, u);
                 if (u) {
-                    const uint64_t idx = ob + __popc(m & lane_lt);
-                    if (idx < capacity) { ulonglong2 o; o.x = key_at(t + i * LEAF_THREADS); o.y = 1ull; reinterpret_cast<ulonglong2*>(out)[idx] = o; }
-                    else status->out_overflow = 1;
+                    ulonglong2 o;
+                    o.x = key_at(t + i * LEAF_THREADS);
+                    o.y = 1ull;
+                    reinterpret_cast<ulonglong2*>(out)[ob + __popc(m & lane_lt)] = o;
                 }
                 ob += __popc(m);
             }

@@ -1,2 +1,2 @@
 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "count or partition or kat_group or sharded or large or empty" 2>&1 | tail -3
-for c in 6 5; do KMER_CUDA_LEAF_CTAS=$c python tools/part_experiment.py 1000000 2>&1 | tail -1; done
+python tools/part_experiment.py 1000000 2>&1 | tail -1
