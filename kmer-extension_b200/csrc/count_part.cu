@@ -34,7 +34,7 @@ constexpr int LEAF_SLOTS = 2048;          // shared-memory table slots per bucke
 #define LEAF_THREADS_N 128
 #endif
 constexpr int LEAF_THREADS = LEAF_THREADS_N;
-constexpr uint32_t TARGET_KMERS_PER_BUCKET = 1000;   // about half of what a bucket may hold; the tail is handled by tier 2
+constexpr uint32_t TARGET_KMERS_PER_BUCKET = 1200;   // about half of what a bucket may hold; the tail is handled by tier 2
 
 // ---------------------------------------------------------------------------------------------
 // record formats
@@ -831,7 +831,9 @@ PartitionPlan make_partition_plan(uint64_t n_kmers, int k) {
     int m = k - p.w + 1;
     p.m = m > 16 ? 16 : m;
     p.rmax = p.recw == 1 ? (30 - k + 1 > 16 ? 16 : 30 - k + 1) : 16;
-    uint64_t nb = (n_kmers + TARGET_KMERS_PER_BUCKET - 1) / TARGET_KMERS_PER_BUCKET;
+    static const char* env_target = getenv("KMER_CUDA_BUCKET_KMERS");   // profiling experiments only
+    const uint32_t target = env_target ? (uint32_t)atoi(env_target) : TARGET_KMERS_PER_BUCKET;
+    uint64_t nb = (n_kmers + target - 1) / target;
     if (nb < 1) nb = 1;
     if (nb > 0x7fffffffull) nb = 0x7fffffffull;
     p.n_buckets = (uint32_t)nb;
@@ -839,7 +841,7 @@ PartitionPlan make_partition_plan(uint64_t n_kmers, int k) {
     p.fine_shift = 0;
     {   // records per bucket: about 2/(w+1) records per k-mer (runs end where the minimizer changes, and at tile borders)
         const double rpk = 2.1 / (p.w + 1) + (p.rmax < p.w ? 1.0 / p.rmax : 0.0);
-        const double mean = TARGET_KMERS_PER_BUCKET * rpk;
+        const double mean = target * rpk;
         p.cap = ((uint32_t)(1.25 * mean + 5.0 * sqrt(3.0 * mean) + 16.0) + 1u) & ~1u;
     }
     uint64_t sc = (uint64_t)p.n_buckets * p.cap / 8;          // spill list: 1/8 of the bucket regions
