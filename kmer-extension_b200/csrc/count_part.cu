@@ -175,49 +175,54 @@ __global__ void __launch_bounds__(NT, PART_MINB) partition_kernel(ScanArgs a, Pa
             for (int j = 0; j < 16; j++)
                 if ((starts >> j) & 1u) wruns[rbase++] = ((unsigned long long)h[j + 1] << 32) | (uint32_t)(16 * t + j);
         }
-        __syncthreads();                                              // boundary bits of the whole tile are visible
-        // ---- emission: run i of the warp is handled by lane i % 32; EMIT_Q slot reservations (64-bit atomicAdd with
-        //      return) are in flight per lane before any of them is consumed
+        // ---- emission: run i of the warp is handled by lane i % 32.  The region slots (64-bit atomicAdd with return on the
+        //      bucket's fill word, record count in the low half) are requested BEFORE the tile barrier: up to EMIT_Q round
+        //      trips per lane are in flight while the warp waits for the other warps' boundary bits.
         constexpr int EMIT_Q = 6;
-        for (uint32_t r0 = 0; r0 < n_warp_runs; r0 += EMIT_Q * 32) {
-            uint32_t pR[EMIT_Q], bq[EMIT_Q], slot[EMIT_Q];           // (windows << 16) | start base ; bucket ; region slot
+        __syncwarp();
+        uint32_t posq[EMIT_Q], bq[EMIT_Q], slot[EMIT_Q];             // start base ; bucket ; region slot
 #pragma unroll
-            for (int q = 0; q < EMIT_Q; q++) {
-                const uint32_t r = r0 + q * 32 + lane;
-                pR[q] = 0; bq[q] = 0;
-                if (r < n_warp_runs) {
-                    const unsigned long long d = wruns[r];
-                    bq[q] = __umulhi(mix32((uint32_t)(d >> 32)), plan.hash_buckets) >> plan.fine_shift;
-                    // the run ends before the next boundary bit after its first window
-                    uint32_t p = (uint32_t)d + 1, R = 1;
-                    for (;;) {
-                        const uint32_t nb32 = bits32(bdm, p);
-                        if (nb32) { R += __ffs(nb32) - 1; break; }
-                        R += 32; p += 32;
-                    }
-                    pR[q] = (R << 16) | (uint32_t)d;
-                }
+        for (int q = 0; q < EMIT_Q; q++) {
+            const uint32_t r = q * 32 + lane;
+            posq[q] = 0xffffffffu; bq[q] = 0; slot[q] = 0;
+            if (r < n_warp_runs) {
+                const unsigned long long d = wruns[r];
+                bq[q] = __umulhi(mix32((uint32_t)(d >> 32)), plan.hash_buckets) >> plan.fine_shift;
+                posq[q] = (uint32_t)d;
+                slot[q] = (plan.debug & 2) ? ((mix32(posq[q] + (uint32_t)sc.tile) >> 8) % plan.cap) : (uint32_t)atomicAdd(&fill[bq[q]], 1ull);
             }
+        }
+        __syncthreads();                                              // boundary bits of the whole tile are visible
+        auto run_length = [&](uint32_t p0) {                          // the run ends before the next boundary bit after its first window
+            uint32_t p = p0 + 1, R = 1;
+            for (;;) {
+                const uint32_t nb32 = bits32(bdm, p);
+                if (nb32) { R += __ffs(nb32) - 1; break; }
+                R += 32; p += 32;
+            }
+            return R;
+        };
+        // one run: its first record takes the slot reserved above; the k-mer count of the bucket (high half of the fill
+        // word) is bumped without a return value; a run longer than one record holds takes further slots (repetitive text)
+        auto emit_run = [&](uint32_t b, uint32_t slot0, uint32_t p0) {
+            const uint32_t R = run_length(p0);
+            const uint32_t L0 = R < rmax ? R : rmax;
+            if (!(plan.debug & 2)) atomicAdd(&fill[b], (unsigned long long)L0 << 32);
+            put_record(b, slot0, (int)p0, (int)L0);
+            for (uint32_t off = rmax; off < R; off += rmax) {
+                const uint32_t L = R - off < rmax ? R - off : rmax;
+                const unsigned long long o2 = atomicAdd(&fill[b], ((unsigned long long)L << 32) | 1ull);
+                put_record(b, (uint32_t)o2, (int)(p0 + off), (int)L);
+            }
+        };
 #pragma unroll
-            for (int q = 0; q < EMIT_Q; q++) {
-                const uint32_t R = pR[q] >> 16;
-                const unsigned long long L0 = R < rmax ? R : rmax;
-                slot[q] = !R ? 0u
-                          : (plan.debug & 2) ? ((mix32(pR[q] + (uint32_t)sc.tile) >> 8) % plan.cap)
-                                             : (uint32_t)atomicAdd(&fill[bq[q]], (L0 << 32) | 1ull);
-            }
-#pragma unroll
-            for (int q = 0; q < EMIT_Q; q++) {
-                const uint32_t R = pR[q] >> 16;
-                if (!R) continue;
-                const int p = (int)(pR[q] & 0xffffu);
-                put_record(bq[q], slot[q], p, (int)(R < rmax ? R : rmax));
-                for (uint32_t off = rmax; off < R; off += rmax) {   // a run longer than one record holds (repetitive text)
-                    const uint32_t L = R - off < rmax ? R - off : rmax;
-                    const unsigned long long o2 = atomicAdd(&fill[bq[q]], ((unsigned long long)L << 32) | 1ull);
-                    put_record(bq[q], (uint32_t)o2, p + (int)off, (int)L);
-                }
-            }
+        for (int q = 0; q < EMIT_Q; q++)
+            if (posq[q] != 0xffffffffu) emit_run(bq[q], slot[q], posq[q]);
+        for (uint32_t r = EMIT_Q * 32 + lane; r < n_warp_runs; r += 32) {   // more than 192 runs in 512 windows: rare
+            const unsigned long long d = wruns[r];
+            const uint32_t b = __umulhi(mix32((uint32_t)(d >> 32)), plan.hash_buckets) >> plan.fine_shift;
+            const uint32_t s0 = (plan.debug & 2) ? 0u : (uint32_t)atomicAdd(&fill[b], 1ull);
+            emit_run(b, s0, (uint32_t)d);
         }
         sc.release();
     }
