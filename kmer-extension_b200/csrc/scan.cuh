@@ -70,7 +70,7 @@ struct TileScanner {
         uint64_t avail = ((a.n_bases - p0) + 15) & ~15ull;    // buffer is readable up to the next 16 B
         uint32_t raw_bytes = avail < RAW_BYTES ? (uint32_t)avail : RAW_BYTES;
         mbar_arrive_expect_tx(&s.mbar[st], raw_bytes + BND_WORDS * 4);
-        bulk_g2s(s.raw[st], a.seq + p0, raw_bytes, &s.mbar[st]);
+        bulk_g2s_stream(s.raw[st], a.seq + p0, raw_bytes, &s.mbar[st], l2_evict_first_policy());
         bulk_g2s(s.bnd[st], a.row_mask + p0 / 32, BND_WORDS * 4, &s.mbar[st]);
     }
 

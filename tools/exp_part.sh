@@ -1,2 +1,1 @@
-python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "count or partition or kat_group or sharded or large or empty or boundaries" 2>&1 | tail -3
 for d in 0 3; do KMER_CUDA_DEBUG_PARTITION=$d python tools/part_experiment.py 1000000 2>&1 | tail -1; done
