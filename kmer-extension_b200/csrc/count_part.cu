@@ -73,6 +73,9 @@ __global__ void __launch_bounds__(NT, PART_MINB) partition_kernel(ScanArgs a, Pa
     const uint32_t mshift = 32 - 2 * m;
     unsigned long long overflow_kmers = 0;
     if (t < 2) bdm[TILE / 32 + t] = 0xffffffffu;   // the tile end ends every run
+    uint64_t pol_last, pol_first;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
 
     // one super-k-mer record: L windows starting at tile-relative base p go to bucket b
     auto put_record = [&](uint32_t b, uint32_t slot, int p, int L) {
@@ -91,14 +94,18 @@ __global__ void __launch_bounds__(NT, PART_MINB) partition_kernel(ScanArgs a, Pa
             if (RECW == 1) {
                 uint64_t v = ((uint64_t)r0w << 32) | r1w;
                 v &= ~0ull << (64 - 2 * nb);                       // nb <= 30
-                reinterpret_cast<uint64_t*>(dst)[0] = v | (uint64_t)(L - 1);
+                // a region's last, partially written 32-byte sector must stay in L2 until it is complete (else every
+                // record costs a sector fill from HBM): evict-last while it fills up, evict-first with its fourth record
+                const uint64_t pol = (slot & 3u) == 3u ? pol_first : pol_last;
+                asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(dst), "l"(v | (uint64_t)(L - 1)), "l"(pol) : "memory");
             } else {
                 uint64_t hi = ((uint64_t)r0w << 32) | r1w;
                 uint64_t lo = (uint64_t)r2w << 32;                  // bases 32..47 (nb <= 47)
                 if (nb <= 32) { hi &= ~0ull << (64 - 2 * nb); lo = 0; }
                 else lo &= ~0ull << (128 - 2 * nb);
-                ulonglong2 o; o.x = hi; o.y = lo | (uint64_t)(L - 1);
-                reinterpret_cast<ulonglong2*>(dst)[0] = o;
+                const uint64_t pol = (slot & 1u) ? pol_first : pol_last;
+                asm volatile("st.global.L2::cache_hint.v2.u64 [%0], {%1, %2}, %3;" ::"l"(dst), "l"(hi), "l"(lo | (uint64_t)(L - 1)), "l"(pol)
+                             : "memory");
             }
         }
     };
@@ -693,6 +700,9 @@ __global__ void __launch_bounds__(256) refine_kernel(PartitionPlan plan, int k, 
     const int t = threadIdx.x;
     const uint32_t mshift = 32 - 2 * plan.m;
     unsigned long long overflow_kmers = 0;
+    uint64_t pol_last, pol_first;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
     for (uint32_t c = blockIdx.x; c < n_coarse; c += gridDim.x) {
         for (uint32_t f = t; f < 2 * F; f += blockDim.x) refine_smem[f] = 0;
         __syncthreads();
@@ -736,9 +746,14 @@ __global__ void __launch_bounds__(256) refine_kernel(PartitionPlan plan, int k, 
                         if (si < plan.spill_cap) dst = spill + si;
                         else overflow_kmers += L;
                     }
-                    if (dst) {
-                        if (RECW == 1) reinterpret_cast<uint64_t*>(dst)[0] = hi[q];
-                        else { ulonglong2 o; o.x = hi[q]; o.y = lo[q]; reinterpret_cast<ulonglong2*>(dst)[0] = o; }
+                    if (dst) {   // same L2 policy as partition_kernel: keep a region's partially written sector resident
+                        if (RECW == 1) {
+                            const uint64_t pol = (slot & 3u) == 3u ? pol_first : pol_last;
+                            asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(dst), "l"(hi[q]), "l"(pol) : "memory");
+                        } else {
+                            const uint64_t pol = (slot & 1u) ? pol_first : pol_last;
+                            asm volatile("st.global.L2::cache_hint.v2.u64 [%0], {%1, %2}, %3;" ::"l"(dst), "l"(hi[q]), "l"(lo[q]), "l"(pol) : "memory");
+                        }
                     }
                 }
             }
