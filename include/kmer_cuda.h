@@ -35,7 +35,7 @@ extern "C" {
 #endif
 
 #define KMER_CUDA_MAX_K 32 /* MAX_KMER_LENGTH, kmer.h:18 */
-#define KMER_CUDA_ABI_VERSION 1
+#define KMER_CUDA_ABI_VERSION 2
 
 typedef enum kmer_status
 {
@@ -120,6 +120,15 @@ int kmer_cuda_submit_extract(kmer_cuda_ctx *ctx, const char *seq, const uint64_t
 int kmer_cuda_submit_count(kmer_cuda_ctx *ctx, const char *seq, const uint64_t *row_off, uint64_t n_rows,
 						   int k, kmer_count_pair **pairs, uint64_t *n_distinct, uint64_t *n_kmers);
 
+/* The same GROUP BY in the split result format: a group whose count is 1 is returned as its bare code,
+ * (*uniq_codes)[0..*n_unique); every other group -- and any count-1 group the device did not prove unique on chip --
+ * as a pair, (*pairs)[0..*n_pairs).  The union of the two is exactly kmer_cuda_submit_count()'s table; no k-mer is in
+ * both.  On mostly distinct k-mers (k >= 14 over unassembled reads) this halves the bytes that cross PCIe: 8 instead
+ * of 16 per group.  Both buffers are released separately with kmer_cuda_release(). */
+int kmer_cuda_submit_count_split(kmer_cuda_ctx *ctx, const char *seq, const uint64_t *row_off, uint64_t n_rows, int k,
+								 uint64_t **uniq_codes, uint64_t *n_unique, kmer_count_pair **pairs, uint64_t *n_pairs,
+								 uint64_t *n_kmers);
+
 /* Replaces per-row calls of kmer_equals / kmer_starts_with[_op] / kmer_contains / kmer_containing
  * (kmer.c:226-285) over a column of m k-mers against n_consts constants given as text:
  *   KMER_OP_EQUALS, KMER_OP_STARTS_WITH : constants are kmer literals   (kmer_in rules, kmer.c:109-129)
@@ -162,6 +171,7 @@ typedef struct kmer_dev_result
 						  * global hash table (highly repetitive input); diagnostics only */
 	uint64_t n_tier2;	 /* k-mers of buckets that did not fit on chip and were counted by the tier-2
 						  * kernel instead; diagnostics only */
+	uint64_t n_unique;	 /* kmer_cuda_dev_count_split: bare codes written (n_distinct counts the pairs only) */
 } kmer_dev_result;
 
 int kmer_cuda_dev_extract(kmer_cuda_ctx *ctx, const char *d_seq, uint64_t n_bases, const uint64_t *d_row_off,
@@ -171,6 +181,11 @@ int kmer_cuda_dev_extract(kmer_cuda_ctx *ctx, const char *d_seq, uint64_t n_base
 int kmer_cuda_dev_count(kmer_cuda_ctx *ctx, const char *d_seq, uint64_t n_bases, const uint64_t *d_row_off,
 						uint64_t n_rows, int k, kmer_count_pair *d_pairs, uint64_t pairs_capacity, int algo,
 						void *stream);
+
+/* Split result format (see kmer_cuda_submit_count_split): unique k-mers as bare codes in d_uniq, the rest as pairs. */
+int kmer_cuda_dev_count_split(kmer_cuda_ctx *ctx, const char *d_seq, uint64_t n_bases, const uint64_t *d_row_off,
+							  uint64_t n_rows, int k, uint64_t *d_uniq, uint64_t uniq_capacity, kmer_count_pair *d_pairs,
+							  uint64_t pairs_capacity, void *stream);
 
 /* consts / ops are HOST arrays (they are compiled to masks on the host); d_* are device pointers.
  * d_bits: n_consts * ceil(m/32) words; d_hits: n_consts counters. */

@@ -39,7 +39,7 @@ ABI_SYMBOLS = [
     "kmer_cuda_submit_encode", "kmer_cuda_dev_extract", "kmer_cuda_dev_count", "kmer_cuda_dev_match",
     "kmer_cuda_dev_decode", "kmer_cuda_dev_finish", "kmer_cuda_set_profiling", "kmer_cuda_get_phases",
     "kmer_cuda_shard_plan", "kmer_cuda_dev_shard_partition", "kmer_cuda_dev_shard_count", "kmer_cuda_dev_dense_table",
-    "kmer_cuda_dev_dense_emit",
+    "kmer_cuda_dev_dense_emit", "kmer_cuda_submit_count_split", "kmer_cuda_dev_count_split",
 ]
 
 
@@ -49,7 +49,8 @@ class KmerCudaError(C.Structure):
 
 
 class KmerDevResult(C.Structure):
-    _fields_ = [("n_kmers", C.c_uint64), ("n_distinct", C.c_uint64), ("n_overflow", C.c_uint64), ("n_tier2", C.c_uint64)]
+    _fields_ = [("n_kmers", C.c_uint64), ("n_distinct", C.c_uint64), ("n_overflow", C.c_uint64), ("n_tier2", C.c_uint64),
+                ("n_unique", C.c_uint64)]
 
 
 class KmerShardPlan(C.Structure):
@@ -93,6 +94,8 @@ def load_library(path: Path = LIB_PATH) -> C.CDLL:
     L.kmer_cuda_submit_encode.argtypes = [vp, vp, vp, u64, i32, C.POINTER(vp)]
     L.kmer_cuda_dev_extract.argtypes = [vp, vp, u64, vp, u64, i32, vp, u64, vp]
     L.kmer_cuda_dev_count.argtypes = [vp, vp, u64, vp, u64, i32, vp, u64, i32, vp]
+    L.kmer_cuda_dev_count_split.argtypes = [vp, vp, u64, vp, u64, i32, vp, u64, vp, u64, vp]
+    L.kmer_cuda_submit_count_split.argtypes = [vp, vp, vp, u64, i32, C.POINTER(vp), u64p, C.POINTER(vp), u64p, u64p]
     L.kmer_cuda_dev_match.argtypes = [vp, i32, vp, vp, vp, u64, i32, C.POINTER(cp), C.c_uint32, vp, vp, vp]
     L.kmer_cuda_dev_decode.argtypes = [vp, vp, u64, i32, i32, vp, vp]
     L.kmer_cuda_dev_finish.argtypes = [vp, vp, C.POINTER(KmerDevResult)]
@@ -200,6 +203,16 @@ class KmerCuda:
         a = self._take(pairs, d.value * 16, np.uint64).reshape(-1, 2)
         return a[:, 0].copy(), a[:, 1].copy(), int(n.value)
 
+    def count_kmers_split(self, rows_or_flat, k: int, off=None):
+        """The same GROUP BY in the split format -> (unique codes[U], codes[P], counts[P], n_kmers)."""
+        f, o = _flat(rows_or_flat, off)
+        uq, nu, pairs, npairs, n = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.kmer_cuda_submit_count_split(self.ctx, f.ctypes.data, o.ctypes.data, len(o) - 1, k, C.byref(uq),
+                                                          C.byref(nu), C.byref(pairs), C.byref(npairs), C.byref(n)))
+        u = self._take(uq, nu.value * 8, np.uint64)
+        a = self._take(pairs, npairs.value * 16, np.uint64).reshape(-1, 2)
+        return u.copy(), a[:, 0].copy(), a[:, 1].copy(), int(n.value)
+
     def match(self, op, codes: np.ndarray, k: int, consts, lens: np.ndarray | None = None, ops=None):
         """Bit matrix [n_consts, m] (bool) and hits[n_consts] for the column `codes`."""
         codes = np.ascontiguousarray(codes, dtype=np.uint64)
@@ -275,6 +288,12 @@ class KmerCuda:
         """d_pairs: int64/uint64 tensor [capacity, 2]."""
         self._check(self.lib.kmer_cuda_dev_count(self.ctx, d_seq.data_ptr(), n_bases, d_off.data_ptr(), n_rows, k,
                                                  d_pairs.data_ptr(), d_pairs.numel() // 2, algo, self._stream_ptr(stream)))
+
+    def dev_count_split(self, d_seq, n_bases: int, d_off, n_rows: int, k: int, d_uniq, d_pairs, stream=None):
+        """d_uniq: uint64/int64 tensor [capacity]; d_pairs: [capacity, 2]."""
+        self._check(self.lib.kmer_cuda_dev_count_split(self.ctx, d_seq.data_ptr(), n_bases, d_off.data_ptr(), n_rows, k,
+                                                       d_uniq.data_ptr(), d_uniq.numel(), d_pairs.data_ptr(), d_pairs.numel() // 2,
+                                                       self._stream_ptr(stream)))
 
     def dev_match(self, op, d_codes, m: int, k: int, consts, d_bits, d_hits, d_lens=None, ops=None, stream=None):
         consts = [consts] if isinstance(consts, str) else list(consts)

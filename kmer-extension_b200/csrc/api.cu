@@ -196,7 +196,7 @@ __global__ void status_reset_kernel(DevStatus* s) {
     s->n_spill = 0;
     s->n_failed = 0;
     s->failed_kmers = 0;
-    s->reserved = 0;
+    s->n_unique = 0;
 }
 
 // pad := row containing bad_char_pos (so the host never needs the offsets)
@@ -465,9 +465,10 @@ static uint64_t next_pow2(uint64_t v) {
     return p;
 }
 
-extern "C" int kmer_cuda_dev_count(kmer_cuda_ctx* c, const char* d_seq, uint64_t n_bases, const uint64_t* d_row_off,
-                                   uint64_t n_rows, int k, kmer_count_pair* d_pairs, uint64_t pairs_capacity, int algo,
-                                   void* stream) {
+// d_uniq != nullptr: split result format (see kmer_cuda_dev_count_split)
+static int dev_count_impl(kmer_cuda_ctx* c, const char* d_seq, uint64_t n_bases, const uint64_t* d_row_off, uint64_t n_rows, int k,
+                          kmer_count_pair* d_pairs, uint64_t pairs_capacity, uint64_t* d_uniq, uint64_t uniq_capacity, int algo,
+                          void* stream) {
     if (!c) return KMER_ERR_BAD_ARGUMENT;
     cudaStream_t st = pick_stream(c, stream);
     int rc = begin_op(c, st);
@@ -495,7 +496,7 @@ extern "C" int kmer_cuda_dev_count(kmer_cuda_ctx* c, const char* d_seq, uint64_t
         if (rc) return rc;
         MarkArg ma{c, st};
         launch_count_partition(c->di, a, plan, (unsigned long long*)c->fill.p, c->recs.p, c->spill.p, (uint32_t*)c->failed.p,
-                               d_pairs, pairs_capacity, st, mark_cb, &ma);
+                               d_pairs, pairs_capacity, d_uniq, uniq_capacity, st, mark_cb, &ma);
         c->launches += 2;
         // Did everything fit?  (One host round trip; skewed input needs tier 2 or a full recount.)
         CU(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, st), "D2H status");
@@ -556,6 +557,20 @@ extern "C" int kmer_cuda_dev_count(kmer_cuda_ctx* c, const char* d_seq, uint64_t
     c->launches++;
     CU(cudaGetLastError(), "count launch");
     return KMER_OK;
+}
+
+extern "C" int kmer_cuda_dev_count(kmer_cuda_ctx* c, const char* d_seq, uint64_t n_bases, const uint64_t* d_row_off,
+                                   uint64_t n_rows, int k, kmer_count_pair* d_pairs, uint64_t pairs_capacity, int algo,
+                                   void* stream) {
+    return dev_count_impl(c, d_seq, n_bases, d_row_off, n_rows, k, d_pairs, pairs_capacity, nullptr, 0, algo, stream);
+}
+
+extern "C" int kmer_cuda_dev_count_split(kmer_cuda_ctx* c, const char* d_seq, uint64_t n_bases, const uint64_t* d_row_off,
+                                         uint64_t n_rows, int k, uint64_t* d_uniq, uint64_t uniq_capacity,
+                                         kmer_count_pair* d_pairs, uint64_t pairs_capacity, void* stream) {
+    if (c && !d_uniq && uniq_capacity) return bad_arg(c, "d_uniq");
+    return dev_count_impl(c, d_seq, n_bases, d_row_off, n_rows, k, d_pairs, pairs_capacity, d_uniq, d_uniq ? uniq_capacity : 0, 0,
+                          stream);
 }
 
 static int upload_consts(kmer_cuda_ctx* c, int op, const int* ops, const char* const* consts, uint32_t n_consts,
@@ -663,6 +678,7 @@ extern "C" int kmer_cuda_dev_finish(kmer_cuda_ctx* c, void* stream, kmer_dev_res
             result->n_distinct = s.n_distinct;
             result->n_overflow = c->last_overflow;
             result->n_tier2 = c->last_tier2;
+            result->n_unique = s.n_unique;
         }
         if (op == OP_COUNT && s.n_kmers != c->p_expected_kmers)
             return set_error(&c->err, KMER_ERR_CUDA, "XX000", "kmer_cuda: internal error: counted k-mers != windows", "", -1);
@@ -800,7 +816,7 @@ extern "C" int kmer_cuda_dev_shard_count(kmer_cuda_ctx* c, const kmer_shard_plan
                   d_recv_recs, (unsigned long long*)c->fill.p, c->recs.p, c->spill.p, c->d_status, st);
     mark(c, st, "refine");
     launch_bucket_count(c->di, plan, k, 1, (const unsigned long long*)c->fill.p, c->recs.p, (uint32_t*)c->failed.p, d_pairs,
-                        pairs_capacity, c->d_status, st);
+                        pairs_capacity, nullptr, 0, c->d_status, st);
     mark(c, st, "bucket_count");
     c->launches += 2;
     CU(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, st), "D2H status");
@@ -953,6 +969,44 @@ extern "C" int kmer_cuda_submit_count(kmer_cuda_ctx* c, const char* seq, const u
     CU(cudaStreamSynchronize(c->stream), "stream sync");
     *pairs = out;
     *n_distinct = res.n_distinct;
+    if (n_kmers) *n_kmers = res.n_kmers;
+    return KMER_OK;
+}
+
+extern "C" int kmer_cuda_submit_count_split(kmer_cuda_ctx* c, const char* seq, const uint64_t* row_off, uint64_t n_rows, int k,
+                                            uint64_t** uniq_codes, uint64_t* n_unique, kmer_count_pair** pairs,
+                                            uint64_t* n_pairs, uint64_t* n_kmers) {
+    if (!c || !uniq_codes || !n_unique || !pairs || !n_pairs) return KMER_ERR_BAD_ARGUMENT;
+    *uniq_codes = nullptr; *pairs = nullptr;
+    *n_unique = 0; *n_pairs = 0;
+    if (n_kmers) *n_kmers = 0;
+    CU(cudaSetDevice(c->di.device), "cudaSetDevice");
+    uint64_t n_bases = 0;
+    int rc = upload_rows(c, seq, row_off, n_rows, &n_bases);
+    if (rc) return rc;
+    uint64_t cap = kmer_cuda_max_kmers(n_bases, n_rows, k);
+    if (k >= 1 && k < 32 && (1ull << (2 * k)) < cap) cap = 1ull << (2 * k);
+    // a k-mer that is not unique occurs at least twice: at most cap/2 pairs next to the unique codes -- unless a fallback
+    // tier (which writes pairs only) takes over, so the pair buffer keeps the full size
+    rc = ws(c, c->pairs, cap * sizeof(kmer_count_pair));
+    if (!rc) rc = ws(c, c->codes, cap * sizeof(uint64_t));
+    if (rc) return rc;
+    rc = kmer_cuda_dev_count_split(c, (const char*)c->seq.p, n_bases, (const uint64_t*)c->off.p, n_rows, k, (uint64_t*)c->codes.p, cap,
+                                   (kmer_count_pair*)c->pairs.p, cap, KMER_OWN_STREAM);
+    if (rc) return rc;
+    kmer_dev_result res;
+    rc = kmer_cuda_dev_finish(c, KMER_OWN_STREAM, &res);
+    if (rc) return rc;
+    uint64_t* out_u = (uint64_t*)pinned_get(c, res.n_unique * sizeof(uint64_t));
+    kmer_count_pair* out_p = (kmer_count_pair*)pinned_get(c, res.n_distinct * sizeof(kmer_count_pair));
+    if (!out_u || !out_p) return c->err.status;
+    CU(cudaMemcpyAsync(out_u, c->codes.p, res.n_unique * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream), "D2H codes");
+    CU(cudaMemcpyAsync(out_p, c->pairs.p, res.n_distinct * sizeof(kmer_count_pair), cudaMemcpyDeviceToHost, c->stream), "D2H pairs");
+    CU(cudaStreamSynchronize(c->stream), "stream sync");
+    *uniq_codes = out_u;
+    *n_unique = res.n_unique;
+    *pairs = out_p;
+    *n_pairs = res.n_distinct;
     if (n_kmers) *n_kmers = res.n_kmers;
     return KMER_OK;
 }

@@ -23,7 +23,7 @@ struct DevStatus {
     unsigned long long n_spill;        // partition: records that did not fit their bucket region
     unsigned long long n_failed;       // partition: buckets handed to the tier-2 kernel
     unsigned long long failed_kmers;   // k-mers (instances) in those buckets
-    unsigned long long reserved;
+    unsigned long long n_unique;       // split result format: k-mers written as bare codes (count 1)
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -374,6 +374,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1280 / LEAF_THREADS) bucket_coun
                                                                        const unsigned long long* __restrict__ fill,
                                                                        const Rec<RECW>* __restrict__ recs,
                                                                        kmer_count_pair* __restrict__ out, uint64_t capacity,
+                                                                       uint64_t* __restrict__ out_u, uint64_t capacity_u,
                                                                        uint32_t* __restrict__ failed_ids, DevStatus* status,
                                                                        int n_src_) {
     const int n_src = MULTI ? n_src_ : 1;                     // MULTI: sharded counting, one segment per source GPU
@@ -573,7 +574,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1280 / LEAF_THREADS) bucket_coun
         unsigned long long ubase = 0;
         if (t == 0) {
             const uint32_t nu = s_nuniq[par];
-            if (nu) ubase = atomicAdd(&status->n_distinct, (unsigned long long)nu);   // consumed after the next barrier
+            if (nu) ubase = atomicAdd(out_u ? &status->n_unique : &status->n_distinct, (unsigned long long)nu);   // consumed after the next barrier
         }
         // bitmap B is dead: clear it for the next bucket
         for (int i = t; i < LEAF_CELLS / 128; i += LEAF_THREADS) sts128(bmb_s + 16 * i, 0u, 0u, 0u, 0u);
@@ -632,7 +633,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1280 / LEAF_THREADS) bucket_coun
         // ---- emit the unique k-mers: coalesced 16-byte (k-mer, 1) pairs, ranks by ballot
         {
             unsigned long long ob = s_obase[par] + woff;
-            const bool fits = ob + wuniq <= capacity;                   // uniform per warp
+            const bool fits = ob + wuniq <= (out_u ? capacity_u : capacity);   // uniform per warp
             if (!fits && lane == 0) status->out_overflow = 1;
 #pragma unroll
             for (int i = 0; i < LEAF_KPT; i++) {
@@ -640,10 +641,14 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1280 / LEAF_THREADS) bucket_coun
                 const bool u = fits && ((uniq >> i) & 1u);
                 const uint32_t m = __ballot_sync(0xffffffffu, u);
                 if (u) {
-                    ulonglong2 o;
-                    o.x = key_at(t + i * LEAF_THREADS);
-                    o.y = 1ull;
-                    reinterpret_cast<ulonglong2*>(out)[ob + __popc(m & lane_lt)] = o;
+                    const uint64_t key = key_at(t + i * LEAF_THREADS);
+                    if (out_u) out_u[ob + __popc(m & lane_lt)] = key;     // split format: a bare code means count 1
+                    else {
+                        ulonglong2 o;
+                        o.x = key;
+                        o.y = 1ull;
+                        reinterpret_cast<ulonglong2*>(out)[ob + __popc(m & lane_lt)] = o;
+                    }
                 }
                 ob += __popc(m);
             }
@@ -902,7 +907,7 @@ size_t leaf_smem_bytes(const PartitionPlan& p, int n_src) {
 
 void launch_bucket_count(const DeviceInfo& di, const PartitionPlan& p, int k, int n_src, const unsigned long long* d_fill,
                          const void* d_recs, uint32_t* d_failed_ids, kmer_count_pair* d_pairs, uint64_t capacity,
-                         DevStatus* d_status, cudaStream_t st) {
+                         uint64_t* d_uniq, uint64_t uniq_capacity, DevStatus* d_status, cudaStream_t st) {
     const size_t leaf_smem = leaf_smem_bytes(p, n_src);
     int per_sm = (int)((size_t)227 * 1024 / (leaf_smem + 1024));
     static const char* env_ctas = getenv("KMER_CUDA_LEAF_CTAS");   // profiling experiments only
@@ -917,7 +922,7 @@ void launch_bucket_count(const DeviceInfo& di, const PartitionPlan& p, int k, in
         cudaFuncSetAttribute(bucket_count_kernel<RW, MU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leaf_smem);       \
         cudaFuncSetAttribute(bucket_count_kernel<RW, MU>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);               \
         bucket_count_kernel<RW, MU><<<(unsigned)lgrid, LEAF_THREADS, leaf_smem, st>>>(                                        \
-            p, k, d_fill, (const Rec<RW>*)d_recs, d_pairs, capacity, d_failed_ids, d_status, n_src);                          \
+            p, k, d_fill, (const Rec<RW>*)d_recs, d_pairs, capacity, d_uniq, uniq_capacity, d_failed_ids, d_status, n_src);                          \
     } while (0)
     // (sharded counting merges the source segments in refine_kernel: the leaf always sees one segment per bucket)
     if (p.recw == 1) KMER_LEAF_LAUNCH(1, false);
@@ -927,10 +932,10 @@ void launch_bucket_count(const DeviceInfo& di, const PartitionPlan& p, int k, in
 
 void launch_count_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPlan& p, unsigned long long* d_fill,
                             void* d_recs, void* d_spill, uint32_t* d_failed_ids, kmer_count_pair* d_pairs, uint64_t capacity,
-                            cudaStream_t st, void (*mark)(void*, const char*), void* mark_arg) {
+                            uint64_t* d_uniq, uint64_t uniq_capacity, cudaStream_t st, void (*mark)(void*, const char*), void* mark_arg) {
     launch_partition(di, a, p, d_fill, d_recs, d_spill, st);
     if (mark) mark(mark_arg, "minimizer_partition");
-    launch_bucket_count(di, p, a.k, 1, d_fill, d_recs, d_failed_ids, d_pairs, capacity, a.status, st);
+    launch_bucket_count(di, p, a.k, 1, d_fill, d_recs, d_failed_ids, d_pairs, capacity, d_uniq, uniq_capacity, a.status, st);
     if (mark) mark(mark_arg, "bucket_count");
 }
 

@@ -62,12 +62,14 @@ size_t partition_spill_bytes(const PartitionPlan& p);
 // DevStatus: n_overflow != 0 -> discard and recount (tier 3); n_failed / n_spill != 0 -> run tier 2.
 void launch_count_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPlan& p, unsigned long long* d_fill,
                             void* d_recs, void* d_spill, uint32_t* d_failed_ids, kmer_count_pair* d_pairs, uint64_t capacity,
-                            cudaStream_t st, void (*mark)(void*, const char*), void* mark_arg);
+                            uint64_t* d_uniq, uint64_t uniq_capacity, cudaStream_t st, void (*mark)(void*, const char*), void* mark_arg);
 void launch_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPlan& p, unsigned long long* d_fill,
                       void* d_recs, void* d_spill, cudaStream_t st);
 void launch_bucket_count(const DeviceInfo& di, const PartitionPlan& p, int k, int n_src, const unsigned long long* d_fill,
                          const void* d_recs, uint32_t* d_failed_ids, kmer_count_pair* d_pairs, uint64_t capacity,
-                         DevStatus* d_status, cudaStream_t st);
+                         uint64_t* d_uniq, uint64_t uniq_capacity, DevStatus* d_status, cudaStream_t st);
+// d_uniq != nullptr: split result format -- k-mers proven unique on chip are written as bare codes to d_uniq (counted in
+// DevStatus::n_unique), everything else as (k-mer, count) pairs
 void launch_partition_tier2(const DeviceInfo& di, const PartitionPlan& p, int k, int n_src, const unsigned long long* d_fill,
                             const void* d_recs, const void* d_spill, const uint32_t* d_failed_ids, kmer_count_pair* d_slots,
                             uint64_t n_slots, DevStatus* d_status, cudaStream_t st);

@@ -39,7 +39,8 @@ def test_abi_version_and_helpers(lib):
 
 def test_struct_layouts_match_header():
     assert C.sizeof(api.KmerCudaError) == 4 + 6 + 160 + 160 + 6 + 8  # int, char[6], 2*char[160], pad to 8, int64
-    assert C.sizeof(api.KmerDevResult) == 32
+    assert C.sizeof(api.KmerDevResult) == 40
+    assert C.sizeof(api.KmerShardPlan) == 72
 
 
 def test_no_cpu_fallback_without_gpu(lib):
