@@ -531,7 +531,7 @@ static int dev_count_impl(kmer_cuda_ctx* c, const char* d_seq, uint64_t n_bases,
         }
     }
     if (algo == 1) {
-        if (k > 13) return bad_arg(c, "dense counting needs k <= 13");
+        if (k > 15) return bad_arg(c, "dense counting needs k <= 15");
         uint64_t nbins = 1ull << (2 * k);
         rc = ws(c, c->table, nbins * 8);
         if (rc) return rc;

@@ -851,7 +851,9 @@ __global__ void append_special_kernel(kmer_count_pair* out, uint64_t capacity, D
 
 PartitionPlan make_partition_plan(uint64_t n_kmers, int k) {
     PartitionPlan p{};
-    p.w = k <= 17 ? 4 : (k <= 26 ? 8 : 16);
+    // minimizer window: the m-mer (m = k - w + 1, capped at 16 bases) must be long enough (>= 14 bases where k allows) that
+    // the minimizers spread evenly over the buckets; shorter ones leave few distinct minimizers and lopsided buckets
+    p.w = k <= 20 ? 4 : (k <= 28 ? 8 : 16);
     p.recw = k <= 26 ? 1 : 2;
     int m = k - p.w + 1;
     p.m = m > 16 ? 16 : m;
@@ -892,7 +894,8 @@ void launch_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPl
     if (grid > n_tiles) grid = n_tiles;
     if (!n_tiles) return;
     if (p.w == 4) partition_kernel<4, 1><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill);
-    else if (p.w == 8) partition_kernel<8, 1><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill);
+    else if (p.w == 8 && p.recw == 1) partition_kernel<8, 1><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill);
+    else if (p.w == 8) partition_kernel<8, 2><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<2>*)d_recs, (Rec<2>*)d_spill);
     else partition_kernel<16, 2><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<2>*)d_recs, (Rec<2>*)d_spill);
 }
 
@@ -962,9 +965,12 @@ void launch_refine(const DeviceInfo& di, const PartitionPlan& p, int k, int n_sr
     if (p.w == 4)
         refine_kernel<4, 1><<<grid, 256, smem, st>>>(p, k, n_src, n_coarse, coarse_cap, d_recv_fill, (const Rec<1>*)d_recv_recs,
                                                      d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill, d_status);
-    else if (p.w == 8)
+    else if (p.w == 8 && p.recw == 1)
         refine_kernel<8, 1><<<grid, 256, smem, st>>>(p, k, n_src, n_coarse, coarse_cap, d_recv_fill, (const Rec<1>*)d_recv_recs,
                                                      d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill, d_status);
+    else if (p.w == 8)
+        refine_kernel<8, 2><<<grid, 256, smem, st>>>(p, k, n_src, n_coarse, coarse_cap, d_recv_fill, (const Rec<2>*)d_recv_recs,
+                                                     d_fill, (Rec<2>*)d_recs, (Rec<2>*)d_spill, d_status);
     else
         refine_kernel<16, 2><<<grid, 256, smem, st>>>(p, k, n_src, n_coarse, coarse_cap, d_recv_fill, (const Rec<2>*)d_recv_recs,
                                                       d_fill, (Rec<2>*)d_recs, (Rec<2>*)d_spill, d_status);

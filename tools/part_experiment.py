@@ -11,12 +11,13 @@ flat, off = datagen.synth_reads(2, n_rows, 1000)
 d_seq = torch.from_numpy(np.concatenate([flat, np.zeros(64, np.uint8)])).cuda()
 d_off = torch.from_numpy(off.astype(np.int64)).cuda()
 eng = api.KmerCuda(0)
-cap = eng.max_kmers(int(off[-1]), n_rows, 21)
+KK = int(os.environ.get("KMER_K", "21"))
+cap = eng.max_kmers(int(off[-1]), n_rows, KK)
 d_pairs = torch.empty((cap, 2), dtype=torch.int64, device="cuda")
 eng.set_profiling(True)
 for it in range(3):
     try:
-        eng.dev_count(d_seq, int(off[-1]), d_off, n_rows, 21, d_pairs, algo=3)
+        eng.dev_count(d_seq, int(off[-1]), d_off, n_rows, KK, d_pairs, algo=int(os.environ.get('KMER_ALGO','3')))
         eng.dev_finish()
     except api.KmerSqlError as e:
         pass
