@@ -67,7 +67,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -76,7 +76,13 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def stop(self):
         if not self.proc:
@@ -87,8 +93,14 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        t0, t1 = getattr(self, "t_begin", 0.0), getattr(self, "t_end", float("inf"))
+        inside = [ln for (ts, ln) in self.lines if t0 - 0.005 <= ts <= t1 + 0.03]
+        window = "timed region"
+        if len(inside) < 2:          # a timed region shorter than two sampling periods: take the warm-up steps as well
+            inside = [ln for (ts, ln) in self.lines if ts <= t1 + 0.03]
+            window = "warm-up + timed region (same load)"
         sm, smax, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -100,7 +112,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def cpu_reference_run(datagen, n_reads: int, threads: int, steps: int, warmup: int):
@@ -235,7 +247,7 @@ def run_secondary(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU (1 kb each); default = 1 GB")
@@ -304,6 +316,8 @@ def main():
         r.n_kmers, r.n_distinct, r.n_overflow, r.n_tier2 = nk, nd, 0, info["tier2_kmers"]
         return r
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         res = step()
     if world == 1:
@@ -315,9 +329,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
+    sampler.mark_begin()
     l0 = eng.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
@@ -325,6 +338,7 @@ def main():
         res = step()
     ev1.record(stream)
     barrier()
+    sampler.mark_end()
     launches = eng.launches - l0
     clocks = sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
