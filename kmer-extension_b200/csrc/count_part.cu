@@ -150,11 +150,17 @@ __global__ void __launch_bounds__(NT, PART_MINB) partition_kernel(ScanArgs a, Pa
                 uint32_t x = mm * 0x9E3779B1u;
                 h[j + 1] = x ^ (x >> 15);
             }
-            // sliding minimum over W consecutive m-mers (log-step, W is a power of two)
+            // sliding minimum over W consecutive m-mers: log-steps up to the largest power of two P <= W, then two
+            // overlapping P-windows cover a W-window
+            constexpr int P = W >= 16 ? 16 : (W >= 8 ? 8 : (W >= 4 ? 4 : 2));
 #pragma unroll
-            for (int step = 1; step < W; step <<= 1) {
+            for (int step = 1; step < P; step <<= 1) {
 #pragma unroll
                 for (int j = 0; j < 17 + W - 1 - step; j++) h[j] = min(h[j], h[j + step]);
+            }
+            if (W > P) {
+#pragma unroll
+                for (int j = 0; j < 17; j++) h[j] = min(h[j], h[j + W - P]);
             }
             // a run starts where the minimizer changes (identical k-mers have identical minimizers, hence the same
             // bucket = mix(minimizer hash); the bucket itself is only computed once per run, at emission)
@@ -853,16 +859,32 @@ PartitionPlan make_partition_plan(uint64_t n_kmers, int k) {
     PartitionPlan p{};
     // minimizer window: the m-mer (m = k - w + 1, capped at 16 bases) must be long enough (>= 14 bases where k allows) that
     // the minimizers spread evenly over the buckets; shorter ones leave few distinct minimizers and lopsided buckets
-    p.w = k <= 20 ? 4 : (k <= 28 ? 8 : 16);
-    p.recw = k <= 26 ? 1 : 2;
-    int m = k - p.w + 1;
-    p.m = m > 16 ? 16 : m;
-    p.rmax = p.recw == 1 ? (30 - k + 1 > 16 ? 16 : 30 - k + 1) : 16;
     static const char* env_target = getenv("KMER_CUDA_BUCKET_KMERS");   // profiling experiments only
     const uint32_t target = env_target ? (uint32_t)atoi(env_target) : TARGET_KMERS_PER_BUCKET;
     uint64_t nb = (n_kmers + target - 1) / target;
     if (nb < 1) nb = 1;
     if (nb > 0x7fffffffull) nb = 0x7fffffffull;
+    p.recw = k <= 26 ? 1 : 2;
+    // The widest window (fewest records) whose m-mers still spread evenly over the buckets: 4^m >= 65 * buckets.  (Measured at
+    // k=21: 14-base m-mers leave 1 bucket of 817 k above the on-chip limit at 1 GB, 0.2 % of them at 4 GB -- still cheaper than
+    // the 30 % more records of the next narrower window -- and would leave ~2 % at 8 GB.)  n_kmers is the size of the WHOLE job.
+    {
+        static const int ws1[] = {8, 6, 4}, ws2[] = {16, 12, 8};
+        const int* ws = p.recw == 1 ? ws1 : ws2;
+        p.w = ws[2];
+        for (int i = 0; i < 3; i++) {
+            const int m = k - ws[i] + 1 > 16 ? 16 : k - ws[i] + 1;
+            if (m >= 14 && ldexp(1.0, 2 * m) >= 65.0 * (double)nb) { p.w = ws[i]; break; }
+        }
+    }
+    if (const char* fw = getenv("KMER_CUDA_DEBUG_W")) {   // tests: force a window (must suit the record width and k)
+        const int w = atoi(fw);
+        const bool ok = p.recw == 1 ? (w == 4 || w == 6 || w == 8) : (w == 8 || w == 12 || w == 16);
+        if (ok && k - w + 1 >= 2) p.w = w;
+    }
+    int m = k - p.w + 1;
+    p.m = m > 16 ? 16 : m;
+    p.rmax = p.recw == 1 ? (30 - k + 1 > 16 ? 16 : 30 - k + 1) : 16;
     p.n_buckets = (uint32_t)nb;
     p.hash_buckets = p.n_buckets;
     p.fine_shift = 0;
@@ -894,6 +916,8 @@ void launch_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPl
     if (grid > n_tiles) grid = n_tiles;
     if (!n_tiles) return;
     if (p.w == 4) partition_kernel<4, 1><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill);
+    else if (p.w == 6) partition_kernel<6, 1><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill);
+    else if (p.w == 12) partition_kernel<12, 2><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<2>*)d_recs, (Rec<2>*)d_spill);
     else if (p.w == 8 && p.recw == 1) partition_kernel<8, 1><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill);
     else if (p.w == 8) partition_kernel<8, 2><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<2>*)d_recs, (Rec<2>*)d_spill);
     else partition_kernel<16, 2><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<2>*)d_recs, (Rec<2>*)d_spill);
@@ -962,7 +986,13 @@ void launch_refine(const DeviceInfo& di, const PartitionPlan& p, int k, int n_sr
     unsigned grid = (unsigned)di.sm_count * 8;
     if (grid > n_coarse) grid = n_coarse;
     const size_t smem = (size_t)(2u << p.fine_shift) * sizeof(uint32_t);
-    if (p.w == 4)
+    if (p.w == 6)
+        refine_kernel<6, 1><<<grid, 256, smem, st>>>(p, k, n_src, n_coarse, coarse_cap, d_recv_fill, (const Rec<1>*)d_recv_recs,
+                                                     d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill, d_status);
+    else if (p.w == 12)
+        refine_kernel<12, 2><<<grid, 256, smem, st>>>(p, k, n_src, n_coarse, coarse_cap, d_recv_fill, (const Rec<2>*)d_recv_recs,
+                                                      d_fill, (Rec<2>*)d_recs, (Rec<2>*)d_spill, d_status);
+    else if (p.w == 4)
         refine_kernel<4, 1><<<grid, 256, smem, st>>>(p, k, n_src, n_coarse, coarse_cap, d_recv_fill, (const Rec<1>*)d_recv_recs,
                                                      d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill, d_status);
     else if (p.w == 8 && p.recw == 1)
