@@ -275,7 +275,6 @@ constexpr int LEAF_CELLS = 32768;                                    // bits per
 constexpr int LEAF_WARPS = LEAF_THREADS / 32;
 static_assert(LEAF_MAX_KMERS < LEAF_SLOTS, "a probe sequence must always find a free slot");
 static_assert(LEAF_CELLS / 8 >= 2 * (LEAF_MAX_KMERS + 1), "the slow list lives in bitmap A");
-constexpr int MAX_SRC = 16;           // source GPUs a sharded bucket may be assembled from
 
 __device__ __forceinline__ unsigned long long atoms_cas64(uint32_t a, unsigned long long cmp, unsigned long long val) {
     unsigned long long old;
@@ -357,33 +356,22 @@ struct BucketInfo {
     __device__ __forceinline__ bool usable() const { return nrec != 0 && !overflow && nk <= LEAF_MAX_KMERS; }
 };
 
-// sharded counting (n_src > 1): bucket b's records arrive as n_src segments, one per source GPU:
-// segment s is recs[(s * n_buckets + b) * cap ..] with fill[s * n_buckets + b].
-template <bool MULTI>
-__device__ __forceinline__ BucketInfo bucket_info(const unsigned long long* __restrict__ fill, const PartitionPlan& plan,
-                                                  int n_src_, uint32_t b) {
+__device__ __forceinline__ BucketInfo bucket_info(const unsigned long long* __restrict__ fill, const PartitionPlan& plan, uint32_t b) {
     BucketInfo bi;
-    bi.nrec = 0; bi.nk = 0; bi.overflow = false;
-    const int n_src = MULTI ? n_src_ : 1;
-#pragma unroll 1
-    for (int sI = 0; sI < n_src; sI++) {
-        const unsigned long long f = fill[(uint64_t)sI * plan.n_buckets + b];
-        bi.nrec += (uint32_t)f;
-        bi.nk += (uint32_t)(f >> 32);
-        bi.overflow |= (uint32_t)f > plan.cap;
-    }
+    const unsigned long long f = fill[b];
+    bi.nrec = (uint32_t)f;
+    bi.nk = (uint32_t)(f >> 32);
+    bi.overflow = (uint32_t)f > plan.cap;
     return bi;
 }
 
-template <int RECW, bool MULTI>
+template <int RECW>
 __global__ void __launch_bounds__(LEAF_THREADS, 1280 / LEAF_THREADS) bucket_count_kernel(PartitionPlan plan, int k,
                                                                        const unsigned long long* __restrict__ fill,
                                                                        const Rec<RECW>* __restrict__ recs,
                                                                        kmer_count_pair* __restrict__ out, uint64_t capacity,
                                                                        uint64_t* __restrict__ out_u, uint64_t capacity_u,
-                                                                       uint32_t* __restrict__ failed_ids, DevStatus* status,
-                                                                       int n_src_) {
-    const int n_src = MULTI ? n_src_ : 1;                     // MULTI: sharded counting, one segment per source GPU
+                                                                       uint32_t* __restrict__ failed_ids, DevStatus* status) {
     constexpr bool PACKED = RECW == 1;                        // count in bits 63..52 of the key word (k <= 26)
     constexpr uint32_t RECB = RECW * 8;
     constexpr uint64_t KEYMASK = PACKED ? ((1ull << 52) - 1ull) : ~0ull;
@@ -395,9 +383,8 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1280 / LEAF_THREADS) bucket_coun
     const uint32_t bmb_s = bma_s + LEAF_CELLS / 8;                             // bitmap B
     const uint32_t desc_s = bmb_s + LEAF_CELLS / 8;                            // u16[LEAF_MAX_KMERS + 1] k-mer descriptors
     const uint32_t rec0_s = desc_s + (LEAF_MAX_KMERS + 1) * 2;                 // staged records, two buffers
-    const uint32_t rec_stride = (((uint32_t)plan.cap * n_src + 2u * n_src) * RECB + 15u) & ~15u;
+    const uint32_t rec_stride = (((uint32_t)plan.cap + 2u) * RECB + 15u) & ~15u;
     __shared__ __align__(8) uint64_t s_mbar;
-    __shared__ uint32_t s_seg_cum[2][MAX_SRC + 1], s_seg_off[2][MAX_SRC + 1];  // n_src > 1: record prefix / staged offset
     __shared__ uint32_t s_wtot[2][LEAF_WARPS];
     __shared__ uint32_t s_nuniq[2], s_nslow[2];                                // per bucket parity
     __shared__ unsigned long long s_obase[2];
@@ -414,48 +401,30 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1280 / LEAF_THREADS) bucket_coun
     if (t == 0) { mbar_init(&s_mbar, 1); mbar_fence_init(); }
     __syncthreads();
 
-    // thread 0: start the bulk copies of bucket b's records (every segment padded to 16 bytes)
+    // thread 0: start the bulk copy of bucket b's records (padded to 16 bytes; read once: L2 evict-first)
+    const uint64_t pol_stream = l2_evict_first_policy();
     auto issue = [&](uint32_t b, uint32_t buf) {
-        const uint32_t rec_s = rec0_s + buf * rec_stride;
-        uint32_t off = 0, cum = 0, bytes = 0;
-#pragma unroll 1
-        for (int sI = 0; sI < n_src; sI++) {
-            const uint32_t n = (uint32_t)fill[(uint64_t)sI * plan.n_buckets + b];
-            if (MULTI) { s_seg_cum[buf][sI] = cum; s_seg_off[buf][sI] = off; }
-            cum += n;
-            const uint32_t nb = (n * RECB + 15u) & ~15u;
-            off += nb / RECB;
-            bytes += nb;
-        }
-        if (MULTI) s_seg_cum[buf][n_src] = cum;
-        mbar_arrive_expect_tx(&s_mbar, bytes);
-        off = 0;
-#pragma unroll 1
-        for (int sI = 0; sI < n_src; sI++) {
-            const uint32_t n = (uint32_t)fill[(uint64_t)sI * plan.n_buckets + b];
-            const uint32_t nb = (n * RECB + 15u) & ~15u;
-            if (nb) {
-                const Rec<RECW>* src = recs + ((uint64_t)sI * plan.n_buckets + b) * plan.cap;
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                 rec_s + off * RECB),
-                             "l"(src), "r"(nb), "r"(mbar_s)
-                             : "memory");
-            }
-            off += nb / RECB;
-        }
+        const uint32_t n = (uint32_t)fill[b];
+        const uint32_t nb = (n * RECB + 15u) & ~15u;
+        mbar_arrive_expect_tx(&s_mbar, nb);
+        if (nb)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                             rec0_s + buf * rec_stride),
+                         "l"(recs + (uint64_t)b * plan.cap), "r"(nb), "r"(mbar_s), "l"(pol_stream)
+                         : "memory");
     };
 
     uint32_t par = 0, phase = 0, rb = 0;                                // bucket parity, mbarrier phase, record buffer
     BucketInfo cur;
     cur.nrec = 0; cur.nk = 0; cur.overflow = false;
-    if (blockIdx.x < plan.n_buckets) cur = bucket_info<MULTI>(fill, plan, n_src, blockIdx.x);
+    if (blockIdx.x < plan.n_buckets) cur = bucket_info(fill, plan, blockIdx.x);
     if (t == 0 && cur.usable()) issue(blockIdx.x, 0);
 
     for (uint32_t b = blockIdx.x; b < plan.n_buckets; b += gridDim.x) {
         const uint32_t b_next = b + gridDim.x;
         BucketInfo nxt;
         nxt.nrec = 0; nxt.nk = 0; nxt.overflow = false;
-        if (b_next < plan.n_buckets) nxt = bucket_info<MULTI>(fill, plan, n_src, b_next);   // in flight during the probe phase
+        if (b_next < plan.n_buckets) nxt = bucket_info(fill, plan, b_next);   // in flight during the probe phase
         if (!cur.usable()) {                                            // uniform across the CTA
             if (t == 0) {
                 if (cur.nrec) {                                         // does not fit on chip: tier 2
@@ -476,12 +445,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1280 / LEAF_THREADS) bucket_coun
         const uint32_t nrec = cur.nrec;
         uint32_t mysum = 0;
         for (uint32_t r = t; r < nrec; r += LEAF_THREADS) {
-            uint32_t pos = r;
-            if (MULTI) {
-                int sI = 0;
-                while (r >= s_seg_cum[rb][sI + 1]) sI++;
-                pos = r - s_seg_cum[rb][sI] + s_seg_off[rb][sI];
-            }
+            const uint32_t pos = r;
             mysum += (RECW == 1 ? (lds32(rec_s + 8 * pos) & 15u) : (lds32(rec_s + 16 * pos + 8) & 63u)) + 1;
         }
         uint32_t incl = mysum;
@@ -504,12 +468,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1280 / LEAF_THREADS) bucket_coun
             nk += v;
         }
         for (uint32_t r = t; r < nrec; r += LEAF_THREADS) {
-            uint32_t pos = r;
-            if (MULTI) {
-                int sI = 0;
-                while (r >= s_seg_cum[rb][sI + 1]) sI++;
-                pos = r - s_seg_cum[rb][sI] + s_seg_off[rb][sI];
-            }
+            const uint32_t pos = r;
             const uint32_t L = (RECW == 1 ? (lds32(rec_s + 8 * pos) & 15u) : (lds32(rec_s + 16 * pos + 8) & 63u)) + 1;
             for (uint32_t o = 0; o < L; o++) sts16(desc_s + 2 * (kbase + o), (pos << 4) | o);
             kbase += L;
@@ -924,18 +883,19 @@ void launch_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPl
 }
 
 // p.n_buckets = buckets counted HERE (all of them on one GPU, the owned range when sharded)
-size_t leaf_smem_bytes(const PartitionPlan& p, int n_src) {
+size_t leaf_smem_bytes(const PartitionPlan& p) {
     const size_t recb = p.recw == 1 ? 8 : 16;
     size_t table = (size_t)LEAF_SLOTS * 8 + (p.recw == 1 ? 0 : (size_t)LEAF_SLOTS * 4) + 2 * (size_t)LEAF_CELLS / 8 +
                    ((size_t)LEAF_MAX_KMERS + 1) * 2;
-    size_t staged = ((size_t)p.cap * n_src + 2 * (size_t)n_src) * recb;   // every segment padded to 16 bytes
+    size_t staged = ((size_t)p.cap + 2) * recb;                           // padded to 16 bytes
     return table + 2 * ((staged + 15) & ~(size_t)15);                    // two record buffers
 }
 
 void launch_bucket_count(const DeviceInfo& di, const PartitionPlan& p, int k, int n_src, const unsigned long long* d_fill,
                          const void* d_recs, uint32_t* d_failed_ids, kmer_count_pair* d_pairs, uint64_t capacity,
                          uint64_t* d_uniq, uint64_t uniq_capacity, DevStatus* d_status, cudaStream_t st) {
-    const size_t leaf_smem = leaf_smem_bytes(p, n_src);
+    (void)n_src;   // sharded counting merges the source segments in refine_kernel: the leaf always sees one segment per bucket
+    const size_t leaf_smem = leaf_smem_bytes(p);
     int per_sm = (int)((size_t)227 * 1024 / (leaf_smem + 1024));
     static const char* env_ctas = getenv("KMER_CUDA_LEAF_CTAS");   // profiling experiments only
     int max_per_sm = env_ctas ? atoi(env_ctas) : 6;
@@ -944,16 +904,15 @@ void launch_bucket_count(const DeviceInfo& di, const PartitionPlan& p, int k, in
     uint64_t lgrid = (uint64_t)di.sm_count * per_sm;
     if (lgrid > p.n_buckets) lgrid = p.n_buckets;
     if (!lgrid) return;
-#define KMER_LEAF_LAUNCH(RW, MU)                                                                                              \
+#define KMER_LEAF_LAUNCH(RW)                                                                                              \
     do {                                                                                                                      \
-        cudaFuncSetAttribute(bucket_count_kernel<RW, MU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leaf_smem);       \
-        cudaFuncSetAttribute(bucket_count_kernel<RW, MU>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);               \
-        bucket_count_kernel<RW, MU><<<(unsigned)lgrid, LEAF_THREADS, leaf_smem, st>>>(                                        \
-            p, k, d_fill, (const Rec<RW>*)d_recs, d_pairs, capacity, d_uniq, uniq_capacity, d_failed_ids, d_status, n_src);                          \
+        cudaFuncSetAttribute(bucket_count_kernel<RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leaf_smem);       \
+        cudaFuncSetAttribute(bucket_count_kernel<RW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);               \
+        bucket_count_kernel<RW><<<(unsigned)lgrid, LEAF_THREADS, leaf_smem, st>>>(                                        \
+            p, k, d_fill, (const Rec<RW>*)d_recs, d_pairs, capacity, d_uniq, uniq_capacity, d_failed_ids, d_status);                          \
     } while (0)
-    // (sharded counting merges the source segments in refine_kernel: the leaf always sees one segment per bucket)
-    if (p.recw == 1) KMER_LEAF_LAUNCH(1, false);
-    else KMER_LEAF_LAUNCH(2, false);
+    if (p.recw == 1) KMER_LEAF_LAUNCH(1);
+    else KMER_LEAF_LAUNCH(2);
 #undef KMER_LEAF_LAUNCH
 }
 

@@ -1,4 +1,2 @@
-python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "split or count or partition or sharded or large" 2>&1 | tail -3
-python bench.py --no-cpu > gpurun_out/bench_1g.log 2>&1; tail -1 gpurun_out/bench_1g.log | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['phases_ms']); print(d['e2e'])"
+python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "count or partition or kat_group or sharded or large or empty or split or window" 2>&1 | tail -3
+python tools/part_experiment.py 1000000 2>&1 | tail -1
