@@ -170,6 +170,12 @@ __global__ void __launch_bounds__(NT, PART_MINB) partition_kernel(ScanArgs a, Pa
                 starts |= (uint32_t)(v && (!pv || h[j + 1] != h[j])) << j;
             }
         }
+        // A run is emitted by ONE lane, piece by piece: keep it short.  It may run on from the previous thread's chunk only if
+        // it began there, and never across a warp edge -- so a homopolymer costs every lane one short run, not one lane thousands.
+        {
+            const uint32_t prev_starts = __shfl_up_sync(0xffffffffu, starts, 1);
+            if (((vmask >> 1) & 1u) && (lane == 0 || prev_starts == 0)) starts |= 1u;
+        }
         const uint32_t bd = (starts | ~(vmask >> 1)) & 0xffffu;
         reinterpret_cast<uint16_t*>(bdm)[t] = (uint16_t)bd;
         // ---- the warp's runs, compacted into the warp's own list (warp-wide exclusive scan of the run counts)
