@@ -59,148 +59,80 @@ struct alignas(16) Rec<2> {
 #ifndef PART_MINB
 #define PART_MINB 4
 #endif
-// The tile pipeline of this kernel (one block barrier per tile):
-//   scan(i)  : run detection on the 2-bit packed tile i (packed three tiles deep), run list per warp
-//   issue(i) : region-slot atomics of tile i's runs (results stay in flight)
-//   pack(i+1): wait for the TMA copy of tile i+1, validate + 2-bit pack it          } the atomics' round trip hides
-//   barrier  : tile i's boundary bits and tile i+1's packed bases are visible       } behind these two
-//   TMA(i+2) : thread 0 starts the bulk copy of tile i+2 into the stage tile i used
-//   emit(i)  : records of tile i's runs into their slots
-struct alignas(16) PartSmem {
-    uint8_t raw[2][RAW_BYTES];
-    uint32_t bnd[2][BND_WORDS];
-    uint32_t packed[3][PACKED_WORDS + 2];
-    uint32_t bdm[2][TILE / 32 + 2];     // bit p: a run cannot continue through window p (run start or invalid window)
-    uint64_t mbar[2];
-};
-
 template <int W, int RECW>
 __global__ void __launch_bounds__(NT, PART_MINB) partition_kernel(ScanArgs a, PartitionPlan plan, unsigned long long* __restrict__ fill,
                                                        Rec<RECW>* __restrict__ recs, Rec<RECW>* __restrict__ spill) {
-    __shared__ PartSmem s;
-    __shared__ unsigned long long runs[TILE];   // per warp: (minimizer hash << 32) | tile-relative start base of a run
+    __shared__ ScanSmem s;
+    __shared__ unsigned long long runs[TILE];   // (minimizer hash << 32) | (windows << 16) | tile-relative start base
+    __shared__ uint32_t bdm[TILE / 32 + 2];     // bit p: a run cannot continue through window p (run start or invalid window)
+    TileScanner sc(a, s);
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int k = a.k;
     const int m = plan.m;
     const uint32_t rmax = plan.rmax;
     const uint32_t mshift = 32 - 2 * m;
-    const uint32_t kmask = (k > 1) ? ((1u << (k - 1)) - 1u) : 0u;
     unsigned long long overflow_kmers = 0;
-    const uint64_t n_tiles = (a.n_bases + TILE - 1) / TILE;
-    const uint64_t tile_begin = n_tiles * blockIdx.x / gridDim.x, tile_end = n_tiles * (blockIdx.x + 1) / gridDim.x;
-    if (tile_begin >= tile_end) return;
-    if (t < 4) s.bdm[t >> 1][TILE / 32 + (t & 1)] = 0xffffffffu;   // the tile end ends every run
+    if (t < 2) bdm[TILE / 32 + t] = 0xffffffffu;   // the tile end ends every run
     uint64_t pol_last, pol_first;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
-    if (t == 0) {
-        mbar_init(&s.mbar[0], 1);
-        mbar_init(&s.mbar[1], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
 
-    // thread 0: start the bulk copies of tile `tile` (ASCII bases + its slice of the row-start mask) into stage st
-    auto issue_tile = [&](uint64_t tile, int st) {
-        const uint64_t p0 = tile * TILE;
-        const uint64_t avail = ((a.n_bases - p0) + 15) & ~15ull;    // the buffer is readable up to the next 16 B
-        const uint32_t raw_bytes = avail < RAW_BYTES ? (uint32_t)avail : RAW_BYTES;
-        mbar_arrive_expect_tx(&s.mbar[st], raw_bytes + BND_WORDS * 4);
-        bulk_g2s_stream(s.raw[st], a.seq + p0, raw_bytes, &s.mbar[st], pol_first);
-        bulk_g2s(s.bnd[st], a.row_mask + p0 / 32, BND_WORDS * 4, &s.mbar[st]);
-    };
-    // all threads: wait for stage st, fold case + validate + 2-bit pack its bases into packed[pk]
-    uint32_t phases = 0;
-    auto pack_tile = [&](uint64_t tile, int st, int pk) {
-        mbar_wait(&s.mbar[st], (phases >> st) & 1u);
-        phases ^= 1u << st;
-        const uint64_t t0 = tile * TILE;
-        for (int c = t; c < PACKED_WORDS; c += NT) {
-            const uint64_t g = t0 + (uint64_t)c * 16;
-            uint32_t word = 0;
-            if (g < a.n_bases) {
-                const uint4 v = *reinterpret_cast<const uint4*>(&s.raw[st][c * 16]);
-                uint32_t bad;
-                word = enc16(v, bad);
-                if (bad) {
-                    const int j = first_bad_byte(v);
-                    if (g + j < a.n_bases) atomicMin(&a.status->bad_char_pos, (unsigned long long)(g + j));
-                }
-            }
-            s.packed[pk][c] = word;
+    // one super-k-mer record: L windows starting at tile-relative base p go to bucket b
+    auto put_record = [&](uint32_t b, uint32_t slot, int p, int L) {
+        const int c = p >> 4, sh = 2 * (p & 15);
+        const uint32_t w0 = s.packed[c], w1 = s.packed[c + 1], w2 = s.packed[c + 2], w3 = s.packed[c + 3];
+        const uint32_t r0w = __funnelshift_l(w1, w0, sh), r1w = __funnelshift_l(w2, w1, sh), r2w = __funnelshift_l(w3, w2, sh);
+        const int nb = L + k - 1;                                  // bases covered
+        Rec<RECW>* dst = nullptr;
+        if (slot < plan.cap) dst = recs + ((uint64_t)b * plan.cap + slot);
+        else {                                                      // region full: spill list (tier 2), else recount
+            unsigned long long si = atomicAdd(&a.status->n_spill, 1ull);
+            if (si < plan.spill_cap) dst = spill + si;
+            else overflow_kmers += L;
         }
-        if (t < 2) s.packed[pk][PACKED_WORDS + t] = 0;
+        if (dst && !(plan.debug & 1)) {
+            if (RECW == 1) {
+                uint64_t v = ((uint64_t)r0w << 32) | r1w;
+                v &= ~0ull << (64 - 2 * nb);                       // nb <= 30
+                // a region's last, partially written 32-byte sector must stay in L2 until it is complete (else every
+                // record costs a sector fill from HBM): evict-last while it fills up, evict-first with its fourth record
+                const uint64_t pol = (slot & 3u) == 3u ? pol_first : pol_last;
+                asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(dst), "l"(v | (uint64_t)(L - 1)), "l"(pol) : "memory");
+            } else {
+                uint64_t hi = ((uint64_t)r0w << 32) | r1w;
+                uint64_t lo = (uint64_t)r2w << 32;                  // bases 32..47 (nb <= 47)
+                if (nb <= 32) { hi &= ~0ull << (64 - 2 * nb); lo = 0; }
+                else lo &= ~0ull << (128 - 2 * nb);
+                const uint64_t pol = (slot & 1u) ? pol_first : pol_last;
+                asm volatile("st.global.L2::cache_hint.v2.u64 [%0], {%1, %2}, %3;" ::"l"(dst), "l"(hi), "l"(lo | (uint64_t)(L - 1)), "l"(pol)
+                             : "memory");
+            }
+        }
     };
 
-    if (t == 0) {
-        issue_tile(tile_begin, 0);
-        if (tile_begin + 1 < tile_end) issue_tile(tile_begin + 1, 1);
-    }
-    pack_tile(tile_begin, 0, 0);
-    __syncthreads();
-
-    for (uint64_t tile = tile_begin; tile < tile_end; tile++) {
-        const uint32_t cur = (uint32_t)(tile - tile_begin);
-        const int st = cur & 1, pk = cur % 3;
-        const uint32_t* packed = s.packed[pk];
-        const uint32_t* bnd = s.bnd[st];
-        uint32_t* bdm = s.bdm[cur & 1];
-        const uint64_t t0 = tile * TILE;
-
-        // one super-k-mer record: L windows starting at tile-relative base p go to bucket b
-        auto put_record = [&](uint32_t b, uint32_t slot, int p, int L) {
-            const int c = p >> 4, sh = 2 * (p & 15);
-            const uint32_t w0 = packed[c], w1 = packed[c + 1], w2 = packed[c + 2], w3 = packed[c + 3];
-            const uint32_t r0w = __funnelshift_l(w1, w0, sh), r1w = __funnelshift_l(w2, w1, sh), r2w = __funnelshift_l(w3, w2, sh);
-            const int nb = L + k - 1;                                  // bases covered
-            Rec<RECW>* dst = nullptr;
-            if (slot < plan.cap) dst = recs + ((uint64_t)b * plan.cap + slot);
-            else {                                                      // region full: spill list (tier 2), else recount
-                unsigned long long si = atomicAdd(&a.status->n_spill, 1ull);
-                if (si < plan.spill_cap) dst = spill + si;
-                else overflow_kmers += L;
-            }
-            if (dst && !(plan.debug & 1)) {
-                if (RECW == 1) {
-                    uint64_t v = ((uint64_t)r0w << 32) | r1w;
-                    v &= ~0ull << (64 - 2 * nb);                       // nb <= 30
-                    // a region's last, partially written 32-byte sector must stay in L2 until it is complete (else every
-                    // record costs a sector fill from HBM): evict-last while it fills up, evict-first with its fourth record
-                    const uint64_t pol = (slot & 3u) == 3u ? pol_first : pol_last;
-                    asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(dst), "l"(v | (uint64_t)(L - 1)), "l"(pol) : "memory");
-                } else {
-                    uint64_t hi = ((uint64_t)r0w << 32) | r1w;
-                    uint64_t lo = (uint64_t)r2w << 32;                  // bases 32..47 (nb <= 47)
-                    if (nb <= 32) { hi &= ~0ull << (64 - 2 * nb); lo = 0; }
-                    else lo &= ~0ull << (128 - 2 * nb);
-                    const uint64_t pol = (slot & 1u) ? pol_first : pol_last;
-                    asm volatile("st.global.L2::cache_hint.v2.u64 [%0], {%1, %2}, %3;" ::"l"(dst), "l"(hi), "l"(lo | (uint64_t)(L - 1)), "l"(pol)
-                                 : "memory");
-                }
-            }
-        };
-
-        // ---- scan(tile): this thread's 16 windows start at tile-relative bases 16t .. 16t+15 and need bases up to 16t+46;
+    while (sc.next()) {
+        const uint32_t* bnd = sc.bnd();
+        // this thread's 16 windows start at tile-relative bases 16t .. 16t+15 and need bases up to 16t+46;
         // window 16t-1 (the previous thread's last) is looked at as well, so that runs continue across threads
         uint32_t w[3];
-        w[0] = packed[t]; w[1] = packed[t + 1]; w[2] = packed[t + 2];
-        const uint32_t wm1 = t ? packed[t - 1] : 0u;
+        w[0] = s.packed[t]; w[1] = s.packed[t + 1]; w[2] = s.packed[t + 2];
+        const uint32_t wm1 = t ? s.packed[t - 1] : 0u;
         // validity of the windows: no row start in (i, i+k-1], and inside the input
         uint32_t vmask = 0;      // bit j+1: window j is valid (j = -1 .. 15)
         {
             const int b0 = 16 * t;                                   // bit q of bw: a row starts at base 16t + q
             const uint32_t lo = bits32(bnd, b0), hi = bits32(bnd, b0 + 32);
             const uint64_t bw = ((uint64_t)hi << 32) | lo;
-            const uint64_t remaining = a.n_bases > t0 + 16ull * t ? a.n_bases - (t0 + 16ull * t) : 0;
+            const uint64_t remaining = a.n_bases > sc.t0 + 16ull * t ? a.n_bases - (sc.t0 + 16ull * t) : 0;
             if (remaining >= 16 && ((bw >> 1) & ((1ull << (15 + k - 1)) - 1ull)) == 0) vmask = 0x1fffeu;   // the common case
             else {
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
-                    bool ok = (((uint32_t)(bw >> (j + 1)) & kmask) == 0) && ((uint64_t)j < remaining);
+                    bool ok = (((uint32_t)(bw >> (j + 1)) & sc.kmask) == 0) && ((uint64_t)j < remaining);
                     vmask |= (uint32_t)ok << (j + 1);
                 }
             }
-            if (t && remaining && (lo & kmask) == 0) vmask |= 1u;     // window 16t-1: bits 16t .. 16t+k-2
+            if (t && remaining && (lo & sc.kmask) == 0) vmask |= 1u;  // window 16t-1: bits 16t .. 16t+k-2
         }
         uint32_t starts = 0;
         uint32_t h[17 + W - 1];                                       // h[j+1]: minimizer hash of window j
@@ -262,8 +194,9 @@ __global__ void __launch_bounds__(NT, PART_MINB) partition_kernel(ScanArgs a, Pa
             for (int j = 0; j < 16; j++)
                 if ((starts >> j) & 1u) wruns[rbase++] = ((unsigned long long)h[j + 1] << 32) | (uint32_t)(16 * t + j);
         }
-        // ---- issue(tile): run i of the warp is handled by lane i % 32; its region slot is a 64-bit atomicAdd with return on the
-        //      bucket's fill word (record count in the low half); up to EMIT_Q round trips per lane stay in flight
+        // ---- emission: run i of the warp is handled by lane i % 32.  The region slots (64-bit atomicAdd with return on the
+        //      bucket's fill word, record count in the low half) are requested BEFORE the tile barrier: up to EMIT_Q round
+        //      trips per lane are in flight while the warp waits for the other warps' boundary bits.
         constexpr int EMIT_Q = 6;
         __syncwarp();
         uint32_t posq[EMIT_Q], bq[EMIT_Q], slot[EMIT_Q];             // start base ; bucket ; region slot
@@ -275,15 +208,10 @@ __global__ void __launch_bounds__(NT, PART_MINB) partition_kernel(ScanArgs a, Pa
                 const unsigned long long d = wruns[r];
                 bq[q] = __umulhi(mix32((uint32_t)(d >> 32)), plan.hash_buckets) >> plan.fine_shift;
                 posq[q] = (uint32_t)d;
-                slot[q] = (plan.debug & 2) ? ((mix32(posq[q] + (uint32_t)tile) >> 8) % plan.cap) : (uint32_t)atomicAdd(&fill[bq[q]], 1ull);
+                slot[q] = (plan.debug & 2) ? ((mix32(posq[q] + (uint32_t)sc.tile) >> 8) % plan.cap) : (uint32_t)atomicAdd(&fill[bq[q]], 1ull);
             }
         }
-        // ---- pack(tile + 1) while the slots are on their way
-        if (tile + 1 < tile_end) pack_tile(tile + 1, st ^ 1, (cur + 1) % 3);
-        __syncthreads();                      // boundary bits of this tile and the packed bases of the next one are visible
-        if (t == 0 && tile + 2 < tile_end) issue_tile(tile + 2, st);   // this tile's stage is free: its bases were packed one tile
-                                                                       // ago, its row-start bits were consumed by the scan above
-        // ---- emit(tile)
+        __syncthreads();                                              // boundary bits of the whole tile are visible
         auto run_length = [&](uint32_t p0) {                          // the run ends before the next boundary bit after its first window
             uint32_t p = p0 + 1, R = 1;
             for (;;) {
@@ -294,11 +222,11 @@ __global__ void __launch_bounds__(NT, PART_MINB) partition_kernel(ScanArgs a, Pa
             return R;
         };
         // one run: its first record takes the slot reserved above; the k-mer count of the bucket (high half of the fill
-        // word) is bumped without a return value; a run longer than one record holds takes further slots
+        // word) is bumped without a return value; a run longer than one record holds takes further slots (repetitive text)
         auto emit_run = [&](uint32_t b, uint32_t slot0, uint32_t p0) {
             const uint32_t R = run_length(p0);
             const uint32_t L0 = R < rmax ? R : rmax;
-            if (!(plan.debug & 6)) atomicAdd(&fill[b], (unsigned long long)L0 << 32);
+            if (!(plan.debug & 2)) atomicAdd(&fill[b], (unsigned long long)L0 << 32);
             put_record(b, slot0, (int)p0, (int)L0);
             for (uint32_t off = rmax; off < R; off += rmax) {
                 const uint32_t L = R - off < rmax ? R - off : rmax;
@@ -315,6 +243,7 @@ __global__ void __launch_bounds__(NT, PART_MINB) partition_kernel(ScanArgs a, Pa
             const uint32_t s0 = (plan.debug & 2) ? 0u : (uint32_t)atomicAdd(&fill[b], 1ull);
             emit_run(b, s0, (uint32_t)d);
         }
+        sc.release();
     }
     if (overflow_kmers) atomicAdd(&a.status->n_overflow, overflow_kmers);
 }
