@@ -129,6 +129,13 @@ int kmer_cuda_submit_count_split(kmer_cuda_ctx *ctx, const char *seq, const uint
 								 uint64_t **uniq_codes, uint64_t *n_unique, kmer_count_pair **pairs, uint64_t *n_pairs,
 								 uint64_t *n_kmers);
 
+/* The split format with the bare codes packed for transport: (*uniq_packed) holds *n_unique little-endian integers
+ * of *code_bytes = ceil(2k/8) bytes each (6 at k=21 instead of 8; the reference's own kmer datum is k+1 = 22 bytes),
+ * code i at byte offset i * *code_bytes.  Everything else as kmer_cuda_submit_count_split. */
+int kmer_cuda_submit_count_packed(kmer_cuda_ctx *ctx, const char *seq, const uint64_t *row_off, uint64_t n_rows, int k,
+								  uint8_t **uniq_packed, uint64_t *n_unique, int *code_bytes, kmer_count_pair **pairs,
+								  uint64_t *n_pairs, uint64_t *n_kmers);
+
 /* Replaces per-row calls of kmer_equals / kmer_starts_with[_op] / kmer_contains / kmer_containing
  * (kmer.c:226-285) over a column of m k-mers against n_consts constants given as text:
  *   KMER_OP_EQUALS, KMER_OP_STARTS_WITH : constants are kmer literals   (kmer_in rules, kmer.c:109-129)

@@ -39,7 +39,7 @@ ABI_SYMBOLS = [
     "kmer_cuda_submit_encode", "kmer_cuda_dev_extract", "kmer_cuda_dev_count", "kmer_cuda_dev_match",
     "kmer_cuda_dev_decode", "kmer_cuda_dev_finish", "kmer_cuda_set_profiling", "kmer_cuda_get_phases",
     "kmer_cuda_shard_plan", "kmer_cuda_dev_shard_partition", "kmer_cuda_dev_shard_count", "kmer_cuda_dev_dense_table",
-    "kmer_cuda_dev_dense_emit", "kmer_cuda_submit_count_split", "kmer_cuda_dev_count_split",
+    "kmer_cuda_dev_dense_emit", "kmer_cuda_submit_count_split", "kmer_cuda_dev_count_split", "kmer_cuda_submit_count_packed",
 ]
 
 
@@ -96,6 +96,7 @@ def load_library(path: Path = LIB_PATH) -> C.CDLL:
     L.kmer_cuda_dev_count.argtypes = [vp, vp, u64, vp, u64, i32, vp, u64, i32, vp]
     L.kmer_cuda_dev_count_split.argtypes = [vp, vp, u64, vp, u64, i32, vp, u64, vp, u64, vp]
     L.kmer_cuda_submit_count_split.argtypes = [vp, vp, vp, u64, i32, C.POINTER(vp), u64p, C.POINTER(vp), u64p, u64p]
+    L.kmer_cuda_submit_count_packed.argtypes = [vp, vp, vp, u64, i32, C.POINTER(vp), u64p, C.POINTER(C.c_int), C.POINTER(vp), u64p, u64p]
     L.kmer_cuda_dev_match.argtypes = [vp, i32, vp, vp, vp, u64, i32, C.POINTER(cp), C.c_uint32, vp, vp, vp]
     L.kmer_cuda_dev_decode.argtypes = [vp, vp, u64, i32, i32, vp, vp]
     L.kmer_cuda_dev_finish.argtypes = [vp, vp, C.POINTER(KmerDevResult)]
@@ -212,6 +213,19 @@ class KmerCuda:
         u = self._take(uq, nu.value * 8, np.uint64)
         a = self._take(pairs, npairs.value * 16, np.uint64).reshape(-1, 2)
         return u.copy(), a[:, 0].copy(), a[:, 1].copy(), int(n.value)
+
+    def count_kmers_packed(self, rows_or_flat, k: int, off=None):
+        """Split format with packed bare codes -> (unique codes[U] (unpacked here), codes[P], counts[P], n_kmers, code_bytes)."""
+        f, o = _flat(rows_or_flat, off)
+        uq, nu, nb, pairs, npairs, n = C.c_void_p(), C.c_uint64(), C.c_int(), C.c_void_p(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.kmer_cuda_submit_count_packed(self.ctx, f.ctypes.data, o.ctypes.data, len(o) - 1, k, C.byref(uq),
+                                                           C.byref(nu), C.byref(nb), C.byref(pairs), C.byref(npairs), C.byref(n)))
+        raw = self._take(uq, nu.value * nb.value, np.uint8).reshape(-1, max(nb.value, 1))
+        u = np.zeros(raw.shape[0], dtype=np.uint64)
+        for b in range(nb.value):
+            u |= raw[:, b].astype(np.uint64) << np.uint64(8 * b)
+        a = self._take(pairs, npairs.value * 16, np.uint64).reshape(-1, 2)
+        return u, a[:, 0].copy(), a[:, 1].copy(), int(n.value), int(nb.value)
 
     def match(self, op, codes: np.ndarray, k: int, consts, lens: np.ndarray | None = None, ops=None):
         """Bit matrix [n_consts, m] (bool) and hits[n_consts] for the column `codes`."""

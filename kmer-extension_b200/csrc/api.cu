@@ -1011,6 +1011,49 @@ extern "C" int kmer_cuda_submit_count_split(kmer_cuda_ctx* c, const char* seq, c
     return KMER_OK;
 }
 
+extern "C" int kmer_cuda_submit_count_packed(kmer_cuda_ctx* c, const char* seq, const uint64_t* row_off, uint64_t n_rows, int k,
+                                             uint8_t** uniq_packed, uint64_t* n_unique, int* code_bytes,
+                                             kmer_count_pair** pairs, uint64_t* n_pairs, uint64_t* n_kmers) {
+    if (!c || !uniq_packed || !n_unique || !code_bytes || !pairs || !n_pairs) return KMER_ERR_BAD_ARGUMENT;
+    *uniq_packed = nullptr; *pairs = nullptr;
+    *n_unique = 0; *n_pairs = 0; *code_bytes = 0;
+    if (n_kmers) *n_kmers = 0;
+    CU(cudaSetDevice(c->di.device), "cudaSetDevice");
+    uint64_t n_bases = 0;
+    int rc = upload_rows(c, seq, row_off, n_rows, &n_bases);
+    if (rc) return rc;
+    uint64_t cap = kmer_cuda_max_kmers(n_bases, n_rows, k);
+    if (k >= 1 && k < 32 && (1ull << (2 * k)) < cap) cap = 1ull << (2 * k);
+    rc = ws(c, c->pairs, cap * sizeof(kmer_count_pair));
+    if (!rc) rc = ws(c, c->codes, cap * sizeof(uint64_t));
+    if (rc) return rc;
+    rc = kmer_cuda_dev_count_split(c, (const char*)c->seq.p, n_bases, (const uint64_t*)c->off.p, n_rows, k, (uint64_t*)c->codes.p, cap,
+                                   (kmer_count_pair*)c->pairs.p, cap, KMER_OWN_STREAM);
+    if (rc) return rc;
+    kmer_dev_result res;
+    rc = kmer_cuda_dev_finish(c, KMER_OWN_STREAM, &res);
+    if (rc) return rc;
+    const int nbytes = k >= 1 ? (2 * k + 7) / 8 : 1;
+    const size_t packed_bytes = (size_t)res.n_unique * (size_t)nbytes;
+    rc = ws(c, c->text, packed_bytes + 16);
+    if (rc) return rc;
+    launch_pack_codes(c->di, (const uint64_t*)c->codes.p, res.n_unique, nbytes, (uint8_t*)c->text.p, c->stream);
+    c->launches++;
+    uint8_t* out_u = (uint8_t*)pinned_get(c, packed_bytes);
+    kmer_count_pair* out_p = (kmer_count_pair*)pinned_get(c, res.n_distinct * sizeof(kmer_count_pair));
+    if (!out_u || !out_p) return c->err.status;
+    CU(cudaMemcpyAsync(out_u, c->text.p, packed_bytes, cudaMemcpyDeviceToHost, c->stream), "D2H packed codes");
+    CU(cudaMemcpyAsync(out_p, c->pairs.p, res.n_distinct * sizeof(kmer_count_pair), cudaMemcpyDeviceToHost, c->stream), "D2H pairs");
+    CU(cudaStreamSynchronize(c->stream), "stream sync");
+    *uniq_packed = out_u;
+    *n_unique = res.n_unique;
+    *code_bytes = nbytes;
+    *pairs = out_p;
+    *n_pairs = res.n_distinct;
+    if (n_kmers) *n_kmers = res.n_kmers;
+    return KMER_OK;
+}
+
 extern "C" int kmer_cuda_submit_match(kmer_cuda_ctx* c, int op, const int* ops, const uint64_t* codes, const uint8_t* lens,
                                       uint64_t m, int k, const char* const* consts, uint32_t n_consts, uint32_t** bits,
                                       uint64_t* words_per_row, uint64_t** hits) {

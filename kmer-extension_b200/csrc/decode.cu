@@ -66,4 +66,40 @@ void launch_encode(const DeviceInfo& di, const char* d_text, const uint8_t* d_le
     encode_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_text, d_lens, n, stride, d_codes, d_status);
 }
 
+// codes[n] (uint64) -> n little-endian integers of `nbytes` bytes each (nbytes = ceil(2k/8)): the transport form of a
+// column of k-mers when every byte that crosses PCIe counts.  A CTA packs 1024 codes per step into shared memory and
+// writes them out as 16-byte vectors (1024 * nbytes is a multiple of 16).
+__global__ void __launch_bounds__(256) pack_codes_kernel(const uint64_t* __restrict__ codes, uint64_t n, int nbytes,
+                                                         uint8_t* __restrict__ out) {
+    __shared__ __align__(16) uint8_t buf[1024 * 8];
+    const uint64_t n_steps = (n + 1023) / 1024;
+    for (uint64_t step = blockIdx.x; step < n_steps; step += gridDim.x) {
+        const uint64_t base = step * 1024;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t j = q * 256 + threadIdx.x;
+            const uint64_t i = base + j;
+            uint64_t c = i < n ? codes[i] : 0ull;
+            for (int b = 0; b < nbytes; b++) { buf[j * nbytes + b] = (uint8_t)c; c >>= 8; }
+        }
+        __syncthreads();
+        const uint64_t left = n - base < 1024 ? n - base : 1024;
+        const uint32_t bytes = (uint32_t)left * (uint32_t)nbytes;
+        uint8_t* dst = out + base * (uint64_t)nbytes;
+        for (uint32_t o = threadIdx.x * 16; o < bytes; o += 256 * 16) {
+            if (o + 16 <= bytes) *reinterpret_cast<uint4*>(dst + o) = *reinterpret_cast<const uint4*>(buf + o);
+            else for (uint32_t z = o; z < bytes; z++) dst[z] = buf[z];
+        }
+        __syncthreads();
+    }
+}
+
+void launch_pack_codes(const DeviceInfo& di, const uint64_t* d_codes, uint64_t n, int nbytes, uint8_t* d_out, cudaStream_t st) {
+    if (!n) return;
+    uint64_t blocks = (n + 1023) / 1024;
+    uint64_t maxb = (uint64_t)di.sm_count * 8;
+    if (blocks > maxb) blocks = maxb;
+    pack_codes_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_codes, n, nbytes, d_out);
+}
+
 }  // namespace kmer

@@ -96,6 +96,8 @@ void launch_match(const DeviceInfo& di, int op, const int* d_ops, bool any_conta
 // decode.cu -------------------------------------------------------------------------------------
 void launch_decode(const DeviceInfo& di, const uint64_t* d_codes, uint64_t n, int k, int with_header, char* d_text,
                    cudaStream_t st);
+// uint64 codes -> nbytes-byte little-endian integers (d_out: n * nbytes bytes, 16-byte aligned)
+void launch_pack_codes(const DeviceInfo& di, const uint64_t* d_codes, uint64_t n, int nbytes, uint8_t* d_out, cudaStream_t st);
 void launch_encode(const DeviceInfo& di, const char* d_text, const uint8_t* d_lens, uint64_t n, int stride,
                    uint64_t* d_codes, DevStatus* d_status, cudaStream_t st);
 

@@ -30,7 +30,7 @@ def test_header_symbols_exported(lib):
 
 
 def test_abi_version_and_helpers(lib):
-    assert lib.kmer_cuda_abi_version() == 1
+    assert lib.kmer_cuda_abi_version() == 2
     assert lib.kmer_cuda_max_kmers(1000, 1, 21) == 980
     assert lib.kmer_cuda_max_kmers(10, 5, 21) == 0
     assert lib.kmer_cuda_max_kmers(10, 1, 0) == 0
