@@ -218,7 +218,7 @@ int kmer_cuda_dev_finish(kmer_cuda_ctx *ctx, void *stream, kmer_dev_result *resu
  *   kmer_cuda_shard_plan()            same arguments on every rank -> same plan
  *   kmer_cuda_dev_shard_partition()   rows -> send_recs [n_buckets][cap] records, send_fill [n_buckets]
  *   all-to-all(send_recs, recs_bytes_per_peer)  and  all-to-all(send_fill, fill_bytes_per_peer)
- *   kmer_cuda_dev_shard_count()       recv_recs [n_ranks][buckets_per_rank][cap], recv_fill [n_ranks][buckets_per_rank]
+ *   kmer_cuda_dev_shard_count()       recv_recs [n_ranks * chunks_per_rank][buckets_per_rank][cap], recv_fill likewise
  *                                     -> this rank's (k-mer, count) pairs
  * 14 <= k <= 32.  (Smaller k: kmer_cuda_dev_dense_table + all-reduce + kmer_cuda_dev_dense_emit.) */
 typedef struct kmer_shard_plan
@@ -234,10 +234,17 @@ typedef struct kmer_shard_plan
 	int32_t w, m, recw, rmax;  /* minimizer window / m-mer length / record words / max k-mers per record */
 	uint32_t fine_shift;	   /* every partition is split into 2^fine_shift fine buckets by its owner */
 	uint32_t fine_cap;		   /* records per fine bucket region (owner side workspace) */
-	uint32_t reserved[2];
+	uint32_t chunks_per_rank;  /* segments per source GPU (kmer_cuda_shard_plan_chunked), 1 otherwise */
+	uint32_t reserved;
 } kmer_shard_plan;
 
 int kmer_cuda_shard_plan(uint64_t total_kmers_all_ranks, int k, uint32_t n_ranks, kmer_shard_plan *plan);
+/* The same plan when every GPU partitions its rows in `chunks_per_rank` pieces, each into its own send buffer
+ * ([n_buckets][cap], cap sized for a piece), so that the exchange of piece i overlaps the partition pass of piece i+1.
+ * kmer_cuda_dev_shard_count() then takes recv_recs [chunks_per_rank * n_ranks][buckets_per_rank][cap] (segments in any
+ * order) and recv_fill likewise. */
+int kmer_cuda_shard_plan_chunked(uint64_t total_kmers_all_ranks, int k, uint32_t n_ranks, uint32_t chunks_per_rank,
+								 kmer_shard_plan *plan);
 /* Fails with KMER_ERR_CAPACITY (reported by kmer_cuda_dev_finish) if a segment overflows: input too
  * repetitive for this path; nothing may be used then. */
 int kmer_cuda_dev_shard_partition(kmer_cuda_ctx *ctx, const char *d_seq, uint64_t n_bases, const uint64_t *d_row_off,

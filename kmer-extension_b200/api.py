@@ -39,7 +39,7 @@ ABI_SYMBOLS = [
     "kmer_cuda_submit_encode", "kmer_cuda_dev_extract", "kmer_cuda_dev_count", "kmer_cuda_dev_match",
     "kmer_cuda_dev_decode", "kmer_cuda_dev_finish", "kmer_cuda_set_profiling", "kmer_cuda_get_phases",
     "kmer_cuda_shard_plan", "kmer_cuda_dev_shard_partition", "kmer_cuda_dev_shard_count", "kmer_cuda_dev_dense_table",
-    "kmer_cuda_dev_dense_emit", "kmer_cuda_submit_count_split", "kmer_cuda_dev_count_split", "kmer_cuda_submit_count_packed",
+    "kmer_cuda_dev_dense_emit", "kmer_cuda_submit_count_split", "kmer_cuda_dev_count_split", "kmer_cuda_submit_count_packed", "kmer_cuda_shard_plan_chunked",
 ]
 
 
@@ -57,7 +57,7 @@ class KmerShardPlan(C.Structure):
     _fields_ = [("n_ranks", C.c_uint32), ("n_buckets", C.c_uint32), ("buckets_per_rank", C.c_uint32), ("cap", C.c_uint32),
                 ("k", C.c_int32), ("rec_bytes", C.c_int32), ("recs_bytes_per_peer", C.c_uint64),
                 ("fill_bytes_per_peer", C.c_uint64), ("w", C.c_int32), ("m", C.c_int32), ("recw", C.c_int32), ("rmax", C.c_int32),
-                ("fine_shift", C.c_uint32), ("fine_cap", C.c_uint32), ("reserved", C.c_uint32 * 2)]
+                ("fine_shift", C.c_uint32), ("fine_cap", C.c_uint32), ("chunks_per_rank", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class KmerSqlError(Exception):
@@ -104,6 +104,7 @@ def load_library(path: Path = LIB_PATH) -> C.CDLL:
     L.kmer_cuda_set_profiling.restype = None
     L.kmer_cuda_get_phases.argtypes = [vp, C.POINTER(cp), C.POINTER(C.c_float), i32]
     L.kmer_cuda_shard_plan.argtypes = [u64, i32, C.c_uint32, C.POINTER(KmerShardPlan)]
+    L.kmer_cuda_shard_plan_chunked.argtypes = [u64, i32, C.c_uint32, C.c_uint32, C.POINTER(KmerShardPlan)]
     L.kmer_cuda_dev_shard_partition.argtypes = [vp, vp, u64, vp, u64, C.POINTER(KmerShardPlan), vp, vp, vp]
     L.kmer_cuda_dev_shard_count.argtypes = [vp, C.POINTER(KmerShardPlan), vp, vp, vp, u64, vp]
     L.kmer_cuda_dev_dense_table.argtypes = [vp, vp, u64, vp, u64, i32, vp, vp]
@@ -325,9 +326,9 @@ class KmerCuda:
                                                   self._stream_ptr(stream)))
 
     # ------------------------------------------------------------------ sharded counting (the caller runs the exchange)
-    def shard_plan(self, total_kmers: int, k: int, n_ranks: int) -> KmerShardPlan:
+    def shard_plan(self, total_kmers: int, k: int, n_ranks: int, chunks: int = 1) -> KmerShardPlan:
         plan = KmerShardPlan()
-        if self.lib.kmer_cuda_shard_plan(total_kmers, k, n_ranks, C.byref(plan)):
+        if self.lib.kmer_cuda_shard_plan_chunked(total_kmers, k, n_ranks, chunks, C.byref(plan)):
             raise ValueError("kmer_cuda_shard_plan: needs 14 <= k <= 32 and n_ranks >= 1")
         return plan
 

@@ -711,7 +711,13 @@ extern "C" int kmer_cuda_dev_finish(kmer_cuda_ctx* c, void* stream, kmer_dev_res
 // sharded counting (the caller owns the exchange)
 
 extern "C" int kmer_cuda_shard_plan(uint64_t total_kmers, int k, uint32_t n_ranks, kmer_shard_plan* plan) {
-    if (!plan || n_ranks < 1 || n_ranks > 16 || k < 14 || k > KMER_CUDA_MAX_K) return KMER_ERR_BAD_ARGUMENT;
+    return kmer_cuda_shard_plan_chunked(total_kmers, k, n_ranks, 1, plan);
+}
+
+extern "C" int kmer_cuda_shard_plan_chunked(uint64_t total_kmers, int k, uint32_t n_ranks, uint32_t chunks_per_rank,
+                                            kmer_shard_plan* plan) {
+    if (!plan || n_ranks < 1 || n_ranks > 16 || chunks_per_rank < 1 || n_ranks * chunks_per_rank > 32 || k < 14 || k > KMER_CUDA_MAX_K)
+        return KMER_ERR_BAD_ARGUMENT;
     // fine buckets as on one GPU (about 1000 k-mers each), 2^fine_shift of them per coarse partition
     PartitionPlan p = make_partition_plan(total_kmers, k);
     uint64_t fine_per_rank = ((uint64_t)p.n_buckets + n_ranks - 1) / n_ranks;
@@ -725,13 +731,14 @@ extern "C" int kmer_cuda_shard_plan(uint64_t total_kmers, int k, uint32_t n_rank
     plan->n_buckets = plan->buckets_per_rank * n_ranks;
     plan->fine_shift = fine_shift;
     plan->fine_cap = p.cap;
+    plan->chunks_per_rank = chunks_per_rank;
     plan->k = k;
     plan->w = p.w; plan->m = p.m; plan->recw = p.recw; plan->rmax = p.rmax;
     plan->rec_bytes = p.recw == 1 ? 8 : 16;
     {   // records per (coarse partition, source): 1/n_ranks of a partition's k-mers, about 2.1/(w+1) records per k-mer
         double kmers_per_part = (double)total_kmers / (double)plan->n_buckets;
         double rpk = 2.1 / (p.w + 1) + (p.rmax < p.w ? 1.0 / p.rmax : 0.0);
-        double mean = kmers_per_part * rpk / n_ranks;
+        double mean = kmers_per_part * rpk / (n_ranks * chunks_per_rank);
         double cap = 1.15 * mean + 6.0 * sqrt(3.0 * mean) + 64.0;
         plan->cap = ((uint32_t)cap + 1u) & ~1u;   // even: every (partition, source) segment starts 16-byte aligned
     }
@@ -812,7 +819,8 @@ extern "C" int kmer_cuda_dev_shard_count(kmer_cuda_ctx* c, const kmer_shard_plan
     if (!rc) rc = ws(c, c->spill, partition_spill_bytes(plan));
     if (!rc) rc = ws(c, c->failed, (size_t)plan.n_buckets * 4);
     if (rc) return rc;
-    launch_refine(c->di, plan, k, (int)sp->n_ranks, sp->buckets_per_rank, sp->cap, (const unsigned long long*)d_recv_fill,
+    const int n_src = (int)(sp->n_ranks * (sp->chunks_per_rank ? sp->chunks_per_rank : 1u));
+    launch_refine(c->di, plan, k, n_src, sp->buckets_per_rank, sp->cap, (const unsigned long long*)d_recv_fill,
                   d_recv_recs, (unsigned long long*)c->fill.p, c->recs.p, c->spill.p, c->d_status, st);
     mark(c, st, "refine");
     launch_bucket_count(c->di, plan, k, 1, (const unsigned long long*)c->fill.p, c->recs.p, (uint32_t*)c->failed.p, d_pairs,

@@ -6,7 +6,9 @@ the multi-GPU form of `SELECT kmer, count(*) ... GROUP BY kmer` over generate_km
   1. every rank partitions ITS rows' k-mers into the same global minimizer buckets
      (kmer_cuda_dev_shard_partition),
   2. bucket b is owned by rank b // buckets_per_rank; ONE all-to-all (equal splits) moves every
-     (bucket, source) segment of super-k-mer records to its owner, a second small one the fill counts,
+     (bucket, source) segment of super-k-mer records to its owner, a second small one the fill counts
+     (optionally, chunks=2, the rows are partitioned in two pieces and the exchange of the first piece runs on
+     a side stream while the second piece is being partitioned),
   3. every owner counts its buckets on chip (kmer_cuda_dev_shard_count).
 
 Identical k-mers share a minimizer, hence a bucket, hence an owner, so the per-rank results are
@@ -23,8 +25,9 @@ import torch.distributed as dist
 
 
 class ShardedCounter:
-    def __init__(self, engine, group=None, device=None):
+    def __init__(self, engine, group=None, device=None, chunks=None):
         self.eng = engine
+        self.chunks = chunks       # pieces a rank's rows are partitioned in (None: 1)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -51,6 +54,18 @@ class ShardedCounter:
         dist.all_reduce(t, op=op, group=self.group)
         return int(t.item())
 
+    @staticmethod
+    def _find_cut(d_off, n_rows: int):
+        """A row index near the middle whose first base sits on a 16-byte boundary of the column (or None)."""
+        if n_rows < 64:
+            return None
+        mid = n_rows // 2
+        window = d_off[mid: min(mid + 256, n_rows)]
+        hit = ((window % 16) == 0).nonzero()
+        if hit.numel() == 0:
+            return None
+        return mid + int(hit[0].item())
+
     def _phases(self):
         return list(self.eng.phases()) if hasattr(self.eng, "phases") else []
 
@@ -74,37 +89,77 @@ class ShardedCounter:
             total_kmers = self._allreduce_int(local_kmers)
         if k <= 13:
             return self._count_dense(d_seq, n_bases, d_off, n_rows, k, d_pairs, total_kmers)
-        plan = eng.shard_plan(max(total_kmers, 1), k, self.world)
+        # chunks=2 partitions the rows in two pieces and exchanges the first on a side stream while the second is being
+        # partitioned.  Measured on 2xB200 it LOSES (18.8 vs 17.9 ms/step: two launches and host round trips per step, and
+        # the exchange slows the partition kernel it runs beside), so it is opt-in.
+        chunks = self.chunks if self.chunks is not None else 1
+        # every rank must cut its rows in the same number of pieces: a piece starts on a 16-byte boundary of the column
+        cut = None
+        if chunks == 2:
+            cut = self._find_cut(d_off, n_rows)
+            ok = self._allreduce_int(0 if cut is None else 1, dist.ReduceOp.MIN)
+            if not ok:
+                chunks, cut = 1, None
+        if chunks == 1:
+            plan = eng.shard_plan(max(total_kmers, 1), k, self.world)
+        else:
+            plan = eng.shard_plan(max(total_kmers, 1), k, self.world, chunks)
         self.last_plan = plan
-        recs_bytes = plan.recs_bytes_per_peer * self.world
+        recs_bytes = plan.recs_bytes_per_peer * self.world       # one piece
         fill_words = plan.buckets_per_rank * self.world
-        send_recs = self._buf("send_recs", recs_bytes)
-        send_fill = self._buf("send_fill", fill_words * 8, torch.int64)
+        send_recs = self._buf("send_recs", recs_bytes * chunks)
+        send_fill = self._buf("send_fill", fill_words * 8 * chunks, torch.int64)
+        recv_recs = self._buf("recv_recs", recs_bytes * chunks) if self.world > 1 else send_recs
+        recv_fill = self._buf("recv_fill", fill_words * 8 * chunks, torch.int64) if self.world > 1 else send_fill
+        pieces = [(0, n_rows)] if chunks == 1 else [(0, cut), (cut, n_rows)]
         exc = None
         phases = []
-        try:
-            eng.dev_shard_partition(d_seq, n_bases, d_off, n_rows, plan, send_recs, send_fill)
-            eng.dev_finish()
-            phases += self._phases()
-        except Exception as e:  # input error or segment overflow on this rank
-            exc = e
+        timed = self.device.type == "cuda" and getattr(eng, "profiling", False)
+        comm = None
+        if self.world > 1 and self.device.type == "cuda":
+            if getattr(self, "_comm_stream", None) is None:
+                self._comm_stream = torch.cuda.Stream(device=self.device)
+            comm = self._comm_stream
+        a2a_events = []
+        for ci, (r0, r1) in enumerate(pieces):
+            sr = send_recs[ci * recs_bytes:(ci + 1) * recs_bytes]
+            sf = send_fill[ci * fill_words:(ci + 1) * fill_words]
+            try:
+                if chunks == 1:
+                    eng.dev_shard_partition(d_seq, n_bases, d_off, n_rows, plan, sr, sf)
+                else:
+                    b0 = int(d_off[r0].item())
+                    b1 = int(d_off[r1].item())
+                    eng.dev_shard_partition(d_seq[b0:], b1 - b0, d_off[r0:r1 + 1] - b0, r1 - r0, plan, sr, sf)
+                eng.dev_finish()          # the piece is partitioned (host waits): its exchange may start
+                phases += self._phases()
+            except Exception as e:  # input error or segment overflow on this rank
+                exc = exc or e
+            if self.world > 1:
+                rr = recv_recs[ci * recs_bytes:(ci + 1) * recs_bytes]
+                rf = recv_fill[ci * fill_words:(ci + 1) * fill_words]
+                if comm is not None:
+                    with torch.cuda.stream(comm):
+                        if timed:
+                            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                            e0.record()
+                        dist.all_to_all_single(rf, sf, group=self.group)
+                        dist.all_to_all_single(rr, sr, group=self.group)
+                        if timed:
+                            e1.record()
+                            a2a_events.append((e0, e1))
+                else:
+                    dist.all_to_all_single(rf, sf, group=self.group)
+                    dist.all_to_all_single(rr, sr, group=self.group)
+        if comm is not None:
+            torch.cuda.current_stream().wait_stream(comm)
+            if timed:
+                torch.cuda.synchronize()
+                phases.append(("all_to_all", sum(a.elapsed_time(b) for a, b in a2a_events)))
         self._agree(exc)
         if self.world > 1:
-            recv_recs = self._buf("recv_recs", recs_bytes)
-            recv_fill = self._buf("recv_fill", fill_words * 8, torch.int64)
-            timed = self.device.type == "cuda" and getattr(eng, "profiling", False)
-            if timed:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-            dist.all_to_all_single(recv_fill, send_fill, group=self.group)
-            dist.all_to_all_single(recv_recs, send_recs, group=self.group)
-            if timed:
-                e1.record()
-                e1.synchronize()
-                phases.append(("all_to_all", e0.elapsed_time(e1)))
-            self.last_exchange_bytes = int(recs_bytes + fill_words * 8) * (self.world - 1) // self.world
+            self.last_exchange_bytes = int(recs_bytes + fill_words * 8) * chunks * (self.world - 1) // self.world
         else:
-            recv_recs, recv_fill = send_recs, send_fill
             self.last_exchange_bytes = 0
         eng.dev_shard_count(plan, recv_recs, recv_fill, d_pairs)
         r = eng.dev_finish()
