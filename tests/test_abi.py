@@ -59,3 +59,45 @@ def test_product_never_imports_oracle():
         if p.suffix in {".py", ".cu", ".cuh", ".c", ".h"}:
             txt = p.read_text()
             assert "oracle" not in txt.lower().replace("oracle/pgshim", ""), f"{p} mentions the oracle"
+
+
+def test_shard_plan_invariants(lib):
+    """kmer_cuda_shard_plan is host-only arithmetic: check what the kernels and the exchange rely on."""
+    for total in (1, 10_000, 3_000_000, 980_000_000, 7_840_000_000, 80_000_000_000):
+        for k in (14, 17, 19, 21, 26, 27, 29, 32):
+            for n_ranks in (1, 2, 3, 8, 16):
+                for chunks in (1, 2):
+                    p = api.KmerShardPlan()
+                    assert lib.kmer_cuda_shard_plan_chunked(total, k, n_ranks, chunks, C.byref(p)) == 0
+                    assert p.n_ranks == n_ranks and p.chunks_per_rank == chunks and p.k == k
+                    assert p.n_buckets == p.buckets_per_rank * n_ranks and p.buckets_per_rank >= 1
+                    assert p.cap % 2 == 0 and p.cap >= 64                      # segments start 16-byte aligned
+                    assert p.fine_cap % 4 == 0                                  # fine regions are whole 32-byte sectors
+                    assert p.rec_bytes == (8 if k <= 26 else 16) and p.recw == (1 if k <= 26 else 2)
+                    assert p.recs_bytes_per_peer == p.buckets_per_rank * p.cap * p.rec_bytes
+                    assert p.fill_bytes_per_peer == p.buckets_per_rank * 8
+                    assert 0 <= p.fine_shift <= 8 and (p.n_buckets << p.fine_shift) < 2 ** 31
+                    # every fine bucket holds about 1200 k-mers of the whole job (never more than 2x unless the job is tiny)
+                    fine_total = p.n_buckets << p.fine_shift
+                    assert fine_total * 1200 >= total
+                    # minimizer window: suits the record width, m-mer at most 16 bases, windows fit a record
+                    assert p.w in ((4, 6, 8) if k <= 26 else (8, 12, 16))
+                    assert p.m == min(16, k - p.w + 1) and p.m >= 2
+                    assert 1 <= p.rmax <= 16 and p.rmax + k - 1 <= (30 if k <= 26 else 61)
+    bad = api.KmerShardPlan()
+    assert lib.kmer_cuda_shard_plan(1000, 13, 2, C.byref(bad)) != 0          # k <= 13 is the dense path
+    assert lib.kmer_cuda_shard_plan(1000, 21, 0, C.byref(bad)) != 0
+    assert lib.kmer_cuda_shard_plan_chunked(1000, 21, 16, 4, C.byref(bad)) != 0   # at most 32 segments per bucket
+
+
+def test_shard_plan_window_follows_job_size(lib):
+    """Bigger jobs get narrower minimizer windows (longer m-mers) so that buckets stay even."""
+    def w(total, k):
+        p = api.KmerShardPlan()
+        assert lib.kmer_cuda_shard_plan(total, k, 8, C.byref(p)) == 0
+        return p.w, p.m
+    assert w(980_000_000, 21) == (8, 14)        # 1 GB: 14-base m-mers are enough
+    assert w(7_840_000_000, 21) == (6, 16)      # 8 GB
+    assert w(9_700_000_000, 31) == (16, 16)     # C3: already 16-base m-mers
+    assert w(980_000_000, 27) == (12, 16)       # W=16 would leave 12-base m-mers
+    assert w(980_000_000, 17)[0] == 4
