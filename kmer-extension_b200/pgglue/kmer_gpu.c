@@ -77,7 +77,8 @@ kmer_gpu_count_datums(struct varlena **dnas, uint64_t n, int k, struct varlena *
 {
 	kmer_cuda_ctx *ctx = kmer_gpu_context();
 	uint64_t *off = (uint64_t *) palloc((n + 1) * sizeof(uint64_t));
-	uint64_t total = 0, i, n_kmers = 0, d = 0;
+	uint64_t total = 0, i, n_kmers = 0, d = 0, n_uniq = 0, n_pairs = 0;
+	uint64_t *uniq = NULL;
 	char *flat, *text = NULL;
 	kmer_count_pair *pairs = NULL;
 	uint64_t *codes;
@@ -92,17 +93,26 @@ kmer_gpu_count_datums(struct varlena **dnas, uint64_t n, int k, struct varlena *
 	for (i = 0; i < n; i++)
 		memcpy(flat + off[i], VARDATA_ANY(dnas[i]), (size_t) (off[i + 1] - off[i]));
 
-	if (kmer_cuda_submit_count(ctx, flat, off, n, k, &pairs, &d, &n_kmers) != KMER_OK)
+	/* split result format: groups with count 1 come back as bare codes, the rest as (code, count) pairs --
+	 * the same table as kmer_cuda_submit_count(), half the bytes across PCIe on mostly distinct k-mers */
+	if (kmer_cuda_submit_count_split(ctx, flat, off, n, k, &uniq, &n_uniq, &pairs, &n_pairs, &n_kmers) != KMER_OK)
 		kmer_gpu_raise(kmer_cuda_last_error(ctx));
+	d = n_uniq + n_pairs;
 
 	/* text of the groups with the short varlena header already in place: d * (k+1) bytes */
 	codes = (uint64_t *) palloc((d ? d : 1) * sizeof(uint64_t));
 	*counts = (int64_t *) palloc((d ? d : 1) * sizeof(int64_t));
-	for (i = 0; i < d; i++)
+	for (i = 0; i < n_uniq; i++)
 	{
-		codes[i] = pairs[i].code;
-		(*counts)[i] = (int64_t) pairs[i].count;
+		codes[i] = uniq[i];
+		(*counts)[i] = 1;
 	}
+	for (i = 0; i < n_pairs; i++)
+	{
+		codes[n_uniq + i] = pairs[i].code;
+		(*counts)[n_uniq + i] = (int64_t) pairs[i].count;
+	}
+	kmer_cuda_release(ctx, uniq);
 	kmer_cuda_release(ctx, pairs);
 	if (kmer_cuda_submit_decode(ctx, codes, d, k, 1, &text) != KMER_OK)
 		kmer_gpu_raise(kmer_cuda_last_error(ctx));
