@@ -57,7 +57,7 @@ struct alignas(16) Rec<2> {
 // partition
 
 #ifndef PART_MINB
-#define PART_MINB 4
+#define PART_MINB 3
 #endif
 template <int W, int RECW>
 __global__ void __launch_bounds__(NT, PART_MINB) partition_kernel(ScanArgs a, PartitionPlan plan, unsigned long long* __restrict__ fill,
