@@ -5,20 +5,22 @@
 // two kernels with a compact intermediate:
 //
 //  partition_kernel   tile scanner (TMA-staged ASCII -> 2-bit) -> for every window the minimum
-//                     hashed m-mer over its first W m-mers -> bucket = mix(min) * NB >> 32.
+//                     hashed m-mer over its W m-mers -> bucket = mix(min) * NB >> 32.
 //                     Identical k-mers have identical minimizers, hence the same bucket.
-//                     Consecutive windows that share a bucket are emitted as ONE super-k-mer record
+//                     Consecutive windows that share a minimizer are emitted as ONE super-k-mer record
 //                     (2 bits per base + a length), appended to the bucket's region with a single
-//                     64-bit atomicAdd per record (about 0.3 records per k-mer on random DNA).
-//  bucket_count_kernel one CTA per bucket: expand the records, insert every k-mer into a 4096-slot
-//                     shared-memory hash table (64-bit atomicCAS), append the distinct
-//                     (k-mer, count) pairs to the result with one global atomicAdd per bucket.
+//                     64-bit atomicAdd per record (about 0.22 records per k-mer at W = 8).
+//  bucket_count_kernel one CTA per bucket (about 1200 k-mers): a bitmap filter proves most k-mers unique
+//                     (they are written straight to the result), the rest is counted exactly in a
+//                     2048-slot shared-memory hash table (64-bit atomicCAS).
+//  refine_*_kernel    sharded counting only: a source GPU partitions into few coarse partitions, the owner
+//                     splits them into the fine buckets above.
 //
-// HBM traffic: read N bases once, write + read ~2.3 B per k-mer of records, write 16 B per group.
+// HBM traffic: read N bases once, write + read ~1.8 B per k-mer of records, write 16 B per group.
 //
 // What does not fit is handled in tiers (skewed / repetitive input):
-//   tier 2  a bucket whose region overflowed (extra records go to a spill list) or whose distinct
-//           k-mers overflow the shared table is put on a failed list and emits nothing; one more
+//   tier 2  a bucket whose region overflowed (extra records go to a spill list) or that holds more
+//           k-mers than the leaf takes (2047) is put on a failed list and emits nothing; one more
 //           kernel counts exactly those buckets' records in a global hash table and appends them;
 //   tier 3  if even the spill list overflows, DevStatus::n_overflow is set and the caller recounts
 //           the whole batch with the global-hash-table path (count_hash.cu).
@@ -251,12 +253,12 @@ __global__ void __launch_bounds__(NT, PART_MINB) partition_kernel(ScanArgs a, Pa
 // ---------------------------------------------------------------------------------------------
 // per-bucket counting
 //
-// One CTA (256 threads) per bucket (about 1000 k-mers, at most 2047).  Most k-mers of a bucket occur once; proving
+// One CTA (128 threads) per bucket (about 1200 k-mers, at most 2047).  Most k-mers of a bucket occur once; proving
 // that is much cheaper than inserting them into an exact table, so the table only sees the rest:
 //   stage  : the bucket's record region (contiguous in HBM) is brought to shared memory by the TMA engine
 //            (cp.async.bulk + mbarrier); the copy for bucket i+1 is issued while bucket i is being emitted.
 //   expand : k-mer j of the bucket -> 16-bit descriptor (staged record << 4 | window) via a block-wide prefix sum of
-//            the record lengths, so that every later phase works on single k-mers, 8 per thread, all lanes busy.
+//            the record lengths, so that every later phase works on single k-mers, ~10 per thread, all lanes busy.
 //   mark   : every k-mer sets bit hash(k-mer) of bitmap A (atom.or with return); whoever finds the bit already set
 //            sets the same bit of bitmap B.                                                        -- barrier --
 //   sort   : a k-mer whose B bit is clear is the ONLY k-mer of the bucket in its cell: it is unique, count 1.

@@ -44,7 +44,7 @@ void launch_hash_compact(const DeviceInfo& di, const kmer_count_pair* d_slots, u
 
 // count_part.cu --------------------------------------------------------------------------------
 struct PartitionPlan {
-    uint32_t n_buckets;   // buckets the k-mers are spread over (about 2400 k-mers each)
+    uint32_t n_buckets;   // buckets the k-mers are spread over (about 1200 k-mers each)
     uint32_t cap;         // records a bucket region holds
     int w;                // m-mers per minimizer window (4, 8 or 16)
     int m;                // m-mer length (<= 16)
