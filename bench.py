@@ -466,15 +466,22 @@ def main():
         else:
             # sharded e2e: every rank copies its rows from pinned host memory, counts with the all-to-all, and reads
             # its share of the (k-mer,count) table back into pinned host memory
-            h_pairs = torch.empty((cap, 2), dtype=torch.int64).pin_memory()
+            # (split result format: groups with count 1 as bare 8-byte codes, the rest as 16-byte pairs)
+            h_pairs = torch.empty((cap // 2 + (1 << 20), 2), dtype=torch.int64).pin_memory()
+            h_uniq = torch.empty(cap, dtype=torch.int64).pin_memory()
+            d_uniq = torch.empty(cap, dtype=torch.int64, device="cuda")
+            d2h_bytes = [0]
 
             def e2e_step():
                 d_seq.copy_(h_seq, non_blocking=True)
                 d_off.copy_(h_off, non_blocking=True)
-                nd, nk_, _ = sharder.count(d_seq, n_bases, d_off, n_rows, K, d_pairs, total_kmers=total_kmers)
+                nd, nk_, info = sharder.count(d_seq, n_bases, d_off, n_rows, K, d_pairs, total_kmers=total_kmers, d_uniq=d_uniq)
+                nu = info["n_unique"]
                 h_pairs[:nd].copy_(d_pairs[:nd], non_blocking=True)
+                h_uniq[:nu].copy_(d_uniq[:nu], non_blocking=True)
                 torch.cuda.synchronize()
-                return nd, int(h_pairs[0, 1])
+                d2h_bytes[0] = 16 * nd + 8 * nu
+                return nd + nu, int(h_uniq[0]) if nu else 0
 
             e2e_steps = max(1, min(args.steps, 3))
             for _ in range(2):
@@ -487,10 +494,12 @@ def main():
             dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             dt = float(dt.item())
+            d2h_sum = torch.tensor([d2h_bytes[0]], dtype=torch.int64, device="cuda")
+            dist.all_reduce(d2h_sum)
             e2e = {"value": total_kmers * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": (n_bases + 8 * (n_rows + 1)) * world,
-                   "d2h_bytes_per_step": 16 * n_distinct_total, "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
-                   "api": "ShardedCounter.count per rank: pinned host rows -> HBM, partition + NCCL all-to-all + bucket count, "
-                          "(k-mer,count) shares -> pinned host"}
+                   "d2h_bytes_per_step": int(d2h_sum.item()), "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
+                   "api": "ShardedCounter.count per rank: pinned host rows -> HBM, partition + NCCL all-to-all + refine + bucket count, "
+                          "this rank's share of the table (split format: bare codes + pairs) -> pinned host"}
 
     # ---------------------------------------------------------------- CPU baseline beside it (rank 0, bounded sample)
     cpu = None

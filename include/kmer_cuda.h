@@ -253,6 +253,10 @@ int kmer_cuda_dev_shard_partition(kmer_cuda_ctx *ctx, const char *d_seq, uint64_
 int kmer_cuda_dev_shard_count(kmer_cuda_ctx *ctx, const kmer_shard_plan *plan, const void *d_recv_recs,
 							  const uint64_t *d_recv_fill, kmer_count_pair *d_pairs, uint64_t pairs_capacity,
 							  void *stream);
+/* The same with this rank's share in the split result format (kmer_cuda_dev_count_split). */
+int kmer_cuda_dev_shard_count_split(kmer_cuda_ctx *ctx, const kmer_shard_plan *plan, const void *d_recv_recs,
+									const uint64_t *d_recv_fill, uint64_t *d_uniq, uint64_t uniq_capacity,
+									kmer_count_pair *d_pairs, uint64_t pairs_capacity, void *stream);
 /* k <= 13: the dense 4^k table of uint64 counters of this rank's rows (to be summed across ranks),
  * and the emission of the bins owned by `rank` (bin % n_ranks == rank) of a summed table. */
 int kmer_cuda_dev_dense_table(kmer_cuda_ctx *ctx, const char *d_seq, uint64_t n_bases, const uint64_t *d_row_off,

@@ -39,7 +39,7 @@ ABI_SYMBOLS = [
     "kmer_cuda_submit_encode", "kmer_cuda_dev_extract", "kmer_cuda_dev_count", "kmer_cuda_dev_match",
     "kmer_cuda_dev_decode", "kmer_cuda_dev_finish", "kmer_cuda_set_profiling", "kmer_cuda_get_phases",
     "kmer_cuda_shard_plan", "kmer_cuda_dev_shard_partition", "kmer_cuda_dev_shard_count", "kmer_cuda_dev_dense_table",
-    "kmer_cuda_dev_dense_emit", "kmer_cuda_submit_count_split", "kmer_cuda_dev_count_split", "kmer_cuda_submit_count_packed", "kmer_cuda_shard_plan_chunked",
+    "kmer_cuda_dev_dense_emit", "kmer_cuda_submit_count_split", "kmer_cuda_dev_count_split", "kmer_cuda_submit_count_packed", "kmer_cuda_shard_plan_chunked", "kmer_cuda_dev_shard_count_split",
 ]
 
 
@@ -107,6 +107,7 @@ def load_library(path: Path = LIB_PATH) -> C.CDLL:
     L.kmer_cuda_shard_plan_chunked.argtypes = [u64, i32, C.c_uint32, C.c_uint32, C.POINTER(KmerShardPlan)]
     L.kmer_cuda_dev_shard_partition.argtypes = [vp, vp, u64, vp, u64, C.POINTER(KmerShardPlan), vp, vp, vp]
     L.kmer_cuda_dev_shard_count.argtypes = [vp, C.POINTER(KmerShardPlan), vp, vp, vp, u64, vp]
+    L.kmer_cuda_dev_shard_count_split.argtypes = [vp, C.POINTER(KmerShardPlan), vp, vp, vp, u64, vp, u64, vp]
     L.kmer_cuda_dev_dense_table.argtypes = [vp, vp, u64, vp, u64, i32, vp, vp]
     L.kmer_cuda_dev_dense_emit.argtypes = [vp, vp, i32, C.c_uint32, C.c_uint32, vp, u64, vp]
     return L
@@ -340,6 +341,11 @@ class KmerCuda:
     def dev_shard_count(self, plan: KmerShardPlan, d_recv_recs, d_recv_fill, d_pairs, stream=None):
         self._check(self.lib.kmer_cuda_dev_shard_count(self.ctx, C.byref(plan), d_recv_recs.data_ptr(), d_recv_fill.data_ptr(),
                                                        d_pairs.data_ptr(), d_pairs.numel() // 2, self._stream_ptr(stream)))
+
+    def dev_shard_count_split(self, plan: KmerShardPlan, d_recv_recs, d_recv_fill, d_uniq, d_pairs, stream=None):
+        self._check(self.lib.kmer_cuda_dev_shard_count_split(self.ctx, C.byref(plan), d_recv_recs.data_ptr(), d_recv_fill.data_ptr(),
+                                                             d_uniq.data_ptr(), d_uniq.numel(), d_pairs.data_ptr(), d_pairs.numel() // 2,
+                                                             self._stream_ptr(stream)))
 
     def dev_dense_table(self, d_seq, n_bases: int, d_off, n_rows: int, k: int, d_table, stream=None):
         self._check(self.lib.kmer_cuda_dev_dense_table(self.ctx, d_seq.data_ptr(), n_bases, d_off.data_ptr(), n_rows, k,

@@ -700,6 +700,7 @@ extern "C" int kmer_cuda_dev_finish(kmer_cuda_ctx* c, void* stream, kmer_dev_res
             result->n_kmers = s.n_kmers;
             result->n_distinct = s.n_distinct;
             result->n_tier2 = c->last_tier2;
+            result->n_unique = s.n_unique;
         }
     } else if (op == OP_ENCODE) {
         if (s.bad_char_pos != kNoError) return ref_error(&c->err, KMER_ERR_INVALID_DNA, (int64_t)s.bad_char_pos);
@@ -800,9 +801,9 @@ extern "C" int kmer_cuda_dev_shard_partition(kmer_cuda_ctx* c, const char* d_seq
     return KMER_OK;
 }
 
-extern "C" int kmer_cuda_dev_shard_count(kmer_cuda_ctx* c, const kmer_shard_plan* sp, const void* d_recv_recs,
-                                         const uint64_t* d_recv_fill, kmer_count_pair* d_pairs, uint64_t pairs_capacity,
-                                         void* stream) {
+static int dev_shard_count_impl(kmer_cuda_ctx* c, const kmer_shard_plan* sp, const void* d_recv_recs, const uint64_t* d_recv_fill,
+                                uint64_t* d_uniq, uint64_t uniq_capacity, kmer_count_pair* d_pairs, uint64_t pairs_capacity,
+                                void* stream) {
     if (!c || !sp) return KMER_ERR_BAD_ARGUMENT;
     cudaStream_t st = pick_stream(c, stream);
     int rc = begin_op(c, st);
@@ -824,7 +825,7 @@ extern "C" int kmer_cuda_dev_shard_count(kmer_cuda_ctx* c, const kmer_shard_plan
                   d_recv_recs, (unsigned long long*)c->fill.p, c->recs.p, c->spill.p, c->d_status, st);
     mark(c, st, "refine");
     launch_bucket_count(c->di, plan, k, 1, (const unsigned long long*)c->fill.p, c->recs.p, (uint32_t*)c->failed.p, d_pairs,
-                        pairs_capacity, nullptr, 0, c->d_status, st);
+                        pairs_capacity, d_uniq, d_uniq ? uniq_capacity : 0, c->d_status, st);
     mark(c, st, "bucket_count");
     c->launches += 2;
     CU(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, st), "D2H status");
@@ -850,6 +851,19 @@ extern "C" int kmer_cuda_dev_shard_count(kmer_cuda_ctx* c, const kmer_shard_plan
     }
     CU(cudaGetLastError(), "shard count launch");
     return KMER_OK;
+}
+
+extern "C" int kmer_cuda_dev_shard_count(kmer_cuda_ctx* c, const kmer_shard_plan* sp, const void* d_recv_recs,
+                                         const uint64_t* d_recv_fill, kmer_count_pair* d_pairs, uint64_t pairs_capacity,
+                                         void* stream) {
+    return dev_shard_count_impl(c, sp, d_recv_recs, d_recv_fill, nullptr, 0, d_pairs, pairs_capacity, stream);
+}
+
+extern "C" int kmer_cuda_dev_shard_count_split(kmer_cuda_ctx* c, const kmer_shard_plan* sp, const void* d_recv_recs,
+                                               const uint64_t* d_recv_fill, uint64_t* d_uniq, uint64_t uniq_capacity,
+                                               kmer_count_pair* d_pairs, uint64_t pairs_capacity, void* stream) {
+    if (c && !d_uniq && uniq_capacity) return bad_arg(c, "d_uniq");
+    return dev_shard_count_impl(c, sp, d_recv_recs, d_recv_fill, d_uniq, uniq_capacity, d_pairs, pairs_capacity, stream);
 }
 
 extern "C" int kmer_cuda_dev_dense_table(kmer_cuda_ctx* c, const char* d_seq, uint64_t n_bases, const uint64_t* d_row_off,

@@ -78,10 +78,12 @@ class ShardedCounter:
             raise RuntimeError("sharded count aborted: another rank reported an input error")
 
     # ------------------------------------------------------------------ the operation
-    def count(self, d_seq, n_bases: int, d_off, n_rows: int, k: int, d_pairs, total_kmers: int | None = None):
+    def count(self, d_seq, n_bases: int, d_off, n_rows: int, k: int, d_pairs, total_kmers: int | None = None, d_uniq=None):
         """Counts this rank's rows together with all other ranks' rows.
 
         d_pairs: int64 [capacity, 2] on this rank; returns (n_distinct_here, n_kmers_counted_here, info dict).
+        d_uniq (int64 [capacity], k >= 14): split result format -- groups with count 1 come back as bare codes in d_uniq
+        (info["n_unique"] of them), n_distinct_here then counts the pairs only.
         Collective: every rank of the group must call it with the same k."""
         eng = self.eng
         local_kmers = eng.max_kmers(n_bases, n_rows, k)
@@ -161,14 +163,18 @@ class ShardedCounter:
             self.last_exchange_bytes = int(recs_bytes + fill_words * 8) * chunks * (self.world - 1) // self.world
         else:
             self.last_exchange_bytes = 0
-        eng.dev_shard_count(plan, recv_recs, recv_fill, d_pairs)
+        if d_uniq is not None:
+            eng.dev_shard_count_split(plan, recv_recs, recv_fill, d_uniq, d_pairs)
+        else:
+            eng.dev_shard_count(plan, recv_recs, recv_fill, d_pairs)
         r = eng.dev_finish()
         phases += self._phases()
         self.last_phases = phases
         counted = self._allreduce_int(int(r.n_kmers))
         if counted != total_kmers:
             raise RuntimeError(f"sharded count lost k-mers: counted {counted}, expected {total_kmers}")
-        return int(r.n_distinct), int(r.n_kmers), {"tier2_kmers": int(r.n_tier2), "plan": plan}
+        return int(r.n_distinct), int(r.n_kmers), {"tier2_kmers": int(r.n_tier2), "plan": plan,
+                                                  "n_unique": int(getattr(r, "n_unique", 0))}
 
     def _count_dense(self, d_seq, n_bases, d_off, n_rows, k, d_pairs, total_kmers):
         eng = self.eng
