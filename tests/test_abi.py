@@ -101,3 +101,21 @@ def test_shard_plan_window_follows_job_size(lib):
     assert w(9_700_000_000, 31) == (16, 16)     # C3: already 16-base m-mers
     assert w(980_000_000, 27) == (12, 16)       # W=16 would leave 12-base m-mers
     assert w(980_000_000, 17)[0] == 4
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the reference's C functions on the host cores) needs no GPU: one JSON line with the
+    keys the driver reads; under torchrun every rank but 0 stays silent."""
+    import json, os, subprocess, sys
+    cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-reads", "200"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "kmers_counted_per_sec_k21" and d["unit"] == "k-mers/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["cpu_baseline"]["kind"] in ("reference", "port")
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert out.returncode == 0 and not [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
