@@ -39,7 +39,7 @@ struct kmer_cuda_ctx {
     DevStatus* d_status = nullptr;
     DevStatus* h_status = nullptr;  // pinned
     // device workspaces, grown on demand and kept between calls
-    Buf seq, off, mask, tile_row, table, consts, ops, codes, pairs, bits, hits, lens, text, fill, recs, spill, failed;
+    Buf seq, off, mask, tile_row, table, consts, ops, codes, pairs, bits, hits, lens, text, fill, recs, spill, failed, seg, segfill;
     uint64_t last_tier2 = 0;      // k-mers counted by the tier-2 kernel in the last count
     uint64_t last_overflow = 0;   // k-mers the partition counter could not place (batch was recounted)
     std::vector<PinnedBuf> pinned;
@@ -338,7 +338,7 @@ extern "C" void kmer_cuda_shutdown(kmer_cuda_ctx* c) {
     cudaSetDevice(c->di.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     Buf* all[] = {&c->seq, &c->off, &c->mask, &c->tile_row, &c->table, &c->consts, &c->ops,
-                  &c->codes, &c->pairs, &c->bits, &c->hits, &c->lens, &c->text, &c->fill, &c->recs, &c->spill, &c->failed};
+                  &c->codes, &c->pairs, &c->bits, &c->hits, &c->lens, &c->text, &c->fill, &c->recs, &c->spill, &c->failed, &c->seg, &c->segfill};
     for (Buf* b : all) buf_free(*b);
     for (auto& p : c->pinned) cudaFreeHost(p.p);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -489,15 +489,28 @@ static int dev_count_impl(kmer_cuda_ctx* c, const char* d_seq, uint64_t n_bases,
     if (algo == 3) {
         if (k < 14) return bad_arg(c, "minimizer-partition counting needs k >= 14");
         PartitionPlan plan = make_partition_plan(c->p_expected_kmers, k);
+        ScatterPlan sp{};
+        const bool two_pass = make_scatter_plan(c->di, n_bases, c->p_expected_kmers, plan, sp);
         rc = ws(c, c->fill, (size_t)plan.n_buckets * 8);
         if (!rc) rc = ws(c, c->recs, partition_record_bytes(plan));
         if (!rc) rc = ws(c, c->spill, partition_spill_bytes(plan));
         if (!rc) rc = ws(c, c->failed, (size_t)plan.n_buckets * 4);
+        if (!rc && two_pass) rc = ws(c, c->seg, scatter_seg_bytes(plan, sp));
+        if (!rc && two_pass) rc = ws(c, c->segfill, scatter_segfill_bytes(sp));
         if (rc) return rc;
         MarkArg ma{c, st};
-        launch_count_partition(c->di, a, plan, (unsigned long long*)c->fill.p, c->recs.p, c->spill.p, (uint32_t*)c->failed.p,
-                               d_pairs, pairs_capacity, d_uniq, uniq_capacity, st, mark_cb, &ma);
-        c->launches += 2;
+        if (two_pass) {
+            launch_scatter_refine(c->di, a, plan, sp, (uint32_t*)c->segfill.p, c->seg.p, (unsigned long long*)c->fill.p, c->recs.p,
+                                  c->spill.p, st, mark_cb, &ma);
+            launch_bucket_count(c->di, plan, k, (const unsigned long long*)c->fill.p, c->recs.p, c->spill.p, (uint32_t*)c->failed.p, d_pairs,
+                                pairs_capacity, d_uniq, uniq_capacity, c->d_status, st);
+            mark(c, st, "bucket_count");
+            c->launches += 3;
+        } else {
+            launch_count_partition(c->di, a, plan, (unsigned long long*)c->fill.p, c->recs.p, c->spill.p, (uint32_t*)c->failed.p,
+                                   d_pairs, pairs_capacity, d_uniq, uniq_capacity, st, mark_cb, &ma);
+            c->launches += 2;
+        }
         // Did everything fit?  (One host round trip; skewed input needs tier 2 or a full recount.)
         CU(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, st), "D2H status");
         CU(cudaStreamSynchronize(st), "stream sync");
@@ -511,7 +524,7 @@ static int dev_count_impl(kmer_cuda_ctx* c, const char* d_seq, uint64_t n_bases,
             algo = 2;
         } else {
             if (hs.n_failed || hs.n_spill) {         // tier 2: only the buckets that did not fit
-                uint64_t n_slots = next_pow2(std::max<uint64_t>(1024, hs.failed_kmers * 2));
+                uint64_t n_slots = next_pow2(std::max<uint64_t>(1024, (hs.failed_kmers + hs.n_spill * 16) * 2));
                 rc = ws(c, c->table, n_slots * sizeof(kmer_count_pair));
                 if (rc) return rc;
                 launch_hash_clear((kmer_count_pair*)c->table.p, n_slots, st);
@@ -824,7 +837,7 @@ static int dev_shard_count_impl(kmer_cuda_ctx* c, const kmer_shard_plan* sp, con
     launch_refine(c->di, plan, k, n_src, sp->buckets_per_rank, sp->cap, (const unsigned long long*)d_recv_fill,
                   d_recv_recs, (unsigned long long*)c->fill.p, c->recs.p, c->spill.p, c->d_status, st);
     mark(c, st, "refine");
-    launch_bucket_count(c->di, plan, k, 1, (const unsigned long long*)c->fill.p, c->recs.p, (uint32_t*)c->failed.p, d_pairs,
+    launch_bucket_count(c->di, plan, k, (const unsigned long long*)c->fill.p, c->recs.p, c->spill.p, (uint32_t*)c->failed.p, d_pairs,
                         pairs_capacity, d_uniq, d_uniq ? uniq_capacity : 0, c->d_status, st);
     mark(c, st, "bucket_count");
     c->launches += 2;

@@ -24,6 +24,7 @@
 //           kernel counts exactly those buckets' records in a global hash table and appends them;
 //   tier 3  if even the spill list overflows, DevStatus::n_overflow is set and the caller recounts
 //           the whole batch with the global-hash-table path (count_hash.cu).
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 
@@ -31,7 +32,7 @@
 
 namespace kmer {
 
-constexpr int LEAF_SLOTS = 2048;          // shared-memory table slots per bucket
+constexpr int LEAF_SLOTS = 1024;          // shared-memory table slots per bucket (exact counts of the repeated k-mers)
 #ifndef LEAF_THREADS_N
 #define LEAF_THREADS_N 128
 #endif
@@ -253,36 +254,46 @@ __global__ void __launch_bounds__(NT, PART_MINB) partition_kernel(ScanArgs a, Pa
 // ---------------------------------------------------------------------------------------------
 // per-bucket counting
 //
-// One CTA (128 threads) per bucket (about 1200 k-mers, at most 2047).  Most k-mers of a bucket occur once; proving
-// that is much cheaper than inserting them into an exact table, so the table only sees the rest:
-//   stage  : the bucket's record region (contiguous in HBM) is brought to shared memory by the TMA engine
-//            (cp.async.bulk + mbarrier); the copy for bucket i+1 is issued while bucket i is being emitted.
-//   expand : k-mer j of the bucket -> 16-bit descriptor (staged record << 4 | window) via a block-wide prefix sum of
-//            the record lengths, so that every later phase works on single k-mers, ~10 per thread, all lanes busy.
-//   mark   : every k-mer sets bit hash(k-mer) of bitmap A (atom.or with return); whoever finds the bit already set
-//            sets the same bit of bitmap B.                                                        -- barrier --
-//   sort   : a k-mer whose B bit is clear is the ONLY k-mer of the bucket in its cell: it is unique, count 1.
-//            The others (true repeats and the ~3 % that merely share a cell) are listed in a compact "slow list"
-//            (which reuses bitmap A's storage: A is dead after the barrier).                        -- barrier --
-//   count  : the slow list is spread evenly over the warps and counted exactly in a 2048-slot open-addressing
-//            table: one 64-bit shared atomicCAS per lane per iteration (double hashing); a lane whose key is placed
-//            or found takes the warp's next k-mer (ballot + popc on a warp-uniform cursor: no atomics, no idle
-//            lanes).  k <= 26: the count lives in the 12 spare top bits of the key word; k >= 27: separate 32-bit
-//            counters.  The slots a warp claims are listed in place of its consumed slow-list entries.
-//                                                                                                   -- barrier --
-//   emit   : unique k-mers are written straight from their descriptors, table entries from the claimed-slot lists
-//            (which also resets the table); both as coalesced 16-byte (k-mer, count) pairs.  Output ranges: one
-//            global atomicAdd per bucket for the unique k-mers, one per warp that claimed table slots.
-// A bucket holds fewer k-mers than the table has slots, so a probe sequence (odd step) always terminates; buckets
-// above LEAF_MAX_KMERS, or whose region overflowed in the partition pass, go to tier 2 up front.
+// One CTA (128 threads) per bucket (about 1200 k-mers, at most LEAF_MAX_KMERS).  Most k-mers of a bucket occur once;
+// proving that is much cheaper than inserting them into an exact table, so the table only sees the rest:
+//   stage   : the bucket's record region (contiguous in HBM) is brought to shared memory by the TMA engine
+//             (cp.async.bulk + mbarrier), double buffered: the copy for bucket i+1 runs behind bucket i.
+//   index   : thread t takes the records [t*c, t*c+c) (c = ceil(records / 128)); a warp-wide prefix sum of their lengths
+//             numbers the bucket's k-mers ("key index").  Every warp owns a range of key indices that starts on a multiple
+//             of 32 (one shared atomicAdd per warp hands it out), so a 32-key block never mixes two warps' records.
+//             Per record the first key index goes to P[], a start bit to a bit mask over the key indices, and the record
+//             that covers the first key of a 32-key block to blk[].                               -- barrier (E) --
+//   mark    : thread t owns key indices t, t+128, ...: all lanes of a warp look at the SAME 32-key block, so
+//             record(i) = blk[block] + popc(start bits of the block up to the lane) -- one POPC, two broadcast loads --
+//             and the k-mer is two shifts of that record.  No per-k-mer array exists in shared memory: the keys live in
+//             REGISTERS from here to the emission, every lane busy whatever the record lengths are.  Each k-mer sets bit
+//             hash(k-mer) of bitmap A (atom.or with return); whoever finds the bit already set sets the same bit of
+//             bitmap B.                                                                          -- barrier (M) --
+//   classify: a k-mer whose B bit is clear is the ONLY k-mer of the bucket in its cell: it is unique, count 1.
+//             The others (true repeats and the ~4 % that merely share a cell) put their key index on the "slow list".
+//                                                                                                -- barrier (L) --
+//   count   : the slow list is spread evenly over the warps and counted exactly in a 1024-slot open-addressing
+//             table: one 64-bit shared atomicCAS per lane per iteration (double hashing); a lane whose key is placed
+//             or found takes the warp's next k-mer (ballot + popc on a warp-uniform cursor: no atomics, no idle
+//             lanes).  k <= 26: the count lives in the 12 spare top bits of the key word; k >= 27: separate 32-bit
+//             counters.  The slots a warp claims are listed in place of its consumed slow-list entries.  A key that
+//             finds the table full (more than 1023 distinct repeated k-mers in one bucket) is handed to tier 2 as a
+//             one-k-mer spill record.                                                            -- barrier (B) --
+//   emit    : unique k-mers straight from the registers, table entries from the claimed-slot lists (which also
+//             resets the table); both as coalesced 16-byte (k-mer, count) pairs (or bare codes in the split format).
+//             Output ranges: one global atomicAdd per bucket for the unique k-mers, one per warp that claimed slots.
+// Buckets above LEAF_MAX_KMERS, or whose region overflowed in the partition pass, go to tier 2 up front.
 // Shared memory is addressed through explicit 32-bit shared addresses (ld/st/atom.shared PTX).
 
-constexpr int LEAF_KPT = 2048 / LEAF_THREADS;                        // k-mers per thread
-constexpr uint32_t LEAF_MAX_KMERS = LEAF_KPT * LEAF_THREADS - 1;    // 2047 < LEAF_SLOTS: the table can never fill up
-constexpr int LEAF_CELLS = 32768;                                    // bits per filter bitmap
+constexpr int LEAF_KPT = 16;                                          // key indices per thread
+constexpr uint32_t LEAF_KEYS = LEAF_KPT * LEAF_THREADS;              // 2048 key indices
 constexpr int LEAF_WARPS = LEAF_THREADS / 32;
-static_assert(LEAF_MAX_KMERS < LEAF_SLOTS, "a probe sequence must always find a free slot");
-static_assert(LEAF_CELLS / 8 >= 2 * (LEAF_MAX_KMERS + 1), "the slow list lives in bitmap A");
+constexpr uint32_t LEAF_MAX_KMERS = LEAF_KEYS - 32 * LEAF_WARPS;     // 1920: every warp's index range is padded to 32
+constexpr int LEAF_CELLS = 32768;                                    // bits per filter bitmap
+constexpr int LEAF_BLOCKS = LEAF_KEYS / 32;                          // 32-key blocks
+#ifndef LEAF_MINB
+#define LEAF_MINB 7
+#endif
 
 __device__ __forceinline__ unsigned long long atoms_cas64(uint32_t a, unsigned long long cmp, unsigned long long val) {
     unsigned long long old;
@@ -350,12 +361,9 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
-__device__ __forceinline__ uint32_t leaf_hash(uint64_t key) {
-    uint32_t h = ((uint32_t)key * 0x9E3779B1u) ^ ((uint32_t)(key >> 32) * 0x85EBCA6Bu);
-    h ^= h >> 15;
-    h *= 0x2C1B3C6Du;
-    h ^= h >> 13;
-    return h;
+// cell of the filter bitmaps (15 bits) and, decorrelated from it, the slot hash of the exact table
+__device__ __forceinline__ uint32_t leaf_mix(uint64_t key) {
+    return (uint32_t)key * 0x9E3779B1u + (uint32_t)(key >> 32) * 0x85EBCA6Bu;
 }
 
 struct BucketInfo {
@@ -374,12 +382,13 @@ __device__ __forceinline__ BucketInfo bucket_info(const unsigned long long* __re
 }
 
 template <int RECW>
-__global__ void __launch_bounds__(LEAF_THREADS, 1280 / LEAF_THREADS) bucket_count_kernel(PartitionPlan plan, int k,
+__global__ void __launch_bounds__(LEAF_THREADS, LEAF_MINB) bucket_count_kernel(PartitionPlan plan, int k,
                                                                        const unsigned long long* __restrict__ fill,
                                                                        const Rec<RECW>* __restrict__ recs,
                                                                        kmer_count_pair* __restrict__ out, uint64_t capacity,
                                                                        uint64_t* __restrict__ out_u, uint64_t capacity_u,
-                                                                       uint32_t* __restrict__ failed_ids, DevStatus* status) {
+                                                                       uint32_t* __restrict__ failed_ids, Rec<RECW>* __restrict__ spill,
+                                                                       DevStatus* status) {
     constexpr bool PACKED = RECW == 1;                        // count in bits 63..52 of the key word (k <= 26)
     constexpr uint32_t RECB = RECW * 8;
     constexpr uint64_t KEYMASK = PACKED ? ((1ull << 52) - 1ull) : ~0ull;
@@ -387,26 +396,33 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1280 / LEAF_THREADS) bucket_coun
     uint32_t tbl_s = smem_u32(leaf_dyn);                                       // u64[LEAF_SLOTS]
     asm volatile("" : "+r"(tbl_s));                                            // keep it in a register (no rematerialisation)
     const uint32_t cnt_s = tbl_s + LEAF_SLOTS * 8;                             // u32[LEAF_SLOTS]   (k >= 27 only)
-    const uint32_t bma_s = cnt_s + (PACKED ? 0 : LEAF_SLOTS * 4);             // bitmap A / slow list (u16 k-mer indices)
+    const uint32_t bma_s = cnt_s + (PACKED ? 0 : LEAF_SLOTS * 4);             // bitmap A
     const uint32_t bmb_s = bma_s + LEAF_CELLS / 8;                             // bitmap B
-    const uint32_t desc_s = bmb_s + LEAF_CELLS / 8;                            // u16[LEAF_MAX_KMERS + 1] k-mer descriptors
-    const uint32_t rec0_s = desc_s + (LEAF_MAX_KMERS + 1) * 2;                 // staged records, two buffers
+    const uint32_t slow_s = bmb_s + LEAF_CELLS / 8;                            // u16[LEAF_KEYS]: slow list (key indices), then claimed slots
+    const uint32_t p_s = slow_s + LEAF_KEYS * 2;                               // u16[cap + 2]: first key index of every record
+    const uint32_t rec0_s = p_s + ((((uint32_t)plan.cap + 2u) * 2u + 15u) & ~15u);   // staged records, two buffers
     const uint32_t rec_stride = (((uint32_t)plan.cap + 2u) * RECB + 15u) & ~15u;
     __shared__ __align__(8) uint64_t s_mbar;
-    __shared__ uint32_t s_wtot[2][LEAF_WARPS];
+    __shared__ uint32_t s_mask[2][LEAF_BLOCKS];                                // per bucket parity: bit i&31 of word i>>5: a record starts at key index i
+    __shared__ uint32_t s_blk[LEAF_BLOCKS];                                    // record that covers key index 32*block
+    __shared__ uint32_t s_kcur;                                                // index phase: next free key index (a multiple of 32)
     __shared__ uint32_t s_nuniq[2], s_nslow[2];                                // per bucket parity
     __shared__ unsigned long long s_obase[2];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint32_t lane_lt = (1u << lane) - 1u;
+    const uint32_t lane_starts = (2u << lane) - 2u;                            // start bits 1..lane of a 32-key block
     const int kshift = 64 - 2 * k;
     const uint32_t mbar_s = smem_u32(&s_mbar);
+    const uint32_t kcur_s = smem_u32(&s_kcur);
+    const uint32_t blk_s = smem_u32(s_blk);
     unsigned long long special_total = 0, kmers_total = 0;
     for (int i = t; i < LEAF_SLOTS / 2; i += LEAF_THREADS) sts128(tbl_s + 16 * i, ~0u, ~0u, ~0u, ~0u);
     if (!PACKED)
         for (int i = t; i < LEAF_SLOTS / 4; i += LEAF_THREADS) sts128(cnt_s + 16 * i, 0u, 0u, 0u, 0u);
     for (int i = t; i < 2 * LEAF_CELLS / 128; i += LEAF_THREADS) sts128(bma_s + 16 * i, 0u, 0u, 0u, 0u);   // A and B
+    if (t < LEAF_BLOCKS) { s_mask[0][t] = 0; s_mask[1][t] = 0; }
     if (t < 2) { s_nuniq[t] = 0; s_nslow[t] = 0; }
-    if (t == 0) { mbar_init(&s_mbar, 1); mbar_fence_init(); }
+    if (t == 0) { s_kcur = 0; mbar_init(&s_mbar, 1); mbar_fence_init(); }
     __syncthreads();
 
     // thread 0: start the bulk copy of bucket b's records (padded to 16 bytes; read once: L2 evict-first)
@@ -432,7 +448,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1280 / LEAF_THREADS) bucket_coun
         const uint32_t b_next = b + gridDim.x;
         BucketInfo nxt;
         nxt.nrec = 0; nxt.nk = 0; nxt.overflow = false;
-        if (b_next < plan.n_buckets) nxt = bucket_info(fill, plan, b_next);   // in flight during the probe phase
+        if (b_next < plan.n_buckets) nxt = bucket_info(fill, plan, b_next);   // in flight during the index phase
         if (!cur.usable()) {                                            // uniform across the CTA
             if (t == 0) {
                 if (cur.nrec) {                                         // does not fit on chip: tier 2
@@ -448,66 +464,63 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1280 / LEAF_THREADS) bucket_coun
         mbar_wait_s(mbar_s, phase);
         phase ^= 1u;
         const uint32_t rec_s = rec0_s + rb * rec_stride;
-        // ---- expand: k-mer j of the bucket -> descriptor (staged record << 4 | window).  Thread t lists the k-mers of
-        //      records t, t+256, ...; the block-wide prefix sum of the record lengths gives their positions.
-        const uint32_t nrec = cur.nrec;
-        uint32_t mysum = 0;
-        for (uint32_t r = t; r < nrec; r += LEAF_THREADS) {
-            const uint32_t pos = r;
-            mysum += (RECW == 1 ? (lds32(rec_s + 8 * pos) & 15u) : (lds32(rec_s + 16 * pos + 8) & 63u)) + 1;
-        }
-        uint32_t incl = mysum;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += n;
-        }
-        if (lane == 31) s_wtot[par][warp] = incl;
-        __syncthreads();                                                // (S) also: the previous bucket is fully emitted
-        // bitmap A doubled as the previous bucket's slow list / claimed-slot lists: clear it now; the other record
-        // buffer is free as well: start the next bucket's copy
-        for (int i = t; i < LEAF_CELLS / 128; i += LEAF_THREADS) sts128(bma_s + 16 * i, 0u, 0u, 0u, 0u);
-        if (t == 0 && nxt.usable()) issue(b_next, rb ^ 1u);
-        uint32_t kbase = incl - mysum, nk = 0;
-#pragma unroll
-        for (int q = 0; q < LEAF_WARPS; q++) {
-            const uint32_t v = s_wtot[par][q];
-            if (q < warp) kbase += v;
-            nk += v;
-        }
-        for (uint32_t r = t; r < nrec; r += LEAF_THREADS) {
-            const uint32_t pos = r;
-            const uint32_t L = (RECW == 1 ? (lds32(rec_s + 8 * pos) & 15u) : (lds32(rec_s + 16 * pos + 8) & 63u)) + 1;
-            for (uint32_t o = 0; o < L; o++) sts16(desc_s + 2 * (kbase + o), (pos << 4) | o);
-            kbase += L;
-        }
-        __syncthreads();                                                // (E) descriptors complete, bitmap A clear
-        auto key_at = [&](uint32_t j) -> uint64_t {                     // k-mer j of the bucket
-            const uint32_t d = lds16(desc_s + 2 * j);
-            const uint32_t o2 = 2 * (d & 15u);
-            if (RECW == 1) return (lds64(rec_s + 8 * (d >> 4)) << o2) >> kshift;
-            unsigned long long hi, lo;
-            lds128(rec_s + 16 * (d >> 4), hi, lo);
-            return (o2 ? ((hi << o2) | (lo >> (64 - o2))) : hi) >> kshift;
+        const uint32_t mask_s = smem_u32(s_mask[par]);
+        auto rec_len = [&](uint32_t r) -> uint32_t {
+            return RECW == 1 ? (lds32(rec_s + 8 * r) & 15u) + 1 : (lds32(rec_s + 16 * r + 8) & 63u) + 1;
         };
-        // ---- mark: thread t owns k-mers t, t+256, ...
-        uint32_t valid = 0, multi = 0, special = 0;                     // bit i: k-mer t + 256 i exists / shares its cell
-        uint32_t cells[LEAF_KPT / 2];                                   // its 15-bit cell, two per register
+        // window j of record r (the low length bits are shifted out: j + k <= 30 resp. 61 bases)
+        auto window = [&](uint32_t r, uint32_t j) -> uint64_t {
+            if (RECW == 1) return (lds64(rec_s + 8 * r) << (2 * j)) >> kshift;
+            unsigned long long hi, lo;
+            lds128(rec_s + 16 * r, hi, lo);
+            return (j ? ((hi << (2 * j)) | (lo >> (64 - 2 * j))) : hi) >> kshift;
+        };
+        // ---- index: thread t numbers the k-mers of records [t*c, t*c + c)
+        const uint32_t nrec = cur.nrec;
+        {
+            const uint32_t c = (nrec + LEAF_THREADS - 1) / LEAF_THREADS;
+            const uint32_t r0 = t * c, r1 = min(r0 + c, nrec);
+            uint32_t S = 0;
+            for (uint32_t r = r0; r < r1; r++) S += rec_len(r);
+            uint32_t incl = S;
 #pragma unroll
-        for (int i = 0; i < LEAF_KPT / 2; i++) cells[i] = 0;
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += n;
+            }
+            uint32_t base = 0;
+            if (lane == 31 && incl) base = atoms_add32(kcur_s, (incl + 31u) & ~31u);   // the warp's index range starts on a 32-key block
+            base = __shfl_sync(0xffffffffu, base, 31);
+            uint32_t p = base + incl - S;
+            for (uint32_t r = r0; r < r1; r++) {
+                const uint32_t L = rec_len(r), e = p + L - 1;
+                sts16(p_s + 2 * r, p);
+                reds_or32(mask_s + 4 * (p >> 5), 1u << (p & 31u));
+                if ((p & 31u) == 0 || (e >> 5) != (p >> 5)) sts32(blk_s + 4 * (e >> 5), r);   // covers the first key of block e>>5
+                p += L;
+            }
+        }
+        __syncthreads();                                                // (E) index complete; the other record buffer is free
+        const uint32_t nkeys = s_kcur;                                  // key indices handed out (padded per warp)
+        if (t == 0 && nxt.usable()) issue(b_next, rb ^ 1u);
+        // ---- mark: thread t owns key indices t, t+128, ...  (block = warp + 4 i, bit = lane)
+        uint64_t key[LEAF_KPT];
+        uint32_t valid = 0, multi = 0, special = 0;                     // bit i: key i exists / shares its cell
 #pragma unroll
         for (int i = 0; i < LEAF_KPT; i++) {
-            if (i * LEAF_THREADS >= nk) break;                          // uniform
-            const uint32_t j = t + i * LEAF_THREADS;
-            if (j < nk) {
-                const uint64_t key = key_at(j);
-                if (RECW == 2 && key == kEmpty) special++;              // k == 32, 't'*32: kept out of the tables
+            key[i] = 0;
+            if (i * LEAF_THREADS >= (int)nkeys) break;                  // uniform
+            const uint32_t blk = warp + LEAF_WARPS * i;
+            if (blk * 32u >= nkeys) break;                              // uniform per warp: the block was not handed out
+            const uint32_t r = lds32(blk_s + 4 * blk) + __popc(lds32(mask_s + 4 * blk) & lane_starts);
+            const uint32_t j = (uint32_t)(t + i * LEAF_THREADS) - lds16(p_s + 2 * r);
+            if (j < rec_len(r)) {                                       // not in the padding behind the warp's last record
+                key[i] = window(r, j);
+                if (RECW == 2 && key[i] == kEmpty) special++;           // k == 32, 't'*32: kept out of the tables
                 else {
-                    const uint32_t x = (uint32_t)key * 0x9E3779B1u + (uint32_t)(key >> 32) * 0x85EBCA6Bu;
-                    const uint32_t cell = x >> 17;
-                    cells[i >> 1] |= cell << (16 * (i & 1));
-                    const uint32_t bit = 1u << (cell & 31u), w = (cell >> 5) * 4;
                     valid |= 1u << i;
+                    const uint32_t cell = leaf_mix(key[i]) >> 17;
+                    const uint32_t bit = 1u << (cell & 31u), w = (cell >> 5) * 4;
                     if (atoms_or32(bma_s + w, bit) & bit) {
                         reds_or32(bmb_s + w, bit);
                         multi |= 1u << i;
@@ -515,33 +528,30 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1280 / LEAF_THREADS) bucket_coun
                 }
             }
         }
-        __syncthreads();                                                // (M) both bitmaps final; A is free from here on
-        // ---- sort: unique k-mers stay where they are, the others go to the slow list
+        __syncthreads();                                                // (M) both bitmaps final
+        if (t == 0) s_kcur = 0;
+        // ---- classify: unique k-mers stay in their registers, the others put their key index on the slow list
 #pragma unroll
         for (int i = 0; i < LEAF_KPT; i++) {
-            if (i * LEAF_THREADS >= nk) break;
-            if (((valid & ~multi) >> i) & 1u) {
-                const uint32_t cell = (cells[i >> 1] >> (16 * (i & 1))) & 0x7fffu;
-                if ((lds32(bmb_s + (cell >> 5) * 4) >> (cell & 31u)) & 1u) multi |= 1u << i;
+            if (i * LEAF_THREADS >= (int)nkeys) break;
+            if ((valid >> i) & 1u) {
+                bool slow = (multi >> i) & 1u;
+                if (!slow) {
+                    const uint32_t cell = leaf_mix(key[i]) >> 17;
+                    slow = (lds32(bmb_s + (cell >> 5) * 4) >> (cell & 31u)) & 1u;
+                }
+                if (slow) {
+                    multi |= 1u << i;
+                    sts16(slow_s + 2 * atoms_add32(smem_u32(&s_nslow[par]), 1u), t + i * LEAF_THREADS);
+                }
             }
         }
         const uint32_t uniq = valid & ~multi;
-        // the warp's unique k-mers get a contiguous share of the bucket's output; every lane that has slow k-mers
-        // takes its slow-list positions with one shared atomicAdd
+        // the warp's unique k-mers get a contiguous share of the bucket's output
         const uint32_t wuniq = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(uniq));
         uint32_t woff = 0;
         if (lane == 0 && wuniq) woff = atoms_add32(smem_u32(&s_nuniq[par]), wuniq);
         woff = __shfl_sync(0xffffffffu, woff, 0);
-        if (multi) {
-            uint32_t sb = atoms_add32(smem_u32(&s_nslow[par]), (uint32_t)__popc(multi));
-            uint32_t m2 = multi;
-            while (m2) {
-                const uint32_t i = __ffs(m2) - 1;
-                m2 &= m2 - 1;
-                sts16(bma_s + 2 * sb, t + i * LEAF_THREADS);
-                sb++;
-            }
-        }
         __syncthreads();                                                // (L) slow list complete
         const uint32_t ns = s_nslow[par];
         unsigned long long ubase = 0;
@@ -549,8 +559,8 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1280 / LEAF_THREADS) bucket_coun
             const uint32_t nu = s_nuniq[par];
             if (nu) ubase = atomicAdd(out_u ? &status->n_unique : &status->n_distinct, (unsigned long long)nu);   // consumed after the next barrier
         }
-        // bitmap B is dead: clear it for the next bucket
-        for (int i = t; i < LEAF_CELLS / 128; i += LEAF_THREADS) sts128(bmb_s + 16 * i, 0u, 0u, 0u, 0u);
+        // both bitmaps are dead: clear them for the next bucket
+        for (int i = t; i < 2 * LEAF_CELLS / 128; i += LEAF_THREADS) sts128(bma_s + 16 * i, 0u, 0u, 0u, 0u);
         // ---- count: the slow list is cut into one slice per warp, but never thinner than 32 entries (a warp pays for
         //      the probe loop whether 1 or 32 of its lanes are busy)
         const uint32_t slice = max(32u, (ns + LEAF_WARPS - 1) / LEAF_WARPS);
@@ -559,7 +569,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1280 / LEAF_THREADS) bucket_coun
         uint32_t nwin = 0;                                              // warp-uniform: slots this warp has claimed so far
         if (kb < end) {
             uint32_t next = kb, x = 0, tries = 0;
-            uint64_t key = 0;
+            uint64_t skey = 0;
             bool active = false;
             for (;;) {
                 const uint32_t m = __ballot_sync(0xffffffffu, !active);
@@ -567,33 +577,44 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1280 / LEAF_THREADS) bucket_coun
                     const uint32_t idx = next + __popc(m & lane_lt);
                     next += __popc(m);
                     if (!active && idx < end) {
-                        key = key_at(lds16(bma_s + 2 * idx));
-                        x = (uint32_t)key * 0x9E3779B1u + (uint32_t)(key >> 32) * 0x85EBCA6Bu;
-                        x *= 0x2C1B3C6Du;                               // decorrelate from the cell index
+                        const uint32_t ki = lds16(slow_s + 2 * idx), blk = ki >> 5;
+                        const uint32_t r = lds32(blk_s + 4 * blk) + __popc(lds32(mask_s + 4 * blk) & ((2u << (ki & 31u)) - 2u));
+                        skey = window(r, ki - lds16(p_s + 2 * r));
+                        x = leaf_mix(skey) * 0x2C1B3C6Du;               // decorrelate from the cell index
                         tries = 0;
                         active = true;
                     }
                 }
                 if (__all_sync(0xffffffffu, !active)) break;            // the warp's share is exhausted
                 const uint32_t step = (x >> 6) | 1u;                    // double hashing: an odd step visits every slot
-                const uint32_t h = ((x >> 21) + tries * step) & (LEAF_SLOTS - 1);
+                const uint32_t h = ((x >> 22) + tries * step) & (LEAF_SLOTS - 1);
                 const uint32_t slot = tbl_s + 8 * h;
                 bool won = false;
                 if (active) {
-                    const unsigned long long old = atoms_cas64(slot, kEmpty, key);
-                    won = old == kEmpty;
-                    const bool dup = (old & KEYMASK) == key;           // (never true together with won)
-                    if (dup) {
-                        if (PACKED) reds_add64(slot, 1ull << 52);
-                        else reds_add32(cnt_s + 4 * h, 1u);
+                    if (tries >= LEAF_SLOTS) {                          // table full: tier 2 counts this k-mer (one-k-mer record)
+                        const unsigned long long si = atomicAdd(&status->n_spill, 1ull);
+                        if (si < plan.spill_cap) {
+                            if (RECW == 1) reinterpret_cast<unsigned long long*>(spill)[si] = skey << kshift;
+                            else { ulonglong2 o; o.x = skey << kshift; o.y = 0ull; reinterpret_cast<ulonglong2*>(spill)[si] = o; }
+                        } else atomicAdd(&status->n_overflow, 1ull);
+                        atomicAdd(&status->n_kmers, ~0ull);            // not counted here
+                        active = false;
+                    } else {
+                        const unsigned long long old = atoms_cas64(slot, kEmpty, skey);
+                        won = old == kEmpty;
+                        const bool dup = !won && (old & KEYMASK) == skey;   // !won: at k == 26 't'*26 equals kEmpty & KEYMASK
+                        if (dup) {
+                            if (PACKED) reds_add64(slot, 1ull << 52);
+                            else reds_add32(cnt_s + 4 * h, 1u);
+                        }
+                        active = !(won | dup);
+                        tries++;
                     }
-                    active = !(won | dup);
-                    tries++;
                 }
                 // the claimed slots are listed in place of the warp's consumed slow-list entries (nwin < next - kb always
                 // holds: every claim follows the fetch of its k-mer, and all entries below `next` have been read)
                 const uint32_t wm = __ballot_sync(0xffffffffu, won);
-                if (won) sts16(bma_s + 2 * (kb + nwin + __popc(wm & lane_lt)), h);
+                if (won) sts16(slow_s + 2 * (kb + nwin + __popc(wm & lane_lt)), h);
                 nwin += __popc(wm);
             }
         }
@@ -602,34 +623,39 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1280 / LEAF_THREADS) bucket_coun
         if (t == 0) s_obase[par] = ubase;
         if (RECW == 2) special_total += special;
         __syncthreads();                                                // (B) all counts final
-        if (t == 0) { s_nuniq[par ^ 1] = 0; s_nslow[par ^ 1] = 0; }   // idle until the next bucket's sort phase
+        if (t < 2) { if (t == 0) s_nuniq[par ^ 1] = 0; else s_nslow[par ^ 1] = 0; }   // idle until the next bucket's classify phase
+        if (t >= 32 && t < 32 + LEAF_BLOCKS) s_mask[par][t - 32] = 0;   // this bucket's start bits: idle until the bucket after the next
         // ---- emit the unique k-mers: coalesced 16-byte (k-mer, 1) pairs, ranks by ballot
         {
-            unsigned long long ob = s_obase[par] + woff;
+            const unsigned long long ob = s_obase[par] + woff;
             const bool fits = ob + wuniq <= (out_u ? capacity_u : capacity);   // uniform per warp
             if (!fits && lane == 0) status->out_overflow = 1;
+            ulonglong2* const po = reinterpret_cast<ulonglong2*>(out) + ob;
+            uint64_t* const pu = out_u + ob;
+            uint32_t rank = 0;
+            const uint32_t um = fits ? uniq : 0u;
 #pragma unroll
             for (int i = 0; i < LEAF_KPT; i++) {
-                if (i * LEAF_THREADS >= nk) break;
-                const bool u = fits && ((uniq >> i) & 1u);
+                if (i * LEAF_THREADS >= (int)nkeys) break;
+                const bool u = (um >> i) & 1u;
                 const uint32_t m = __ballot_sync(0xffffffffu, u);
                 if (u) {
-                    const uint64_t key = key_at(t + i * LEAF_THREADS);
-                    if (out_u) out_u[ob + __popc(m & lane_lt)] = key;     // split format: a bare code means count 1
+                    const uint32_t o = rank + __popc(m & lane_lt);
+                    if (out_u) pu[o] = key[i];                          // split format: a bare code means count 1
                     else {
-                        ulonglong2 o;
-                        o.x = key;
-                        o.y = 1ull;
-                        reinterpret_cast<ulonglong2*>(out)[ob + __popc(m & lane_lt)] = o;
+                        ulonglong2 v;
+                        v.x = key[i];
+                        v.y = 1ull;
+                        po[o] = v;
                     }
                 }
-                ob += __popc(m);
+                rank += __popc(m);
             }
         }
         // ---- emit + reset the table entries this warp claimed
         wbase = __shfl_sync(0xffffffffu, wbase, 0);
         for (uint32_t i = lane; i < nwin; i += 32) {
-            const uint32_t h = lds16(bma_s + 2 * (kb + i));
+            const uint32_t h = lds16(slow_s + 2 * (kb + i));
             const unsigned long long v = lds64(tbl_s + 8 * h);
             sts64(tbl_s + 8 * h, kEmpty);
             unsigned long long c;
@@ -908,7 +934,7 @@ __global__ void __launch_bounds__(256) tier2_insert_kernel(PartitionPlan plan, i
     for (uint32_t fi = blockIdx.x; fi < n_failed; fi += gridDim.x) {
         const uint32_t b = failed_ids[fi];
         for (int sI = 0; sI < n_src; sI++) {
-            const uint32_t nrec = min((uint32_t)fill[(uint64_t)sI * plan.n_buckets + b], plan.cap);
+            const uint32_t nrec = min((uint32_t)fill[(uint64_t)sI * plan.n_buckets + b] & 0x7fffffffu, plan.cap);   // bit 31: poison (scatter.cuh)
             const Rec<RECW>* base = recs + ((uint64_t)sI * plan.n_buckets + b) * plan.cap;
             for (uint32_t r0 = 0; r0 < nrec; r0 += blockDim.x) {
                 uint32_t r = r0 + threadIdx.x;
@@ -934,8 +960,125 @@ __global__ void append_special_kernel(kmer_count_pair* out, uint64_t capacity, D
     atomicAdd(&status->n_kmers, sc);
 }
 
+}  // namespace kmer
+#include "scatter.cuh"
+namespace kmer {
+
 // ---------------------------------------------------------------------------------------------
 // host side
+
+static double poisson_tail(double lam, int c) {          // P(X > c), X ~ Poisson(lam)
+    double term = exp(-lam), cdf = term;
+    for (int i = 1; i <= c; i++) { term *= lam / i; cdf += term; }
+    return cdf >= 1.0 ? 0.0 : 1.0 - cdf;
+}
+// staging slots per destination: a sector's leftover (sect - 1) plus the arrivals of one round, so that a round needs
+// a second flush (a destination's slots taken) with probability < budget
+static uint32_t stage_slots(double lam, uint32_t sect, double dests, double budget, uint32_t max_slots) {
+    uint32_t c;
+    if (lam > 30.0) c = (uint32_t)(lam + 6.0 * sqrt(lam)) + sect;      // normal tail (few, large destinations: small jobs)
+    else {
+        c = sect;
+        while (c < max_slots && dests * poisson_tail(lam, (int)(c - (sect - 1))) > budget) c++;
+    }
+    return c < max_slots ? c : max_slots;
+}
+static size_t stage_bytes(uint32_t dests, uint32_t caps, int recw) { return (((size_t)dests * 4 + 15) & ~(size_t)15) + (size_t)dests * caps * (recw == 1 ? 8 : 16); }
+static size_t scatter_static_smem() { return sizeof(ScanSmem) + (NT / 32) * SCAT_RUNCAP * 4 + (TILE / 32 + 2) * 4 + 64; }
+
+bool make_scatter_plan(const DeviceInfo& di, uint64_t n_bases, uint64_t n_kmers, PartitionPlan& p, ScatterPlan& sp) {
+    uint32_t fine_shift = 10;                              // F = 1024 fine buckets per coarse partition: one per refine2 thread
+#ifdef KMER_TUNE
+    if (const char* e = getenv("KMER_FINE_SHIFT")) fine_shift = (uint32_t)atoi(e);
+#endif
+    while (fine_shift > 0 && (1u << fine_shift) > p.n_buckets) fine_shift--;
+    const uint64_t D = ((uint64_t)p.n_buckets + (1u << fine_shift) - 1) >> fine_shift;
+    if (D > (uint64_t)SCAT_DPT * NT || fine_shift > 10) return false;
+    const double rpk = 2.1 / (p.w + 1) + (p.rmax < p.w ? 1.0 / p.rmax : 0.0);   // records per k-mer (make_partition_plan)
+    const uint32_t sect = p.recw == 1 ? 4 : 2;
+    const uint64_t n_tiles = (n_bases + TILE - 1) / TILE;
+    // pass 1: as many CTAs per SM as the staging area allows (at most SCAT_MINB)
+    uint32_t caps = 0, per_sm = SCAT_MINB;
+    for (; per_sm >= 1; per_sm--) {
+        const size_t budget = (size_t)227 * 1024 / per_sm - 1024 - scatter_static_smem();
+        const uint32_t max_slots = (uint32_t)std::min<size_t>(4096, (budget - (((size_t)D * 4 + 15) & ~(size_t)15)) / (D * (p.recw == 1 ? 8 : 16)));
+        if (max_slots < sect + 2) continue;
+        caps = stage_slots(TILE * rpk / (double)D, sect, (double)D, 0.02, max_slots);
+        if (caps < max_slots || per_sm == 1) break;       // the slots wanted fit (or nothing smaller is left to try)
+    }
+    if (per_sm < 1 || caps < sect) return false;
+#ifdef KMER_TUNE
+    if (const char* e = getenv("KMER_SCAT_CAPS")) caps = (uint32_t)atoi(e);
+    if (const char* e = getenv("KMER_SCAT_PER_SM")) per_sm = (uint32_t)atoi(e);
+#endif
+    uint64_t grid = (uint64_t)di.sm_count * per_sm;
+    if (grid > n_tiles) grid = n_tiles ? n_tiles : 1;
+    const double mean = (double)n_kmers * rpk / ((double)grid * (double)D);
+    sp.n_coarse = (uint32_t)D;
+    sp.n_src = (uint32_t)grid;
+    sp.seg_cap = ((uint32_t)(1.1 * mean + 6.0 * sqrt(mean) + 32.0) + 3u) & ~3u;
+    sp.caps = caps;
+    const uint32_t F = 1u << fine_shift;
+    const size_t budget2 = (size_t)227 * 1024 - 1024 - (((size_t)F * 4 + 15) & ~(size_t)15) * 2;
+    const uint32_t max2 = (uint32_t)std::min<size_t>(4096, budget2 / ((size_t)F * (p.recw == 1 ? 8 : 16)));
+    sp.caps2 = stage_slots((double)RF2_THREADS * RF2_RQ / (double)F, sect, (double)F, 0.02, max2);
+    p.n_buckets = (uint32_t)(D << fine_shift);
+    p.hash_buckets = p.n_buckets;
+    p.fine_shift = (int)fine_shift;
+    const uint64_t sc = (uint64_t)p.n_buckets * p.cap / 8;
+    p.spill_cap = sc < 4096 ? 4096 : sc;
+    return true;
+}
+
+size_t scatter_seg_bytes(const PartitionPlan& p, const ScatterPlan& sp) {
+    return (size_t)sp.n_src * sp.n_coarse * sp.seg_cap * (p.recw == 1 ? 8 : 16);
+}
+size_t scatter_segfill_bytes(const ScatterPlan& sp) { return (size_t)sp.n_src * sp.n_coarse * 4; }
+
+template <int W, int RECW>
+static void launch_scatter_refine_t(const DeviceInfo& di, const ScanArgs& a, const PartitionPlan& p, const ScatterPlan& sp, uint32_t* d_segfill,
+                                    void* d_seg, unsigned long long* d_fill, void* d_recs, void* d_spill, cudaStream_t st,
+                                    void (*mark)(void*, const char*), void* mark_arg) {
+    static size_t conf1[64] = {}, conf2[64] = {};          // per device: dynamic shared memory opted in so far
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t smem1 = stage_bytes(sp.n_coarse, sp.caps, RECW);
+    const size_t smem2 = ((((size_t)4 << p.fine_shift) + 15) & ~(size_t)15) + stage_bytes(1u << p.fine_shift, sp.caps2, RECW);
+    if (dev >= 0 && dev < 64 && conf1[dev] < smem1) {
+        cudaFuncSetAttribute(scatter_kernel<W, RECW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+        cudaFuncSetAttribute(scatter_kernel<W, RECW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        conf1[dev] = smem1;
+    }
+    if (dev >= 0 && dev < 64 && conf2[dev] < smem2) {
+        cudaFuncSetAttribute(refine2_kernel<W, RECW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        cudaFuncSetAttribute(refine2_kernel<W, RECW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        conf2[dev] = smem2;
+    }
+    cudaMemsetAsync(d_fill, 0, (size_t)p.n_buckets * sizeof(unsigned long long), st);
+    scatter_kernel<W, RECW><<<sp.n_src, NT, smem1, st>>>(a, p, sp, d_segfill, (Rec<RECW>*)d_seg, d_fill, (Rec<RECW>*)d_spill);
+    if (mark) mark(mark_arg, "scatter");
+    unsigned grid2 = (unsigned)std::min<uint64_t>(sp.n_coarse, (uint64_t)di.sm_count);
+    refine2_kernel<W, RECW><<<grid2, RF2_THREADS, smem2, st>>>(p, sp, d_segfill, (const Rec<RECW>*)d_seg, d_fill, (Rec<RECW>*)d_recs,
+                                                                (Rec<RECW>*)d_spill, a.status);
+    if (mark) mark(mark_arg, "refine");
+}
+
+void launch_scatter_refine(const DeviceInfo& di, const ScanArgs& a, const PartitionPlan& p, const ScatterPlan& sp, uint32_t* d_segfill,
+                           void* d_seg, unsigned long long* d_fill, void* d_recs, void* d_spill, cudaStream_t st,
+                           void (*mark)(void*, const char*), void* mark_arg) {
+#define KMER_SR(W_, R_) launch_scatter_refine_t<W_, R_>(di, a, p, sp, d_segfill, d_seg, d_fill, d_recs, d_spill, st, mark, mark_arg)
+    if (p.recw == 1) {
+        if (p.w == 4) KMER_SR(4, 1);
+        else if (p.w == 6) KMER_SR(6, 1);
+        else KMER_SR(8, 1);
+    } else {
+        if (p.w == 8) KMER_SR(8, 2);
+        else if (p.w == 12) KMER_SR(12, 2);
+        else KMER_SR(16, 2);
+    }
+#undef KMER_SR
+}
+
 
 PartitionPlan make_partition_plan(uint64_t n_kmers, int k) {
     PartitionPlan p{};
@@ -1008,35 +1151,42 @@ void launch_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPl
 // p.n_buckets = buckets counted HERE (all of them on one GPU, the owned range when sharded)
 size_t leaf_smem_bytes(const PartitionPlan& p) {
     const size_t recb = p.recw == 1 ? 8 : 16;
-    size_t table = (size_t)LEAF_SLOTS * 8 + (p.recw == 1 ? 0 : (size_t)LEAF_SLOTS * 4) + 2 * (size_t)LEAF_CELLS / 8 +
-                   ((size_t)LEAF_MAX_KMERS + 1) * 2;
+    size_t fixed = (size_t)LEAF_SLOTS * 8 + (p.recw == 1 ? 0 : (size_t)LEAF_SLOTS * 4) + 2 * (size_t)LEAF_CELLS / 8 + (size_t)LEAF_KEYS * 2 +
+                   ((((size_t)p.cap + 2) * 2 + 15) & ~(size_t)15);
     size_t staged = ((size_t)p.cap + 2) * recb;                           // padded to 16 bytes
-    return table + 2 * ((staged + 15) & ~(size_t)15);                    // two record buffers
+    return fixed + 2 * ((staged + 15) & ~(size_t)15);                     // two record buffers
 }
 
-void launch_bucket_count(const DeviceInfo& di, const PartitionPlan& p, int k, int n_src, const unsigned long long* d_fill,
-                         const void* d_recs, uint32_t* d_failed_ids, kmer_count_pair* d_pairs, uint64_t capacity,
+// once per process and device: opt in to the leaf's dynamic shared memory
+static void leaf_configure(size_t smem) {
+    static size_t configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || configured[dev] >= smem) return;
+    cudaFuncSetAttribute(bucket_count_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(bucket_count_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(bucket_count_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(bucket_count_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    configured[dev] = smem;
+}
+
+void launch_bucket_count(const DeviceInfo& di, const PartitionPlan& p, int k, const unsigned long long* d_fill,
+                         const void* d_recs, void* d_spill, uint32_t* d_failed_ids, kmer_count_pair* d_pairs, uint64_t capacity,
                          uint64_t* d_uniq, uint64_t uniq_capacity, DevStatus* d_status, cudaStream_t st) {
-    (void)n_src;   // sharded counting merges the source segments in refine_kernel: the leaf always sees one segment per bucket
     const size_t leaf_smem = leaf_smem_bytes(p);
     int per_sm = (int)((size_t)227 * 1024 / (leaf_smem + 1024));
-    static const char* env_ctas = getenv("KMER_CUDA_LEAF_CTAS");   // profiling experiments only
-    int max_per_sm = env_ctas ? atoi(env_ctas) : 6;
-    if (per_sm > max_per_sm) per_sm = max_per_sm;
+    if (per_sm > LEAF_MINB) per_sm = LEAF_MINB;
     if (per_sm < 1) per_sm = 1;
     uint64_t lgrid = (uint64_t)di.sm_count * per_sm;
     if (lgrid > p.n_buckets) lgrid = p.n_buckets;
     if (!lgrid) return;
-#define KMER_LEAF_LAUNCH(RW)                                                                                              \
-    do {                                                                                                                      \
-        cudaFuncSetAttribute(bucket_count_kernel<RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leaf_smem);       \
-        cudaFuncSetAttribute(bucket_count_kernel<RW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);               \
-        bucket_count_kernel<RW><<<(unsigned)lgrid, LEAF_THREADS, leaf_smem, st>>>(                                        \
-            p, k, d_fill, (const Rec<RW>*)d_recs, d_pairs, capacity, d_uniq, uniq_capacity, d_failed_ids, d_status);                          \
-    } while (0)
-    if (p.recw == 1) KMER_LEAF_LAUNCH(1);
-    else KMER_LEAF_LAUNCH(2);
-#undef KMER_LEAF_LAUNCH
+    leaf_configure(leaf_smem);
+    if (p.recw == 1)
+        bucket_count_kernel<1><<<(unsigned)lgrid, LEAF_THREADS, leaf_smem, st>>>(p, k, d_fill, (const Rec<1>*)d_recs, d_pairs, capacity, d_uniq,
+                                                                                 uniq_capacity, d_failed_ids, (Rec<1>*)d_spill, d_status);
+    else
+        bucket_count_kernel<2><<<(unsigned)lgrid, LEAF_THREADS, leaf_smem, st>>>(p, k, d_fill, (const Rec<2>*)d_recs, d_pairs, capacity, d_uniq,
+                                                                                 uniq_capacity, d_failed_ids, (Rec<2>*)d_spill, d_status);
 }
 
 void launch_count_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPlan& p, unsigned long long* d_fill,
@@ -1044,7 +1194,7 @@ void launch_count_partition(const DeviceInfo& di, const ScanArgs& a, const Parti
                             uint64_t* d_uniq, uint64_t uniq_capacity, cudaStream_t st, void (*mark)(void*, const char*), void* mark_arg) {
     launch_partition(di, a, p, d_fill, d_recs, d_spill, st);
     if (mark) mark(mark_arg, "minimizer_partition");
-    launch_bucket_count(di, p, a.k, 1, d_fill, d_recs, d_failed_ids, d_pairs, capacity, d_uniq, uniq_capacity, a.status, st);
+    launch_bucket_count(di, p, a.k, d_fill, d_recs, d_spill, d_failed_ids, d_pairs, capacity, d_uniq, uniq_capacity, a.status, st);
     if (mark) mark(mark_arg, "bucket_count");
 }
 

@@ -56,6 +56,23 @@ struct PartitionPlan {
     int debug;            // profiling experiments only (env KMER_CUDA_DEBUG_PARTITION)
 };
 PartitionPlan make_partition_plan(uint64_t n_kmers, int k);
+// two write-combining passes (scatter.cuh): column -> n_coarse partitions (one segment per scatter CTA) -> fine buckets
+struct ScatterPlan {
+    uint32_t n_coarse;   // destinations of the first pass
+    uint32_t seg_cap;    // records per (scatter CTA, coarse partition) segment; whole sectors
+    uint32_t n_src;      // scatter CTAs = segments per coarse partition
+    uint32_t caps;       // staging slots per destination, first pass
+    uint32_t caps2;      // staging slots per fine bucket, second pass
+};
+// Adjusts p (n_buckets = n_coarse << fine_shift) and fills sp; false: the job does not suit the two-pass path (the caller uses
+// launch_partition).  n_ranks > 1: the coarse partitions of ALL ranks (sharded counting; not built yet).
+bool make_scatter_plan(const DeviceInfo& di, uint64_t n_bases, uint64_t n_kmers, PartitionPlan& p, ScatterPlan& sp);
+size_t scatter_seg_bytes(const PartitionPlan& p, const ScatterPlan& sp);
+size_t scatter_segfill_bytes(const ScatterPlan& sp);
+// d_fill (p.n_buckets words) is zeroed here; afterwards it holds k-mers << 32 | records in the region | poison (bit 31)
+void launch_scatter_refine(const DeviceInfo& di, const ScanArgs& a, const PartitionPlan& p, const ScatterPlan& sp, uint32_t* d_segfill,
+                           void* d_seg, unsigned long long* d_fill, void* d_recs, void* d_spill, cudaStream_t st,
+                           void (*mark)(void*, const char*), void* mark_arg);
 size_t partition_record_bytes(const PartitionPlan& p);
 size_t partition_spill_bytes(const PartitionPlan& p);
 // minimizer partition + per-bucket shared-memory counting (14 <= k <= 32).  Afterwards the host reads
@@ -65,8 +82,8 @@ void launch_count_partition(const DeviceInfo& di, const ScanArgs& a, const Parti
                             uint64_t* d_uniq, uint64_t uniq_capacity, cudaStream_t st, void (*mark)(void*, const char*), void* mark_arg);
 void launch_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPlan& p, unsigned long long* d_fill,
                       void* d_recs, void* d_spill, cudaStream_t st);
-void launch_bucket_count(const DeviceInfo& di, const PartitionPlan& p, int k, int n_src, const unsigned long long* d_fill,
-                         const void* d_recs, uint32_t* d_failed_ids, kmer_count_pair* d_pairs, uint64_t capacity,
+void launch_bucket_count(const DeviceInfo& di, const PartitionPlan& p, int k, const unsigned long long* d_fill,
+                         const void* d_recs, void* d_spill, uint32_t* d_failed_ids, kmer_count_pair* d_pairs, uint64_t capacity,
                          uint64_t* d_uniq, uint64_t uniq_capacity, DevStatus* d_status, cudaStream_t st);
 // d_uniq != nullptr: split result format -- k-mers proven unique on chip are written as bare codes to d_uniq (counted in
 // DevStatus::n_unique), everything else as (k-mer, count) pairs

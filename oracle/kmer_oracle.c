@@ -259,3 +259,54 @@ int orc_count(const char *flat, const uint64_t *off, uint64_t n_rows, int k, uin
 	*n_kmers = n;
 	return ORC_OK;
 }
+
+/* Order-independent checksum of the k-mer multiset generate_kmers (kmer.c:289-351) produces over a table of rows:
+ *   *sum = sum over all windows of mix64(code)  (mod 2^64),   *n_out = number of windows.
+ * A (k-mer, count) table holds the same multiset iff  sum over groups of count * mix64(code) == *sum  (and its keys are
+ * distinct, its counts sum to *n_out).  Used by bench.py / the tests to pin results at sizes where the full table cannot be
+ * compared.  mix64 is the murmur3 finaliser (a bijection of 64-bit words). */
+static uint64_t orc_mix64(uint64_t x)
+{
+	x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
+	x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
+	x ^= x >> 33;
+	return x;
+}
+
+int orc_multiset_checksum(const char *flat, const uint64_t *off, uint64_t n_rows, int k, uint64_t *sum,
+						  uint64_t *n_out, int64_t *bad_row)
+{
+	uint64_t acc = 0, n = 0;
+	const uint64_t mask = k >= 32 ? ~0ULL : ((1ULL << (2 * k)) - 1ULL);
+	*bad_row = -1;
+	*sum = 0;
+	*n_out = 0;
+	for (uint64_t r = 0; r < n_rows; r++)
+	{
+		const char *s = flat + off[r];
+		uint64_t len = off[r + 1] - off[r];
+		if (orc_validate_dna(s, len) >= 0)
+		{
+			*bad_row = (int64_t) r;
+			return ORC_INVALID_DNA;
+		}
+		if ((int64_t) len < (int64_t) k || k <= 0 || k > ORC_MAX_K)
+		{
+			*bad_row = (int64_t) r;
+			return ORC_INVALID_K;
+		}
+		uint64_t v = 0;
+		for (uint64_t p = 0; p < len; p++)
+		{
+			v = ((v << 2) | (uint64_t) base_code((unsigned char) s[p])) & mask;
+			if (p + 1 >= (uint64_t) k)
+			{
+				acc += orc_mix64(v);
+				n++;
+			}
+		}
+	}
+	*sum = acc;
+	*n_out = n;
+	return ORC_OK;
+}

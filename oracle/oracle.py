@@ -182,6 +182,18 @@ class COracle:
         L.orc_generate.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]
         L.orc_count.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p,
                                 C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]
+        L.orc_multiset_checksum.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64),
+                                            C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]
+
+    def multiset_checksum(self, flat, off: np.ndarray, k: int) -> tuple[int, int]:
+        """(sum of mix64(code) over all windows mod 2^64, number of windows) -- see orc_multiset_checksum."""
+        f = _as_flat(flat)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        s, n, bad = C.c_uint64(), C.c_uint64(), C.c_int64()
+        rc = self.lib.orc_multiset_checksum(f.ctypes.data, off.ctypes.data, len(off) - 1, k, C.byref(s), C.byref(n), C.byref(bad))
+        if rc:
+            raise OracleError(rc, bad.value)
+        return int(s.value), int(n.value)
 
     def kmer_encode(self, text: str) -> tuple[int, int]:
         v = C.c_uint64()
@@ -286,6 +298,24 @@ def np_count(flat, off: np.ndarray, k: int):
     codes = np_generate(flat, off, k)
     keys, counts = np.unique(codes, return_counts=True)
     return keys.astype(np.uint64), counts.astype(np.uint64), int(codes.size)
+
+
+def np_mix64(x: np.ndarray) -> np.ndarray:
+    """murmur3 finaliser on uint64 arrays (wraps mod 2^64), the hash of the multiset checksum."""
+    x = np.asarray(x, dtype=np.uint64).copy()
+    with np.errstate(over="ignore"):
+        x ^= x >> np.uint64(33)
+        x *= np.uint64(0xff51afd7ed558ccd)
+        x ^= x >> np.uint64(33)
+        x *= np.uint64(0xc4ceb9fe1a85ec53)
+        x ^= x >> np.uint64(33)
+    return x
+
+
+def np_table_checksum(keys: np.ndarray, counts: np.ndarray) -> int:
+    """sum over groups of count * mix64(code) mod 2^64: equals COracle.multiset_checksum of the rows the table counts."""
+    with np.errstate(over="ignore"):
+        return int((np_mix64(keys) * np.asarray(counts, dtype=np.uint64)).sum(dtype=np.uint64))
 
 
 def np_decode(codes: np.ndarray, k: int) -> np.ndarray:
