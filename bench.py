@@ -55,6 +55,60 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+
+# ------------------------------------------------------------------------------------------------------------------
+# parity at config scale (outside every timed region): the GROUP BY table must hold exactly the multiset of windows
+# generate_kmers yields.  CPU side: the C oracle's order-independent checksum of the INPUT rows, sum of mix64(code) over
+# all windows mod 2^64 (oracle/kmer_oracle.c orc_multiset_checksum, validated against np_count in tests/test_oracle.py).
+# GPU side (torch, harness only): sum over groups of count * mix64(code), plus sum of counts and key uniqueness by a sort.
+M64 = (1 << 64) - 1
+
+
+def _s64(v):
+    v &= M64
+    return v - (1 << 64) if v >> 63 else v
+
+
+def mix64_torch(torch, x):
+    """murmur3 finaliser on int64 tensors (two's complement wrap == uint64 arithmetic)."""
+    lo31 = (1 << 31) - 1
+    x = x ^ ((x >> 33) & lo31)
+    x = x * _s64(0xff51afd7ed558ccd)
+    x = x ^ ((x >> 33) & lo31)
+    x = x * _s64(0xc4ceb9fe1a85ec53)
+    x = x ^ ((x >> 33) & lo31)
+    return x
+
+
+def table_checksum(torch, keys, counts=None, chunk=1 << 26):
+    """(sum count*mix64(key) mod 2^64, sum of counts) of a device table; counts=None means every count is 1."""
+    tot, cnt = 0, 0
+    n = keys.numel()
+    for i in range(0, n, chunk):
+        k = keys[i:i + chunk]
+        m = mix64_torch(torch, k)
+        if counts is not None:
+            c = counts[i:i + chunk]
+            m = m * c
+            cnt += int(c.sum().item())
+        else:
+            cnt += k.numel()
+        tot = (tot + int(m.sum().item())) & M64
+    return tot, cnt
+
+
+def keys_unique(torch, keys):
+    if keys.numel() < 2:
+        return True
+    s, _ = torch.sort(keys)
+    return not bool((s[1:] == s[:-1]).any().item())
+
+
+def input_checksum(flat, off, k):
+    from oracle import oracle as O
+    return O.COracle().multiset_checksum(flat, off, k)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -259,6 +313,7 @@ def main():
     ap.add_argument("--match-m", type=int, default=0, help="k-mers in the match workloads (default: the config's size)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle checksum of the result tables (profiling runs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         print(f"note: warmup {args.warmup} < 3 is below the timing rule", file=sys.stderr)
@@ -354,6 +409,43 @@ def main():
     ms_step = ms_total / args.steps
     value = total_kmers * args.steps / (ms_total * 1e-3)
 
+    # ---------------------------------------------------------------- parity of the table the LAST timed step left in HBM
+    parity = {"what": "sum(count*mix64(code)) over the table == sum(mix64(code)) over all windows of the input rows (C oracle), "
+                      "sum(count) == windows, keys unique (device sort); N>1: sums all-reduced, keys re-partitioned by hash "
+                      "across ranks and checked unique there"}
+    if not args.no_parity:
+        nd_last = int(res.n_distinct)
+        t_in = time.perf_counter()
+        in_sum, in_n = input_checksum(flat, off, K)
+        parity["oracle_seconds"] = time.perf_counter() - t_in
+        keys_t, counts_t = d_pairs[:nd_last, 0], d_pairs[:nd_last, 1]
+        tab_sum, tab_cnt = table_checksum(torch, keys_t, counts_t)
+        uniq_ok = keys_unique(torch, keys_t)
+        if world > 1:
+            v = torch.tensor([_s64(in_sum), in_n, _s64(tab_sum), tab_cnt, 0 if uniq_ok else 1], dtype=torch.int64, device="cuda")
+            dist.all_reduce(v)
+            in_sum, in_n, tab_sum, tab_cnt = int(v[0].item()) & M64, int(v[1].item()), int(v[2].item()) & M64, int(v[3].item())
+            uniq_ok = int(v[4].item()) == 0
+            # a group split over two owners keeps both sums: send every key to rank hash(key) % world and look for duplicates there
+            dest = ((mix64_torch(torch, keys_t) >> 17) & 0xffff) % world
+            order = torch.argsort(dest)
+            send = keys_t[order].contiguous()
+            scnt = torch.bincount(dest, minlength=world)
+            rcnt = torch.empty_like(scnt)
+            dist.all_to_all_single(rcnt, scnt)
+            recv = torch.empty(int(rcnt.sum().item()), dtype=torch.int64, device="cuda")
+            dist.all_to_all_single(recv, send, output_split_sizes=rcnt.tolist(), input_split_sizes=scnt.tolist())
+            cross = torch.tensor([0 if keys_unique(torch, recv) else 1], dtype=torch.int64, device="cuda")
+            dist.all_reduce(cross)
+            parity["cross_rank_unique_ok"] = int(cross.item()) == 0
+            uniq_ok = uniq_ok and parity["cross_rank_unique_ok"]
+            del dest, order, send, recv
+        parity.update({"checksum_ok": in_sum == tab_sum, "count_ok": in_n == tab_cnt == total_kmers, "unique_ok": bool(uniq_ok),
+                       "windows": in_n, "groups_checked_rank0": nd_last})
+        torch.cuda.empty_cache()
+    else:
+        parity["skipped"] = True
+
     # ---------------------------------------------------------------- per-kernel phases (separate pass, not the timed one)
     eng.set_profiling(True)
     phase_acc = {}
@@ -412,35 +504,72 @@ def main():
             uq, nu = C.c_void_p(), C.c_uint64()
             seq_ptr, off_ptr = h_seq.data_ptr(), h_off.data_ptr()
 
-            def e2e_step_pairs():
+            in_chk = input_checksum(flat, off, K) if not args.no_parity else None
+
+            def host_view(ptr, n_items, dtype):
+                return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n_items * np.dtype(dtype).itemsize,)).view(dtype)
+
+            def check_table(uniq_codes, pair_arr):
+                """the host result of one e2e call (unique codes as int64 array or None, pairs as [n,2] int64) against the oracle's checksum"""
+                tot, cnt, ok_u = 0, 0, True
+                allkeys = []
+                if uniq_codes is not None and uniq_codes.size:
+                    ku = torch.from_numpy(uniq_codes).cuda()
+                    a, b = table_checksum(torch, ku)
+                    tot, cnt = (tot + a) & M64, cnt + b
+                    allkeys.append(ku)
+                if pair_arr.size:
+                    pa = torch.from_numpy(pair_arr).cuda()
+                    a, b = table_checksum(torch, pa[:, 0], pa[:, 1])
+                    tot, cnt = (tot + a) & M64, cnt + b
+                    allkeys.append(pa[:, 0].contiguous())
+                    del pa
+                ok_u = keys_unique(torch, torch.cat(allkeys)) if allkeys else True
+                del allkeys
+                torch.cuda.empty_cache()
+                return {"checksum_ok": tot == in_chk[0], "count_ok": cnt == in_chk[1], "unique_ok": ok_u}
+
+            def e2e_step_pairs(check=False):
                 rc = eng.lib.kmer_cuda_submit_count(eng.ctx, seq_ptr, off_ptr, n_rows, K, C.byref(pairs), C.byref(d), C.byref(nk))
                 if rc:
                     eng._raise(eng.ctx)
                 chk = (C.c_uint64 * 2).from_address(pairs.value)  # touch the result on the host
-                got = (int(chk[0]), int(chk[1]), int(d.value), int(nk.value), 16 * int(d.value))
+                got = [int(chk[0]), int(chk[1]), int(d.value), int(nk.value), 16 * int(d.value), None]
+                if check:
+                    got[5] = check_table(None, host_view(pairs, 2 * int(d.value), np.int64).reshape(-1, 2))
                 eng.lib.kmer_cuda_release(eng.ctx, pairs)
                 return got
 
-            def e2e_step_split():
+            def e2e_step_split(check=False):
                 rc = eng.lib.kmer_cuda_submit_count_split(eng.ctx, seq_ptr, off_ptr, n_rows, K, C.byref(uq), C.byref(nu),
                                                           C.byref(pairs), C.byref(d), C.byref(nk))
                 if rc:
                     eng._raise(eng.ctx)
                 chk = (C.c_uint64 * 1).from_address(uq.value) if nu.value else [0]  # touch the result on the host
-                got = (int(chk[0]), 0, int(d.value) + int(nu.value), int(nk.value), 16 * int(d.value) + 8 * int(nu.value))
+                got = [int(chk[0]), 0, int(d.value) + int(nu.value), int(nk.value), 16 * int(d.value) + 8 * int(nu.value), None]
+                if check:
+                    got[5] = check_table(host_view(uq, int(nu.value), np.int64), host_view(pairs, 2 * int(d.value), np.int64).reshape(-1, 2))
                 eng.lib.kmer_cuda_release(eng.ctx, uq)
                 eng.lib.kmer_cuda_release(eng.ctx, pairs)
                 return got
 
             nbytes_c = C.c_int()
 
-            def e2e_step_packed():
+            def e2e_step_packed(check=False):
                 rc = eng.lib.kmer_cuda_submit_count_packed(eng.ctx, seq_ptr, off_ptr, n_rows, K, C.byref(uq), C.byref(nu), C.byref(nbytes_c),
                                                            C.byref(pairs), C.byref(d), C.byref(nk))
                 if rc:
                     eng._raise(eng.ctx)
                 chk = (C.c_uint8 * 8).from_address(uq.value) if nu.value else [0]  # touch the result on the host
-                got = (int(chk[0]), 0, int(d.value) + int(nu.value), int(nk.value), 16 * int(d.value) + nbytes_c.value * int(nu.value))
+                got = [int(chk[0]), 0, int(d.value) + int(nu.value), int(nk.value), 16 * int(d.value) + nbytes_c.value * int(nu.value), None]
+                if check:
+                    nb = nbytes_c.value
+                    raw = torch.from_numpy(host_view(uq, int(nu.value) * nb, np.uint8)).cuda().view(-1, nb).to(torch.int64)
+                    codes = torch.zeros(raw.shape[0], dtype=torch.int64, device="cuda")
+                    for j in range(nb):                         # little-endian ceil(2k/8)-byte integers
+                        codes |= raw[:, j] << (8 * j)
+                    del raw
+                    got[5] = check_table(codes.cpu().numpy(), host_view(pairs, 2 * int(d.value), np.int64).reshape(-1, 2))
                 eng.lib.kmer_cuda_release(eng.ctx, uq)
                 eng.lib.kmer_cuda_release(eng.ctx, pairs)
                 return got
@@ -454,8 +583,11 @@ def main():
                     got = step_fn()
                 dt = time.perf_counter() - t0
                 assert got[2] == n_distinct and got[3] == n_kmers
-                return {"value": n_kmers * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": n_bases + 8 * (n_rows + 1),
-                        "d2h_bytes_per_step": got[4], "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps, "api": api_name}
+                r = {"value": n_kmers * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": n_bases + 8 * (n_rows + 1),
+                     "d2h_bytes_per_step": got[4], "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps, "api": api_name}
+                if not args.no_parity:                           # one more call, untimed, whose host result is checked
+                    r["parity"] = step_fn(check=True)[5]
+                return r
 
             # the result of the GROUP BY crosses PCIe either as 16-byte (k-mer, count) pairs, or in the split format
             # (a group with count 1 as its bare 8-byte code, the rest as pairs): same table, half the bytes on this input
@@ -463,6 +595,12 @@ def main():
                                          "bare ceil(2k/8)-byte codes + (k-mer,count) pairs for the rest)")
             e2e["split_format"] = timed(e2e_step_split, "kmer_cuda_submit_count_split (unique k-mers as bare 8-byte codes + pairs)")
             e2e["pairs_format"] = timed(e2e_step_pairs, "kmer_cuda_submit_count (pinned host input -> pinned host (k-mer,count) table)")
+            # what the PostgreSQL glue feeds: palloc'ed, i.e. PAGEABLE, input (the driver stages it through its own pinned buffers)
+            pg_seq = np.ascontiguousarray(flat)
+            pg_off = np.ascontiguousarray(off.astype(np.uint64))
+            seq_ptr, off_ptr = pg_seq.ctypes.data, pg_off.ctypes.data
+            e2e["pageable_input"] = timed(e2e_step_packed, "kmer_cuda_submit_count_packed with PAGEABLE host input (what palloc gives the glue)")
+            seq_ptr, off_ptr = h_seq.data_ptr(), h_off.data_ptr()
         else:
             # sharded e2e: every rank copies its rows from pinned host memory, counts with the all-to-all, and reads
             # its share of the (k-mer,count) table back into pinned host memory
@@ -471,6 +609,7 @@ def main():
             h_uniq = torch.empty(cap, dtype=torch.int64).pin_memory()
             d_uniq = torch.empty(cap, dtype=torch.int64, device="cuda")
             d2h_bytes = [0]
+            e2e_last = [0, 0]
 
             def e2e_step():
                 d_seq.copy_(h_seq, non_blocking=True)
@@ -481,6 +620,7 @@ def main():
                 h_uniq[:nu].copy_(d_uniq[:nu], non_blocking=True)
                 torch.cuda.synchronize()
                 d2h_bytes[0] = 16 * nd + 8 * nu
+                e2e_last[0], e2e_last[1] = nd, nu
                 return nd + nu, int(h_uniq[0]) if nu else 0
 
             e2e_steps = max(1, min(args.steps, 3))
@@ -496,10 +636,22 @@ def main():
             dt = float(dt.item())
             d2h_sum = torch.tensor([d2h_bytes[0]], dtype=torch.int64, device="cuda")
             dist.all_reduce(d2h_sum)
+            e2e_parity = None
+            if not args.no_parity:                               # the HOST copies of the last step against the oracle's checksum
+                nd_h, nu_h = int(e2e_last[0]), int(e2e_last[1])
+                a1, c1 = table_checksum(torch, h_uniq[:nu_h].cuda())
+                hp = h_pairs[:nd_h].cuda()
+                a2, c2 = table_checksum(torch, hp[:, 0], hp[:, 1]) if nd_h else (0, 0)
+                in_sum2, in_n2 = input_checksum(flat, off, K)
+                v = torch.tensor([_s64(in_sum2), in_n2, _s64((a1 + a2) & M64), c1 + c2], dtype=torch.int64, device="cuda")
+                dist.all_reduce(v)
+                e2e_parity = {"checksum_ok": (int(v[0].item()) & M64) == (int(v[2].item()) & M64), "count_ok": int(v[1].item()) == int(v[3].item())}
+                del hp
             e2e = {"value": total_kmers * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": (n_bases + 8 * (n_rows + 1)) * world,
                    "d2h_bytes_per_step": int(d2h_sum.item()), "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
                    "api": "ShardedCounter.count per rank: pinned host rows -> HBM, partition + NCCL all-to-all + refine + bucket count, "
-                          "this rank's share of the table (split format: bare codes + pairs) -> pinned host"}
+                          "this rank's share of the table (split format: bare codes + pairs) -> pinned host",
+                   "parity": e2e_parity}
 
     # ---------------------------------------------------------------- CPU baseline beside it (rank 0, bounded sample)
     cpu = None
@@ -521,10 +673,16 @@ def main():
                        "exchange_bytes_per_gpu_per_step": (sharder.last_exchange_bytes if sharder is not None else 0), "l2": "inputs and tables larger than L2 (no flush needed)",
                        "bases_per_sec": n_bases * world * args.steps / (ms_total * 1e-3)},
             "roofline": roofline, "roofline_kernels": roofline_kernels, "roofline_step": roofline_step, "phases_ms": phases, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": clocks}
+            "parity": parity, "gpu_launches": int(launches), "clocks": clocks}
     if rank == 0:
         print(json.dumps(line), flush=True)
     eng.close()
+    bad = [k for k in ("checksum_ok", "count_ok", "unique_ok") if parity.get(k) is False]
+    for fmt in ([e2e] + [e2e.get("split_format"), e2e.get("pairs_format")] if isinstance(e2e, dict) else []):
+        if isinstance(fmt, dict) and isinstance(fmt.get("parity"), dict):
+            bad += [f"e2e:{k}" for k, v in fmt["parity"].items() if v is False]
+    if bad:
+        raise SystemExit(f"PARITY FAILURE: {bad}")
 
 
 if __name__ == "__main__":

@@ -95,6 +95,10 @@ void kmer_cuda_release(kmer_cuda_ctx *ctx, void *result);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t kmer_cuda_launch_count(const kmer_cuda_ctx *ctx);
 
+/* Test hook (process-wide, not for production use): forces the minimizer window of the partition counter (4/6/8 for k <= 26,
+ * 8/12/16 for k >= 27; 0 = automatic) so that the parity tests cover every window the kernels are built for. */
+void kmer_cuda_test_force_window(int w);
+
 /* Phase timing for benchmarks: when on, CUDA events bracket every kernel phase of a dev_* call;
  * after kmer_cuda_dev_finish(), kmer_cuda_get_phases() returns the phase names (static strings)
  * and their device durations in ms.  Returns the number of phases of the last finished call. */
@@ -184,7 +188,8 @@ typedef struct kmer_dev_result
 int kmer_cuda_dev_extract(kmer_cuda_ctx *ctx, const char *d_seq, uint64_t n_bases, const uint64_t *d_row_off,
 						  uint64_t n_rows, int k, uint64_t *d_codes, uint64_t codes_capacity, void *stream);
 
-/* algo: 0 = automatic, 1 = dense table (k small), 2 = global hash table, 3 = minimizer partition */
+/* algo: 0 = automatic, 1 = dense table (k small), 2 = global hash table, 3 = minimizer partition,
+ * 4 = minimizer partition through two write-combining passes (experimental; falls back to 3 when the job does not suit it) */
 int kmer_cuda_dev_count(kmer_cuda_ctx *ctx, const char *d_seq, uint64_t n_bases, const uint64_t *d_row_off,
 						uint64_t n_rows, int k, kmer_count_pair *d_pairs, uint64_t pairs_capacity, int algo,
 						void *stream);
@@ -263,6 +268,20 @@ int kmer_cuda_dev_dense_table(kmer_cuda_ctx *ctx, const char *d_seq, uint64_t n_
 							  uint64_t n_rows, int k, uint64_t *d_table, void *stream);
 int kmer_cuda_dev_dense_emit(kmer_cuda_ctx *ctx, const uint64_t *d_table, int k, uint32_t rank, uint32_t n_ranks,
 							 kmer_count_pair *d_pairs, uint64_t pairs_capacity, void *stream);
+
+/* Exact fallback of sharded counting for input the minimizer exchange refuses (KMER_ERR_CAPACITY: a segment or the spill
+ * list overflowed -- highly repetitive rows): every rank counts ITS rows with kmer_cuda_dev_count (exact on any input), then
+ * the per-rank tables are merged by owner: owner(k-mer) = hash(k-mer) % n_ranks.  Every rank sees every rank's table in turn
+ * (a broadcast by the caller) and adds the groups it owns:
+ *   kmer_cuda_dev_merge_begin(max_groups)            table for at most max_groups groups owned by this rank
+ *   kmer_cuda_dev_merge_add(table, n, rank, n_ranks) once per source table
+ *   kmer_cuda_dev_merge_emit(k, pairs, capacity)     this rank's groups; kmer_cuda_dev_finish() reports n_distinct / n_kmers
+ * The per-rank results are disjoint, their union is the GROUP BY of all rows (HashAggregate never refuses input:
+ * kmer-tests.sql:1208-1213). */
+int kmer_cuda_dev_merge_begin(kmer_cuda_ctx *ctx, uint64_t max_groups, void *stream);
+int kmer_cuda_dev_merge_add(kmer_cuda_ctx *ctx, const kmer_count_pair *d_pairs, uint64_t n, uint32_t rank, uint32_t n_ranks,
+							void *stream);
+int kmer_cuda_dev_merge_emit(kmer_cuda_ctx *ctx, int k, kmer_count_pair *d_pairs, uint64_t pairs_capacity, void *stream);
 
 /* Upper bound of the number of k-mers (= groups) a batch can produce: n_bases - n_rows*(k-1). */
 uint64_t kmer_cuda_max_kmers(uint64_t n_bases, uint64_t n_rows, int k);

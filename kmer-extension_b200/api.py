@@ -29,7 +29,7 @@ KMER_OK = 0
 KMER_ERR_INVALID_DNA, KMER_ERR_KMER_TOO_LONG, KMER_ERR_INVALID_QKMER, KMER_ERR_INVALID_K, KMER_ERR_QKMER_TOO_LONG = 1, 2, 3, 4, 5
 KMER_ERR_BAD_ARGUMENT, KMER_ERR_CUDA, KMER_ERR_OOM, KMER_ERR_NO_DEVICE, KMER_ERR_CAPACITY = 16, 17, 18, 19, 20
 OP_EQUALS, OP_STARTS_WITH, OP_CONTAINS = 0, 1, 2
-ALGO_AUTO, ALGO_DENSE, ALGO_HASH, ALGO_PARTITION = 0, 1, 2, 3
+ALGO_AUTO, ALGO_DENSE, ALGO_HASH, ALGO_PARTITION, ALGO_TWO_PASS = 0, 1, 2, 3, 4
 
 # every symbol include/kmer_cuda.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
@@ -40,6 +40,7 @@ ABI_SYMBOLS = [
     "kmer_cuda_dev_decode", "kmer_cuda_dev_finish", "kmer_cuda_set_profiling", "kmer_cuda_get_phases",
     "kmer_cuda_shard_plan", "kmer_cuda_dev_shard_partition", "kmer_cuda_dev_shard_count", "kmer_cuda_dev_dense_table",
     "kmer_cuda_dev_dense_emit", "kmer_cuda_submit_count_split", "kmer_cuda_dev_count_split", "kmer_cuda_submit_count_packed", "kmer_cuda_shard_plan_chunked", "kmer_cuda_dev_shard_count_split",
+    "kmer_cuda_dev_merge_begin", "kmer_cuda_dev_merge_add", "kmer_cuda_dev_merge_emit", "kmer_cuda_test_force_window",
 ]
 
 
@@ -110,6 +111,11 @@ def load_library(path: Path = LIB_PATH) -> C.CDLL:
     L.kmer_cuda_dev_shard_count_split.argtypes = [vp, C.POINTER(KmerShardPlan), vp, vp, vp, u64, vp, u64, vp]
     L.kmer_cuda_dev_dense_table.argtypes = [vp, vp, u64, vp, u64, i32, vp, vp]
     L.kmer_cuda_dev_dense_emit.argtypes = [vp, vp, i32, C.c_uint32, C.c_uint32, vp, u64, vp]
+    L.kmer_cuda_test_force_window.argtypes = [i32]
+    L.kmer_cuda_test_force_window.restype = None
+    L.kmer_cuda_dev_merge_begin.argtypes = [vp, u64, vp]
+    L.kmer_cuda_dev_merge_add.argtypes = [vp, vp, u64, C.c_uint32, C.c_uint32, vp]
+    L.kmer_cuda_dev_merge_emit.argtypes = [vp, i32, vp, u64, vp]
     return L
 
 
@@ -346,6 +352,15 @@ class KmerCuda:
         self._check(self.lib.kmer_cuda_dev_shard_count_split(self.ctx, C.byref(plan), d_recv_recs.data_ptr(), d_recv_fill.data_ptr(),
                                                              d_uniq.data_ptr(), d_uniq.numel(), d_pairs.data_ptr(), d_pairs.numel() // 2,
                                                              self._stream_ptr(stream)))
+
+    def dev_merge_begin(self, max_groups: int, stream=None):
+        self._check(self.lib.kmer_cuda_dev_merge_begin(self.ctx, max_groups, self._stream_ptr(stream)))
+
+    def dev_merge_add(self, d_pairs, n: int, rank: int, n_ranks: int, stream=None):
+        self._check(self.lib.kmer_cuda_dev_merge_add(self.ctx, d_pairs.data_ptr(), n, rank, n_ranks, self._stream_ptr(stream)))
+
+    def dev_merge_emit(self, k: int, d_pairs, stream=None):
+        self._check(self.lib.kmer_cuda_dev_merge_emit(self.ctx, k, d_pairs.data_ptr(), d_pairs.numel() // 2, self._stream_ptr(stream)))
 
     def dev_dense_table(self, d_seq, n_bases: int, d_off, n_rows: int, k: int, d_table, stream=None):
         self._check(self.lib.kmer_cuda_dev_dense_table(self.ctx, d_seq.data_ptr(), n_bases, d_off.data_ptr(), n_rows, k,

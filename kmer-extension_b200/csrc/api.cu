@@ -27,7 +27,7 @@ struct PinnedBuf {
     bool in_use;
 };
 
-enum PendingOp { OP_NONE = 0, OP_EXTRACT, OP_COUNT, OP_MATCH, OP_DECODE, OP_ENCODE, OP_SHARD_PART, OP_SHARD_COUNT, OP_DENSE_TABLE };
+enum PendingOp { OP_NONE = 0, OP_EXTRACT, OP_COUNT, OP_MATCH, OP_DECODE, OP_ENCODE, OP_SHARD_PART, OP_SHARD_COUNT, OP_DENSE_TABLE, OP_MERGE };
 
 }  // namespace
 
@@ -38,8 +38,13 @@ struct kmer_cuda_ctx {
     uint64_t launches = 0;
     DevStatus* d_status = nullptr;
     DevStatus* h_status = nullptr;  // pinned
+    // host-buffer submit: copies run on their own streams beside the kernels (kmer_cuda_submit_count*)
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[8] = {}, ev_leaf[16] = {}, ev_off = nullptr;
+    DevStatus* h_ring = nullptr;    // pinned: status snapshots behind every group of buckets
     // device workspaces, grown on demand and kept between calls
     Buf seq, off, mask, tile_row, table, consts, ops, codes, pairs, bits, hits, lens, text, fill, recs, spill, failed, seg, segfill;
+    uint64_t merge_slots = 0;     // table slots of the merge in progress (kmer_cuda_dev_merge_*)
     uint64_t last_tier2 = 0;      // k-mers counted by the tier-2 kernel in the last count
     uint64_t last_overflow = 0;   // k-mers the partition counter could not place (batch was recounted)
     std::vector<PinnedBuf> pinned;
@@ -48,6 +53,12 @@ struct kmer_cuda_ctx {
     uint64_t p_n_bases = 0, p_n_rows = 0;
     int p_k = 0;
     uint64_t p_expected_kmers = 0;
+    // a partition count whose tiers overflowed is recounted by kmer_cuda_dev_finish through the global hash table
+    bool p_recountable = false;
+    const char* p_seq = nullptr;
+    const uint64_t* p_off = nullptr;
+    kmer_count_pair* p_pairs = nullptr;
+    uint64_t p_pairs_cap = 0;
     // optional phase timing (bench.py's per-kernel roofline): events recorded after each phase
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -197,6 +208,8 @@ __global__ void status_reset_kernel(DevStatus* s) {
     s->n_failed = 0;
     s->failed_kmers = 0;
     s->n_unique = 0;
+    s->t2_mode = 0;
+    s->t2_slots = 0;
 }
 
 // pad := row containing bad_char_pos (so the host never needs the offsets)
@@ -344,6 +357,12 @@ extern "C" void kmer_cuda_shutdown(kmer_cuda_ctx* c) {
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->d_status) cudaFree(c->d_status);
     if (c->h_status) cudaFreeHost(c->h_status);
+    if (c->h_ring) cudaFreeHost(c->h_ring);
+    for (auto e : c->ev_in) if (e) cudaEventDestroy(e);
+    for (auto e : c->ev_leaf) if (e) cudaEventDestroy(e);
+    if (c->ev_off) cudaEventDestroy(c->ev_off);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -372,6 +391,8 @@ extern "C" int kmer_cuda_get_phases(const kmer_cuda_ctx* c, const char** names, 
 
 extern "C" uint64_t kmer_cuda_launch_count(const kmer_cuda_ctx* c) { return c ? c->launches : 0; }
 
+extern "C" void kmer_cuda_test_force_window(int w) { partition_force_window(w); }
+
 extern "C" uint64_t kmer_cuda_max_kmers(uint64_t n_bases, uint64_t n_rows, int k) {
     if (k < 1 || k > KMER_CUDA_MAX_K) return 0;
     uint64_t sub = n_rows * (uint64_t)(k - 1);
@@ -383,7 +404,8 @@ extern "C" uint64_t kmer_cuda_max_kmers(uint64_t n_bases, uint64_t n_rows, int k
 
 // stream argument of the C ABI: NULL = the CUDA default stream (what a caller that never created a
 // stream is using); KMER_OWN_STREAM = the context's private stream (used by the submit_* calls).
-#define KMER_OWN_STREAM ((void*)(uintptr_t)1)
+static const char kOwnStreamTag = 0;                  // its ADDRESS is the sentinel: no CUDA stream handle can equal it
+#define KMER_OWN_STREAM ((void*)&kOwnStreamTag)         // ((void*)1 would be cudaStreamLegacy)
 static cudaStream_t pick_stream(kmer_cuda_ctx* c, void* stream) {
     return stream == KMER_OWN_STREAM ? c->stream : (cudaStream_t)stream;
 }
@@ -395,6 +417,7 @@ static int begin_op(kmer_cuda_ctx* c, cudaStream_t st) {
     status_reset_kernel<<<1, 1, 0, st>>>(c->d_status);
     c->launches++;
     c->pending = OP_NONE;
+    c->p_recountable = false;
     return KMER_OK;
 }
 
@@ -486,17 +509,22 @@ static int dev_count_impl(kmer_cuda_ctx* c, const char* d_seq, uint64_t n_bases,
     if (algo == 0) algo = (k <= 13) ? 1 : 3;
     c->last_overflow = 0;
     c->last_tier2 = 0;
-    if (algo == 3) {
+    if (algo == 3 || algo == 4) {
         if (k < 14) return bad_arg(c, "minimizer-partition counting needs k >= 14");
         PartitionPlan plan = make_partition_plan(c->p_expected_kmers, k);
         ScatterPlan sp{};
-        const bool two_pass = make_scatter_plan(c->di, n_bases, c->p_expected_kmers, plan, sp);
+        // algo 4: the two write-combining passes of scatter.cuh instead of partition_kernel's scattered record stores.  Measured
+        // (1 GB, k=21): 4.2 + 2.4 ms against 6.5 ms -- no gain yet (both passes are instruction bound), so it is opt-in.
+        const bool two_pass = algo == 4 && make_scatter_plan(c->di, n_bases, c->p_expected_kmers, plan, sp);
         rc = ws(c, c->fill, (size_t)plan.n_buckets * 8);
         if (!rc) rc = ws(c, c->recs, partition_record_bytes(plan));
         if (!rc) rc = ws(c, c->spill, partition_spill_bytes(plan));
         if (!rc) rc = ws(c, c->failed, (size_t)plan.n_buckets * 4);
         if (!rc && two_pass) rc = ws(c, c->seg, scatter_seg_bytes(plan, sp));
         if (!rc && two_pass) rc = ws(c, c->segfill, scatter_segfill_bytes(sp));
+        if (rc) return rc;
+        const uint64_t t2_slots = tier2_table_slots(c->p_expected_kmers);
+        rc = ws(c, c->table, t2_slots * sizeof(kmer_count_pair));
         if (rc) return rc;
         MarkArg ma{c, st};
         if (two_pass) {
@@ -511,37 +539,14 @@ static int dev_count_impl(kmer_cuda_ctx* c, const char* d_seq, uint64_t n_bases,
                                    d_pairs, pairs_capacity, d_uniq, uniq_capacity, st, mark_cb, &ma);
             c->launches += 2;
         }
-        // Did everything fit?  (One host round trip; skewed input needs tier 2 or a full recount.)
-        CU(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, st), "D2H status");
-        CU(cudaStreamSynchronize(st), "stream sync");
-        const DevStatus hs = *c->h_status;
-        if (hs.bad_char_pos != kNoError || hs.short_row != kNoError) {
-            algo = -1;  // failing with an input error that finish() reports
-        } else if (hs.n_overflow != 0) {
-            c->last_overflow = hs.n_overflow;        // tier 3: recount the batch through the global hash table
-            status_reset_kernel<<<1, 1, 0, st>>>(c->d_status);
-            c->launches++;
-            algo = 2;
-        } else {
-            if (hs.n_failed || hs.n_spill) {         // tier 2: only the buckets that did not fit
-                uint64_t n_slots = next_pow2(std::max<uint64_t>(1024, (hs.failed_kmers + hs.n_spill * 16) * 2));
-                rc = ws(c, c->table, n_slots * sizeof(kmer_count_pair));
-                if (rc) return rc;
-                launch_hash_clear((kmer_count_pair*)c->table.p, n_slots, st);
-                launch_partition_tier2(c->di, plan, k, 1, (const unsigned long long*)c->fill.p, c->recs.p, c->spill.p,
-                                       (const uint32_t*)c->failed.p, (kmer_count_pair*)c->table.p, n_slots, c->d_status, st);
-                mark(c, st, "tier2_insert");
-                // compaction appends the table and the k==32 special key and adds both to n_kmers
-                launch_hash_compact(c->di, (const kmer_count_pair*)c->table.p, n_slots, k, d_pairs, pairs_capacity, c->d_status, st);
-                mark(c, st, "tier2_compact");
-                c->launches += 2;
-                c->last_tier2 = hs.failed_kmers;
-            } else {
-                launch_append_special(d_pairs, pairs_capacity, c->d_status, st);
-                c->launches++;
-            }
-            algo = -1;
-        }
+        // Tier 2 (buckets that did not fit on chip, spilled records) is decided and run by the device: nothing here waits
+        // for the GPU.  Only a batch that overflows even that (DevStatus::n_overflow) is recounted, by kmer_cuda_dev_finish.
+        launch_partition_tier2(c->di, plan, k, (const unsigned long long*)c->fill.p, c->recs.p, c->spill.p, (const uint32_t*)c->failed.p,
+                               (kmer_count_pair*)c->table.p, t2_slots, d_pairs, pairs_capacity, c->d_status, st, mark_cb, &ma);
+        c->launches += 4;
+        c->p_recountable = true;
+        c->p_seq = d_seq; c->p_off = d_row_off; c->p_pairs = d_pairs; c->p_pairs_cap = pairs_capacity;
+        algo = -1;
     }
     if (algo == 1) {
         if (k > 15) return bad_arg(c, "dense counting needs k <= 15");
@@ -676,9 +681,38 @@ extern "C" int kmer_cuda_dev_finish(kmer_cuda_ctx* c, void* stream, kmer_dev_res
         result->n_distinct = 0;
         result->n_overflow = 0;
         result->n_tier2 = 0;
+        result->n_unique = 0;
     }
     PendingOp op = c->pending;
     c->pending = OP_NONE;
+    if (op == OP_COUNT && c->p_recountable) {
+        c->p_recountable = false;
+        c->last_tier2 = s.t2_mode == 1ull ? s.failed_kmers + s.n_spill : 0;
+        if (s.n_overflow != 0 && s.bad_char_pos == kNoError && s.short_row == kNoError) {
+            // tier 3: even the spill list / the tier-2 table overflowed (highly repetitive input): everything written so far is
+            // discarded and the batch is recounted through the global hash table.  The row mask of the batch is still in place.
+            c->last_overflow = s.n_overflow;
+            const int k = c->p_k;
+            uint64_t maxd = c->p_expected_kmers;
+            if (k < 32 && (1ull << (2 * k)) < maxd) maxd = 1ull << (2 * k);
+            const uint64_t n_slots = next_pow2(std::max<uint64_t>(1024, maxd * 2));
+            int rc = ws(c, c->table, n_slots * sizeof(kmer_count_pair));
+            if (rc) return rc;
+            ScanArgs a;
+            a.seq = reinterpret_cast<const uint8_t*>(c->p_seq);
+            a.n_bases = c->p_n_bases;
+            a.row_mask = (const uint32_t*)c->mask.p;
+            a.k = k;
+            a.status = c->d_status;
+            status_reset_kernel<<<1, 1, 0, st>>>(c->d_status);
+            launch_hash_clear((kmer_count_pair*)c->table.p, n_slots, st);
+            launch_count_hash_insert(c->di, a, (kmer_count_pair*)c->table.p, n_slots, st);
+            launch_hash_compact(c->di, (const kmer_count_pair*)c->table.p, n_slots, k, c->p_pairs, c->p_pairs_cap, c->d_status, st);
+            c->launches += 3;
+            CU(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, st), "D2H status");
+            CU(cudaStreamSynchronize(st), "stream sync");
+        }
+    }
     if (op == OP_EXTRACT || op == OP_COUNT) {
         // the first offending row decides; on the same row dna_in (text -> dna) precedes generate_kmers
         uint64_t bad_row = s.bad_char_pos == kNoError ? kNoError : s.pad;
@@ -706,14 +740,24 @@ extern "C" int kmer_cuda_dev_finish(kmer_cuda_ctx* c, void* stream, kmer_dev_res
     } else if (op == OP_SHARD_COUNT) {
         if (s.out_overflow)
             return set_error(&c->err, KMER_ERR_CAPACITY, "XX000", "kmer_cuda: output buffer too small", "", -1);
-        if (c->last_overflow)
+        if (s.n_overflow)
             return set_error(&c->err, KMER_ERR_CAPACITY, "XX000",
                              "kmer_cuda: the spill list overflowed (input too repetitive for the sharded partition path)", "", -1);
+        c->last_tier2 = s.t2_mode == 1ull ? s.failed_kmers + s.n_spill : 0;
         if (result) {
             result->n_kmers = s.n_kmers;
             result->n_distinct = s.n_distinct;
             result->n_tier2 = c->last_tier2;
             result->n_unique = s.n_unique;
+        }
+    } else if (op == OP_MERGE) {
+        if (s.out_overflow)
+            return set_error(&c->err, KMER_ERR_CAPACITY, "XX000", "kmer_cuda: output buffer too small", "", -1);
+        if (s.n_overflow)
+            return set_error(&c->err, KMER_ERR_CAPACITY, "XX000", "kmer_cuda: merge table full (max_groups too small)", "", -1);
+        if (result) {
+            result->n_kmers = s.n_kmers;
+            result->n_distinct = s.n_distinct;
         }
     } else if (op == OP_ENCODE) {
         if (s.bad_char_pos != kNoError) return ref_error(&c->err, KMER_ERR_INVALID_DNA, (int64_t)s.bad_char_pos);
@@ -770,7 +814,6 @@ static PartitionPlan coarse_partition_plan(const kmer_shard_plan* sp) {
     p.cap = sp->cap;
     p.w = sp->w; p.m = sp->m; p.recw = sp->recw; p.rmax = sp->rmax;
     p.spill_cap = 0;   // no spill list on the source side: a full segment is an error reported by finish()
-    p.debug = 0;
     return p;
 }
 // the owner side: this GPU's fine buckets (local numbering), counted like a single-GPU batch
@@ -783,7 +826,6 @@ static PartitionPlan fine_partition_plan(const kmer_shard_plan* sp) {
     p.w = sp->w; p.m = sp->m; p.recw = sp->recw; p.rmax = sp->rmax;
     uint64_t sc = (uint64_t)p.n_buckets * p.cap / 8;
     p.spill_cap = sc < 4096 ? 4096 : sc;
-    p.debug = 0;
     return p;
 }
 
@@ -841,27 +883,14 @@ static int dev_shard_count_impl(kmer_cuda_ctx* c, const kmer_shard_plan* sp, con
                         pairs_capacity, d_uniq, d_uniq ? uniq_capacity : 0, c->d_status, st);
     mark(c, st, "bucket_count");
     c->launches += 2;
-    CU(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, st), "D2H status");
-    CU(cudaStreamSynchronize(st), "stream sync");
-    const DevStatus hs = *c->h_status;
-    if (hs.n_overflow != 0) {
-        c->last_overflow = hs.n_overflow;   // even the spill list overflowed: reported by finish() as KMER_ERR_CAPACITY
-    } else if (hs.n_failed || hs.n_spill) {   // tier 2: only the buckets that did not fit on chip
-        uint64_t n_slots = next_pow2(std::max<uint64_t>(1024, (hs.failed_kmers + hs.n_spill * 16) * 2));
-        rc = ws(c, c->table, n_slots * sizeof(kmer_count_pair));
-        if (rc) return rc;
-        launch_hash_clear((kmer_count_pair*)c->table.p, n_slots, st);
-        launch_partition_tier2(c->di, plan, k, 1, (const unsigned long long*)c->fill.p, c->recs.p, c->spill.p,
-                               (const uint32_t*)c->failed.p, (kmer_count_pair*)c->table.p, n_slots, c->d_status, st);
-        mark(c, st, "tier2_insert");
-        launch_hash_compact(c->di, (const kmer_count_pair*)c->table.p, n_slots, k, d_pairs, pairs_capacity, c->d_status, st);
-        mark(c, st, "tier2_compact");
-        c->launches += 2;
-        c->last_tier2 = hs.failed_kmers;
-    } else {
-        launch_append_special(d_pairs, pairs_capacity, c->d_status, st);
-        c->launches++;
-    }
+    // tier 2 is decided and run by the device (no host round trip); an overflow of even that is reported by finish()
+    const uint64_t t2_slots = tier2_table_slots((uint64_t)plan.n_buckets * 1200ull);
+    rc = ws(c, c->table, t2_slots * sizeof(kmer_count_pair));
+    if (rc) return rc;
+    MarkArg ma{c, st};
+    launch_partition_tier2(c->di, plan, k, (const unsigned long long*)c->fill.p, c->recs.p, c->spill.p, (const uint32_t*)c->failed.p,
+                           (kmer_count_pair*)c->table.p, t2_slots, d_pairs, pairs_capacity, c->d_status, st, mark_cb, &ma);
+    c->launches += 4;
     CU(cudaGetLastError(), "shard count launch");
     return KMER_OK;
 }
@@ -926,6 +955,47 @@ extern "C" int kmer_cuda_dev_dense_emit(kmer_cuda_ctx* c, const uint64_t* d_tabl
 }
 
 // ------------------------------------------------------------------------------------------------
+// merge of (k-mer, count) tables by owner (the exact fallback of sharded counting)
+
+extern "C" int kmer_cuda_dev_merge_begin(kmer_cuda_ctx* c, uint64_t max_groups, void* stream) {
+    if (!c) return KMER_ERR_BAD_ARGUMENT;
+    cudaStream_t st = pick_stream(c, stream);
+    int rc = begin_op(c, st);
+    if (rc) return rc;
+    c->pending = OP_MERGE;
+    c->merge_slots = next_pow2(std::max<uint64_t>(1024, max_groups * 2));
+    rc = ws(c, c->table, c->merge_slots * sizeof(kmer_count_pair));
+    if (rc) return rc;
+    launch_hash_clear((kmer_count_pair*)c->table.p, c->merge_slots, st);
+    CU(cudaGetLastError(), "merge begin");
+    return KMER_OK;
+}
+
+extern "C" int kmer_cuda_dev_merge_add(kmer_cuda_ctx* c, const kmer_count_pair* d_pairs, uint64_t n, uint32_t rank, uint32_t n_ranks,
+                                       void* stream) {
+    if (!c) return KMER_ERR_BAD_ARGUMENT;
+    if (c->pending != OP_MERGE) return bad_arg(c, "kmer_cuda_dev_merge_add without kmer_cuda_dev_merge_begin");
+    if (n_ranks < 1 || rank >= n_ranks) return bad_arg(c, "merge: rank < n_ranks");
+    cudaStream_t st = pick_stream(c, stream);
+    CU(cudaSetDevice(c->di.device), "cudaSetDevice");
+    launch_merge_pairs(c->di, d_pairs, n, rank, n_ranks, (kmer_count_pair*)c->table.p, c->merge_slots, c->d_status, st);
+    c->launches++;
+    CU(cudaGetLastError(), "merge add");
+    return KMER_OK;
+}
+
+extern "C" int kmer_cuda_dev_merge_emit(kmer_cuda_ctx* c, int k, kmer_count_pair* d_pairs, uint64_t pairs_capacity, void* stream) {
+    if (!c) return KMER_ERR_BAD_ARGUMENT;
+    if (c->pending != OP_MERGE) return bad_arg(c, "kmer_cuda_dev_merge_emit without kmer_cuda_dev_merge_begin");
+    cudaStream_t st = pick_stream(c, stream);
+    CU(cudaSetDevice(c->di.device), "cudaSetDevice");
+    launch_hash_compact(c->di, (const kmer_count_pair*)c->table.p, c->merge_slots, k, d_pairs, pairs_capacity, c->d_status, st);
+    c->launches++;
+    CU(cudaGetLastError(), "merge emit");
+    return KMER_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // host-buffer batch submit
 
 static int h2d(kmer_cuda_ctx* c, void* dst, const void* src, size_t bytes, cudaStream_t st) {
@@ -977,34 +1047,253 @@ extern "C" int kmer_cuda_submit_extract(kmer_cuda_ctx* c, const char* seq, const
     return KMER_OK;
 }
 
+// ---- GROUP BY through host buffers: one implementation for the three result formats ------------------------------------------
+enum CountFormat { FMT_PAIRS = 0, FMT_SPLIT = 1, FMT_PACKED = 2 };
+
+struct CountOut {              // what the three entry points hand back
+    void* uniq = nullptr;      // SPLIT: uint64 codes; PACKED: code_bytes-byte integers
+    uint64_t n_unique = 0;
+    int code_bytes = 0;
+    kmer_count_pair* pairs = nullptr;
+    uint64_t n_pairs = 0, n_kmers = 0;
+};
+
+// a pinned result buffer that goes back to the pool unless it is handed to the caller (no leak on any error return)
+struct PinGuard {
+    kmer_cuda_ctx* c;
+    void* p = nullptr;
+    explicit PinGuard(kmer_cuda_ctx* c_) : c(c_) {}
+    ~PinGuard() { if (p) kmer_cuda_release(c, p); }
+    void* take() { void* r = p; p = nullptr; return r; }
+};
+
+static int ensure_copy_streams(kmer_cuda_ctx* c) {
+    if (c->s_in) return KMER_OK;
+    CU(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking), "cudaStreamCreate");
+    CU(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (auto& e : c->ev_in) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+    for (auto& e : c->ev_leaf) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+    CU(cudaEventCreateWithFlags(&c->ev_off, cudaEventDisableTiming), "cudaEventCreate");
+    CU(cudaHostAlloc((void**)&c->h_ring, sizeof(DevStatus) * 16, cudaHostAllocDefault), "cudaHostAlloc");
+    return KMER_OK;
+}
+
+// The whole table (any tier, any algorithm) -> pinned host memory after everything is counted: the plain sequence
+// upload, count, download.  Used for small batches, k <= 13, and after a tier-3 recount.
+static int download_count_result(kmer_cuda_ctx* c, int k, CountFormat fmt, const kmer_dev_result& res, CountOut* o) {
+    PinGuard gu(c), gp(c);
+    const int nbytes = k >= 1 ? (2 * k + 7) / 8 : 1;
+    if (fmt != FMT_PAIRS) {
+        const size_t ub = (size_t)res.n_unique * (fmt == FMT_PACKED ? (size_t)nbytes : 8);
+        if (fmt == FMT_PACKED) {
+            int rc = ws(c, c->text, ub + 16);
+            if (rc) return rc;
+            launch_pack_codes(c->di, (const uint64_t*)c->codes.p, res.n_unique, nbytes, (uint8_t*)c->text.p, c->stream);
+            c->launches++;
+        }
+        gu.p = pinned_get(c, ub);
+        if (!gu.p) return c->err.status;
+        CU(cudaMemcpyAsync(gu.p, fmt == FMT_PACKED ? c->text.p : c->codes.p, ub, cudaMemcpyDeviceToHost, c->stream), "D2H codes");
+    }
+    gp.p = pinned_get(c, res.n_distinct * sizeof(kmer_count_pair));
+    if (!gp.p) return c->err.status;
+    CU(cudaMemcpyAsync(gp.p, c->pairs.p, res.n_distinct * sizeof(kmer_count_pair), cudaMemcpyDeviceToHost, c->stream), "D2H pairs");
+    CU(cudaStreamSynchronize(c->stream), "stream sync");
+    o->uniq = gu.take();
+    o->n_unique = fmt == FMT_PAIRS ? 0 : res.n_unique;
+    o->code_bytes = fmt == FMT_PACKED ? nbytes : (fmt == FMT_SPLIT ? 8 : 0);
+    o->pairs = (kmer_count_pair*)gp.take();
+    o->n_pairs = res.n_distinct;
+    o->n_kmers = res.n_kmers;
+    return KMER_OK;
+}
+
+// Replaces the scan + HashAggregate of a whole column (kmer.c:289-351 + kmer_hash/kmer_equals) from HOST buffers.  For
+// 14 <= k <= 32 the three legs overlap: the column arrives in pieces on a copy stream while the pieces already there are
+// partitioned; the buckets are counted in groups, and behind every group the part of the result that is final leaves on a
+// second copy stream (PCIe is the bound of this call: the kernels hide under the copies).
+static int submit_count_common(kmer_cuda_ctx* c, const char* seq, const uint64_t* row_off, uint64_t n_rows, int k, CountFormat fmt,
+                               CountOut* o) {
+    CU(cudaSetDevice(c->di.device), "cudaSetDevice");
+    if (n_rows && !row_off) return bad_arg(c, "row_off");
+    const uint64_t n_bases = n_rows ? row_off[n_rows] : 0;
+    if (n_rows && row_off[0] != 0) return bad_arg(c, "row_off[0] must be 0");
+    if (n_bases && !seq) return bad_arg(c, "seq");
+    int rc = ws(c, c->seq, ((n_bases + 15) & ~15ull) + 64);
+    if (!rc) rc = ws(c, c->off, (n_rows + 1) * 8);
+    if (rc) return rc;
+    uint64_t cap = kmer_cuda_max_kmers(n_bases, n_rows, k);
+    if (k >= 1 && k < 32 && (1ull << (2 * k)) < cap) cap = 1ull << (2 * k);
+    // a k-mer that is not unique occurs at least twice: at most cap/2 pairs next to the unique codes -- unless a fallback
+    // tier (which writes pairs only) takes over, so the pair buffer keeps the full size
+    rc = ws(c, c->pairs, cap * sizeof(kmer_count_pair));
+    if (!rc && fmt != FMT_PAIRS) rc = ws(c, c->codes, cap * sizeof(uint64_t));
+    if (rc) return rc;
+    const bool pipelined = k >= 14 && k <= KMER_CUDA_MAX_K && n_rows && n_bases >= (4ull << 20);
+    kmer_dev_result res;
+    if (!pipelined) {
+        rc = h2d(c, c->seq.p, seq, n_bases, c->stream);
+        if (!rc && n_rows) rc = h2d(c, c->off.p, row_off, (n_rows + 1) * 8, c->stream);
+        if (rc) return rc;
+        if (fmt == FMT_PAIRS)
+            rc = kmer_cuda_dev_count(c, (const char*)c->seq.p, n_bases, (const uint64_t*)c->off.p, n_rows, k, (kmer_count_pair*)c->pairs.p, cap,
+                                     0, KMER_OWN_STREAM);
+        else
+            rc = kmer_cuda_dev_count_split(c, (const char*)c->seq.p, n_bases, (const uint64_t*)c->off.p, n_rows, k, (uint64_t*)c->codes.p, cap,
+                                           (kmer_count_pair*)c->pairs.p, cap, KMER_OWN_STREAM);
+        if (rc) return rc;
+        rc = kmer_cuda_dev_finish(c, KMER_OWN_STREAM, &res);
+        if (rc) return rc;
+        return download_count_result(c, k, fmt, res, o);
+    }
+
+    // ---------------------------------------------------------------- pipelined: copy-in | kernels | copy-out
+    rc = ensure_copy_streams(c);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    const char* d_seq = (const char*)c->seq.p;
+    const uint64_t* d_off = (const uint64_t*)c->off.p;
+    kmer_count_pair* d_pairs = (kmer_count_pair*)c->pairs.p;
+    uint64_t* d_uniq = fmt == FMT_PAIRS ? nullptr : (uint64_t*)c->codes.p;
+    const int nbytes = (2 * k + 7) / 8;
+    const size_t ubytes = fmt == FMT_PACKED ? (size_t)nbytes : 8;
+    if (fmt == FMT_PACKED) {
+        rc = ws(c, c->text, cap * ubytes + 16);
+        if (rc) return rc;
+    }
+    // the result buffer the final ranges stream into: sized for the most the batch can produce
+    PinGuard gout(c);
+    gout.p = pinned_get(c, fmt == FMT_PAIRS ? cap * sizeof(kmer_count_pair) : cap * ubytes);
+    if (!gout.p) return c->err.status;
+    // 1. offsets first: the row mask needs nothing else
+    CU(cudaMemcpyAsync(c->off.p, row_off, (n_rows + 1) * 8, cudaMemcpyHostToDevice, c->s_in), "H2D offsets");
+    CU(cudaEventRecord(c->ev_off, c->s_in), "event");
+    CU(cudaStreamWaitEvent(st, c->ev_off, 0), "wait");
+    rc = begin_op(c, st);
+    if (rc) return rc;
+    c->pending = OP_COUNT;
+    c->p_n_bases = n_bases; c->p_n_rows = n_rows; c->p_k = k;
+    c->p_expected_kmers = kmer_cuda_max_kmers(n_bases, n_rows, k);
+    c->last_overflow = 0;
+    c->last_tier2 = 0;
+    ScanArgs a;
+    rc = prepare_rows(c, d_off, n_bases, n_rows, k, st, &a, d_seq);
+    if (rc) return rc;
+    PartitionPlan plan = make_partition_plan(c->p_expected_kmers, k);
+    rc = ws(c, c->fill, (size_t)plan.n_buckets * 8);
+    if (!rc) rc = ws(c, c->recs, partition_record_bytes(plan));
+    if (!rc) rc = ws(c, c->spill, partition_spill_bytes(plan));
+    if (!rc) rc = ws(c, c->failed, (size_t)plan.n_buckets * 4);
+    const uint64_t t2_slots = tier2_table_slots(c->p_expected_kmers);
+    if (!rc) rc = ws(c, c->table, t2_slots * sizeof(kmer_count_pair));
+    if (rc) return rc;
+    CU(cudaMemsetAsync(c->fill.p, 0, (size_t)plan.n_buckets * 8, st), "memset fill");
+    // 2. the column in pieces: piece i is partitioned while piece i+1 crosses PCIe (a piece ends on a tile boundary and is
+    //    copied with the 64 bytes behind it, which its last windows read)
+    const uint64_t n_tiles = (n_bases + TILE - 1) / TILE;
+    const int n_pieces = n_tiles >= 8 ? 8 : 1;
+    for (int i = 0; i < n_pieces; i++) {
+        const uint64_t t0 = n_tiles * i / n_pieces, t1 = n_tiles * (i + 1) / n_pieces;
+        const uint64_t b0 = t0 * TILE, b1 = std::min<uint64_t>(n_bases, t1 * TILE), be = std::min<uint64_t>(n_bases, b1 + 64);
+        CU(cudaMemcpyAsync((char*)c->seq.p + b0, seq + b0, be - b0, cudaMemcpyHostToDevice, c->s_in), "H2D column");
+        CU(cudaEventRecord(c->ev_in[i], c->s_in), "event");
+        CU(cudaStreamWaitEvent(st, c->ev_in[i], 0), "wait");
+        a.tile_begin = t0;
+        a.tile_end = t1;
+        launch_partition(c->di, a, plan, (unsigned long long*)c->fill.p, c->recs.p, c->spill.p, st, false);
+        c->launches++;
+    }
+    mark(c, st, "minimizer_partition");
+    // 3. the buckets in groups; behind every group a snapshot of the result cursors
+    const int n_groups = plan.n_buckets >= 4096 ? 8 : 1;
+    for (int g = 0; g < n_groups; g++) {
+        const uint32_t g0 = (uint32_t)((uint64_t)plan.n_buckets * g / n_groups), g1 = (uint32_t)((uint64_t)plan.n_buckets * (g + 1) / n_groups);
+        launch_bucket_count(c->di, plan, k, (const unsigned long long*)c->fill.p, c->recs.p, c->spill.p, (uint32_t*)c->failed.p, d_pairs,
+                            cap, d_uniq, d_uniq ? cap : 0, c->d_status, st, g0, g1);
+        c->launches++;
+        CU(cudaMemcpyAsync(&c->h_ring[g], c->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, st), "D2H status");
+        CU(cudaEventRecord(c->ev_leaf[g], st), "event");
+    }
+    mark(c, st, "bucket_count");
+    MarkArg ma{c, st};
+    launch_partition_tier2(c->di, plan, k, (const unsigned long long*)c->fill.p, c->recs.p, c->spill.p, (const uint32_t*)c->failed.p,
+                           (kmer_count_pair*)c->table.p, t2_slots, d_pairs, cap, c->d_status, st, mark_cb, &ma);
+    resolve_bad_row_kernel<<<1, 1, 0, st>>>(c->d_status, d_off, n_rows);
+    c->launches += 5;
+    CU(cudaGetLastError(), "count launch");
+    c->p_recountable = true;
+    c->p_seq = d_seq; c->p_off = d_off; c->p_pairs = d_pairs; c->p_pairs_cap = cap;
+    // 4. while later groups are counted, what the finished ones wrote leaves (everything below a snapshot's cursor is final)
+    uint64_t done = 0;                                             // entries of the streamed array already on their way
+    bool input_error = false;
+    for (int g = 0; g < n_groups && !input_error; g++) {
+        CU(cudaEventSynchronize(c->ev_leaf[g]), "event sync");
+        const DevStatus& hs = c->h_ring[g];
+        if (hs.bad_char_pos != kNoError || hs.short_row != kNoError || hs.out_overflow) { input_error = true; break; }
+        const uint64_t cur = fmt == FMT_PAIRS ? hs.n_distinct : hs.n_unique;
+        if (cur <= done) continue;
+        CU(cudaStreamWaitEvent(c->s_out, c->ev_leaf[g], 0), "wait");
+        if (fmt == FMT_PACKED) {
+            const uint64_t p0 = done & ~1023ull;                   // the pack kernel works in steps of 1024 codes
+            launch_pack_codes(c->di, d_uniq + p0, cur - p0, nbytes, (uint8_t*)c->text.p + p0 * ubytes, c->s_out);
+            c->launches++;
+            CU(cudaMemcpyAsync((char*)gout.p + p0 * ubytes, (char*)c->text.p + p0 * ubytes, (cur - p0) * ubytes, cudaMemcpyDeviceToHost, c->s_out),
+               "D2H packed codes");
+        } else if (fmt == FMT_SPLIT) {
+            CU(cudaMemcpyAsync((uint64_t*)gout.p + done, d_uniq + done, (cur - done) * 8, cudaMemcpyDeviceToHost, c->s_out), "D2H codes");
+        } else {
+            CU(cudaMemcpyAsync((kmer_count_pair*)gout.p + done, d_pairs + done, (cur - done) * sizeof(kmer_count_pair), cudaMemcpyDeviceToHost,
+                               c->s_out), "D2H pairs");
+        }
+        done = cur;
+    }
+    // 5. the end of the kernels: input errors, tier 2's groups, or a tier-3 recount
+    rc = kmer_cuda_dev_finish(c, KMER_OWN_STREAM, &res);
+    if (rc) {
+        cudaStreamSynchronize(c->s_out);
+        return rc;
+    }
+    if (res.n_overflow) {                                          // recounted: what left so far is void
+        CU(cudaStreamSynchronize(c->s_out), "stream sync");
+        return download_count_result(c, k, fmt, res, o);
+    }
+    PinGuard gp(c);
+    if (fmt == FMT_PAIRS) {
+        if (res.n_distinct > done)                                 // tier 2's groups and the k == 32 special key
+            CU(cudaMemcpyAsync((kmer_count_pair*)gout.p + done, d_pairs + done, (res.n_distinct - done) * sizeof(kmer_count_pair),
+                               cudaMemcpyDeviceToHost, c->s_out), "D2H pairs");
+    } else {
+        gp.p = pinned_get(c, res.n_distinct * sizeof(kmer_count_pair));
+        if (!gp.p) { cudaStreamSynchronize(c->s_out); return c->err.status; }
+        CU(cudaMemcpyAsync(gp.p, d_pairs, res.n_distinct * sizeof(kmer_count_pair), cudaMemcpyDeviceToHost, c->s_out), "D2H pairs");
+    }
+    CU(cudaStreamSynchronize(c->s_out), "stream sync");
+    if (fmt == FMT_PAIRS) {
+        o->pairs = (kmer_count_pair*)gout.take();
+        o->n_pairs = res.n_distinct;
+    } else {
+        o->uniq = gout.take();
+        o->n_unique = res.n_unique;
+        o->code_bytes = (int)ubytes;
+        o->pairs = (kmer_count_pair*)gp.take();
+        o->n_pairs = res.n_distinct;
+    }
+    o->n_kmers = res.n_kmers;
+    return KMER_OK;
+}
+
 extern "C" int kmer_cuda_submit_count(kmer_cuda_ctx* c, const char* seq, const uint64_t* row_off, uint64_t n_rows, int k,
                                       kmer_count_pair** pairs, uint64_t* n_distinct, uint64_t* n_kmers) {
     if (!c || !pairs || !n_distinct) return KMER_ERR_BAD_ARGUMENT;
     *pairs = nullptr;
     *n_distinct = 0;
     if (n_kmers) *n_kmers = 0;
-    CU(cudaSetDevice(c->di.device), "cudaSetDevice");
-    uint64_t n_bases = 0;
-    int rc = upload_rows(c, seq, row_off, n_rows, &n_bases);
+    CountOut o;
+    int rc = submit_count_common(c, seq, row_off, n_rows, k, FMT_PAIRS, &o);
     if (rc) return rc;
-    uint64_t cap = kmer_cuda_max_kmers(n_bases, n_rows, k);
-    if (k >= 1 && k < 32 && (1ull << (2 * k)) < cap) cap = 1ull << (2 * k);
-    rc = ws(c, c->pairs, cap * sizeof(kmer_count_pair));
-    if (rc) return rc;
-    rc = kmer_cuda_dev_count(c, (const char*)c->seq.p, n_bases, (const uint64_t*)c->off.p, n_rows, k,
-                             (kmer_count_pair*)c->pairs.p, cap, 0, KMER_OWN_STREAM);
-    if (rc) return rc;
-    kmer_dev_result res;
-    rc = kmer_cuda_dev_finish(c, KMER_OWN_STREAM, &res);
-    if (rc) return rc;
-    kmer_count_pair* out = (kmer_count_pair*)pinned_get(c, res.n_distinct * sizeof(kmer_count_pair));
-    if (!out) return c->err.status;
-    CU(cudaMemcpyAsync(out, c->pairs.p, res.n_distinct * sizeof(kmer_count_pair), cudaMemcpyDeviceToHost, c->stream),
-       "D2H pairs");
-    CU(cudaStreamSynchronize(c->stream), "stream sync");
-    *pairs = out;
-    *n_distinct = res.n_distinct;
-    if (n_kmers) *n_kmers = res.n_kmers;
+    *pairs = o.pairs;
+    *n_distinct = o.n_pairs;
+    if (n_kmers) *n_kmers = o.n_kmers;
     return KMER_OK;
 }
 
@@ -1015,34 +1304,14 @@ extern "C" int kmer_cuda_submit_count_split(kmer_cuda_ctx* c, const char* seq, c
     *uniq_codes = nullptr; *pairs = nullptr;
     *n_unique = 0; *n_pairs = 0;
     if (n_kmers) *n_kmers = 0;
-    CU(cudaSetDevice(c->di.device), "cudaSetDevice");
-    uint64_t n_bases = 0;
-    int rc = upload_rows(c, seq, row_off, n_rows, &n_bases);
+    CountOut o;
+    int rc = submit_count_common(c, seq, row_off, n_rows, k, FMT_SPLIT, &o);
     if (rc) return rc;
-    uint64_t cap = kmer_cuda_max_kmers(n_bases, n_rows, k);
-    if (k >= 1 && k < 32 && (1ull << (2 * k)) < cap) cap = 1ull << (2 * k);
-    // a k-mer that is not unique occurs at least twice: at most cap/2 pairs next to the unique codes -- unless a fallback
-    // tier (which writes pairs only) takes over, so the pair buffer keeps the full size
-    rc = ws(c, c->pairs, cap * sizeof(kmer_count_pair));
-    if (!rc) rc = ws(c, c->codes, cap * sizeof(uint64_t));
-    if (rc) return rc;
-    rc = kmer_cuda_dev_count_split(c, (const char*)c->seq.p, n_bases, (const uint64_t*)c->off.p, n_rows, k, (uint64_t*)c->codes.p, cap,
-                                   (kmer_count_pair*)c->pairs.p, cap, KMER_OWN_STREAM);
-    if (rc) return rc;
-    kmer_dev_result res;
-    rc = kmer_cuda_dev_finish(c, KMER_OWN_STREAM, &res);
-    if (rc) return rc;
-    uint64_t* out_u = (uint64_t*)pinned_get(c, res.n_unique * sizeof(uint64_t));
-    kmer_count_pair* out_p = (kmer_count_pair*)pinned_get(c, res.n_distinct * sizeof(kmer_count_pair));
-    if (!out_u || !out_p) return c->err.status;
-    CU(cudaMemcpyAsync(out_u, c->codes.p, res.n_unique * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream), "D2H codes");
-    CU(cudaMemcpyAsync(out_p, c->pairs.p, res.n_distinct * sizeof(kmer_count_pair), cudaMemcpyDeviceToHost, c->stream), "D2H pairs");
-    CU(cudaStreamSynchronize(c->stream), "stream sync");
-    *uniq_codes = out_u;
-    *n_unique = res.n_unique;
-    *pairs = out_p;
-    *n_pairs = res.n_distinct;
-    if (n_kmers) *n_kmers = res.n_kmers;
+    *uniq_codes = (uint64_t*)o.uniq;
+    *n_unique = o.n_unique;
+    *pairs = o.pairs;
+    *n_pairs = o.n_pairs;
+    if (n_kmers) *n_kmers = o.n_kmers;
     return KMER_OK;
 }
 
@@ -1053,39 +1322,15 @@ extern "C" int kmer_cuda_submit_count_packed(kmer_cuda_ctx* c, const char* seq, 
     *uniq_packed = nullptr; *pairs = nullptr;
     *n_unique = 0; *n_pairs = 0; *code_bytes = 0;
     if (n_kmers) *n_kmers = 0;
-    CU(cudaSetDevice(c->di.device), "cudaSetDevice");
-    uint64_t n_bases = 0;
-    int rc = upload_rows(c, seq, row_off, n_rows, &n_bases);
+    CountOut o;
+    int rc = submit_count_common(c, seq, row_off, n_rows, k, FMT_PACKED, &o);
     if (rc) return rc;
-    uint64_t cap = kmer_cuda_max_kmers(n_bases, n_rows, k);
-    if (k >= 1 && k < 32 && (1ull << (2 * k)) < cap) cap = 1ull << (2 * k);
-    rc = ws(c, c->pairs, cap * sizeof(kmer_count_pair));
-    if (!rc) rc = ws(c, c->codes, cap * sizeof(uint64_t));
-    if (rc) return rc;
-    rc = kmer_cuda_dev_count_split(c, (const char*)c->seq.p, n_bases, (const uint64_t*)c->off.p, n_rows, k, (uint64_t*)c->codes.p, cap,
-                                   (kmer_count_pair*)c->pairs.p, cap, KMER_OWN_STREAM);
-    if (rc) return rc;
-    kmer_dev_result res;
-    rc = kmer_cuda_dev_finish(c, KMER_OWN_STREAM, &res);
-    if (rc) return rc;
-    const int nbytes = k >= 1 ? (2 * k + 7) / 8 : 1;
-    const size_t packed_bytes = (size_t)res.n_unique * (size_t)nbytes;
-    rc = ws(c, c->text, packed_bytes + 16);
-    if (rc) return rc;
-    launch_pack_codes(c->di, (const uint64_t*)c->codes.p, res.n_unique, nbytes, (uint8_t*)c->text.p, c->stream);
-    c->launches++;
-    uint8_t* out_u = (uint8_t*)pinned_get(c, packed_bytes);
-    kmer_count_pair* out_p = (kmer_count_pair*)pinned_get(c, res.n_distinct * sizeof(kmer_count_pair));
-    if (!out_u || !out_p) return c->err.status;
-    CU(cudaMemcpyAsync(out_u, c->text.p, packed_bytes, cudaMemcpyDeviceToHost, c->stream), "D2H packed codes");
-    CU(cudaMemcpyAsync(out_p, c->pairs.p, res.n_distinct * sizeof(kmer_count_pair), cudaMemcpyDeviceToHost, c->stream), "D2H pairs");
-    CU(cudaStreamSynchronize(c->stream), "stream sync");
-    *uniq_packed = out_u;
-    *n_unique = res.n_unique;
-    *code_bytes = nbytes;
-    *pairs = out_p;
-    *n_pairs = res.n_distinct;
-    if (n_kmers) *n_kmers = res.n_kmers;
+    *uniq_packed = (uint8_t*)o.uniq;
+    *n_unique = o.n_unique;
+    *code_bytes = k >= 1 ? (2 * k + 7) / 8 : 1;
+    *pairs = o.pairs;
+    *n_pairs = o.n_pairs;
+    if (n_kmers) *n_kmers = o.n_kmers;
     return KMER_OK;
 }
 

@@ -24,6 +24,8 @@ struct DevStatus {
     unsigned long long n_failed;       // partition: buckets handed to the tier-2 kernel
     unsigned long long failed_kmers;   // k-mers (instances) in those buckets
     unsigned long long n_unique;       // split result format: k-mers written as bare codes (count 1)
+    unsigned long long t2_mode;        // tier 2 of the partition counter, decided on the device: 0 not needed, 1 runs, 2 does not fit (recount)
+    unsigned long long t2_slots;       // table slots tier 2 uses (a power of two, sized by what it has to count)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -103,16 +105,21 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// try_wait suspends the thread for a hardware time slice per call; the loop is bounded so that a copy that never arrives
+// (a bug, never a legal state) traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+    const uint32_t a = smem_u32(bar);
+    for (uint32_t spins = 0; spins < (1u << 26); spins++) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
 }
 // bytes must be a multiple of 16; src and dst 16-byte aligned
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {

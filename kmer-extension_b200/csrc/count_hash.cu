@@ -43,6 +43,41 @@ __global__ void __launch_bounds__(NT) count_hash_insert_kernel(ScanArgs a, kmer_
     }
 }
 
+// merge of per-rank (k-mer, count) tables: rank `rank` adds the groups it owns (owner = hash(k-mer) % n_ranks) of a table
+// that every rank sees in turn (sharded counting's exact fallback for skewed input, sharded.py).  A full table sets n_overflow.
+__global__ void merge_pairs_kernel(const kmer_count_pair* __restrict__ in, uint64_t n, uint32_t rank, uint32_t n_ranks,
+                                   kmer_count_pair* __restrict__ slots, uint64_t mask, DevStatus* status) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint4 raw = ld_nc_u128(&in[i]);
+        const uint64_t code = ((uint64_t)raw.y << 32) | raw.x;
+        const unsigned long long cnt = ((uint64_t)raw.w << 32) | raw.z;
+        if (n_ranks > 1 && (uint32_t)((mix64(code ^ 0x9E3779B97F4A7C15ull) >> 32) % n_ranks) != rank) continue;
+        if (code == kEmpty) { atomicAdd(&status->special_count, cnt); continue; }   // k == 32, 't'*32
+        uint64_t h = mix64(code) & mask;
+        bool placed = false;
+        for (uint64_t tries = 0; tries <= mask; tries++) {
+            const unsigned long long prev = atomicCAS((unsigned long long*)&slots[h].code, kEmpty, code);
+            if (prev == kEmpty || prev == code) {
+                atomicAdd((unsigned long long*)&slots[h].count, cnt);
+                placed = true;
+                break;
+            }
+            h = (h + 1) & mask;
+        }
+        if (!placed) atomicAdd(&status->n_overflow, cnt);
+    }
+}
+
+void launch_merge_pairs(const DeviceInfo& di, const kmer_count_pair* d_in, uint64_t n, uint32_t rank, uint32_t n_ranks,
+                        kmer_count_pair* d_slots, uint64_t n_slots, DevStatus* d_status, cudaStream_t st) {
+    if (!n) return;
+    uint64_t blocks = (n + 255) / 256;
+    const uint64_t maxb = (uint64_t)di.sm_count * 8;
+    if (blocks > maxb) blocks = maxb;
+    merge_pairs_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_in, n, rank, n_ranks, d_slots, n_slots - 1, d_status);
+}
+
 void launch_hash_clear(kmer_count_pair* d_slots, uint64_t n_slots, cudaStream_t st) {
     cudaMemsetAsync(d_slots, 0xFF, n_slots * sizeof(kmer_count_pair), st);
 }
@@ -56,11 +91,14 @@ void launch_count_hash_insert(const DeviceInfo& di, const ScanArgs& a, kmer_coun
     count_hash_insert_kernel<<<(unsigned)grid, NT, 0, st>>>(a, d_slots, n_slots - 1);
 }
 
+// gated != 0: the table is tier 2's and is only looked at if the device decided to run tier 2 (DevStatus::t2_mode == 1);
+// the k == 32 special key is appended either way
 __global__ void hash_compact_kernel(const kmer_count_pair* __restrict__ slots, uint64_t n_slots, int k,
-                                    kmer_count_pair* __restrict__ out, uint64_t capacity, DevStatus* status) {
+                                    kmer_count_pair* __restrict__ out, uint64_t capacity, DevStatus* status, int gated) {
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
     unsigned long long total = 0;
+    if (gated) n_slots = status->t2_mode == 1ull ? status->t2_slots : 0;
     for (uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b < n_slots; b += stride) {  // n_slots % 32 == 0
         uint4 raw = ld_nc_u128(&slots[b]);
         uint64_t code = ((uint64_t)raw.y << 32) | raw.x;
@@ -93,11 +131,11 @@ __global__ void hash_compact_kernel(const kmer_count_pair* __restrict__ slots, u
 }
 
 void launch_hash_compact(const DeviceInfo& di, const kmer_count_pair* d_slots, uint64_t n_slots, int k,
-                         kmer_count_pair* d_pairs, uint64_t capacity, DevStatus* d_status, cudaStream_t st) {
+                         kmer_count_pair* d_pairs, uint64_t capacity, DevStatus* d_status, cudaStream_t st, int gated) {
     uint64_t blocks = (n_slots + 255) / 256;
     uint64_t maxb = (uint64_t)di.sm_count * 8;
     if (blocks > maxb) blocks = maxb;
-    hash_compact_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_slots, n_slots, k, d_pairs, capacity, d_status);
+    hash_compact_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_slots, n_slots, k, d_pairs, capacity, d_status, gated);
 }
 
 }  // namespace kmer

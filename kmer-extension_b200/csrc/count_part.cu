@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(NT, PART_MINB) partition_kernel(ScanArgs a, Pa
             if (si < plan.spill_cap) dst = spill + si;
             else overflow_kmers += L;
         }
-        if (dst && !(plan.debug & 1)) {
+        if (dst) {
             if (RECW == 1) {
                 uint64_t v = ((uint64_t)r0w << 32) | r1w;
                 v &= ~0ull << (64 - 2 * nb);                       // nb <= 30
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(NT, PART_MINB) partition_kernel(ScanArgs a, Pa
                 const unsigned long long d = wruns[r];
                 bq[q] = __umulhi(mix32((uint32_t)(d >> 32)), plan.hash_buckets) >> plan.fine_shift;
                 posq[q] = (uint32_t)d;
-                slot[q] = (plan.debug & 2) ? ((mix32(posq[q] + (uint32_t)sc.tile) >> 8) % plan.cap) : (uint32_t)atomicAdd(&fill[bq[q]], 1ull);
+                slot[q] = (uint32_t)atomicAdd(&fill[bq[q]], 1ull);
             }
         }
         __syncthreads();                                              // boundary bits of the whole tile are visible
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(NT, PART_MINB) partition_kernel(ScanArgs a, Pa
         auto emit_run = [&](uint32_t b, uint32_t slot0, uint32_t p0) {
             const uint32_t R = run_length(p0);
             const uint32_t L0 = R < rmax ? R : rmax;
-            if (!(plan.debug & 2)) atomicAdd(&fill[b], (unsigned long long)L0 << 32);
+            atomicAdd(&fill[b], (unsigned long long)L0 << 32);
             put_record(b, slot0, (int)p0, (int)L0);
             for (uint32_t off = rmax; off < R; off += rmax) {
                 const uint32_t L = R - off < rmax ? R - off : rmax;
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(NT, PART_MINB) partition_kernel(ScanArgs a, Pa
         for (uint32_t r = EMIT_Q * 32 + lane; r < n_warp_runs; r += 32) {   // more than 192 runs in 512 windows: rare
             const unsigned long long d = wruns[r];
             const uint32_t b = __umulhi(mix32((uint32_t)(d >> 32)), plan.hash_buckets) >> plan.fine_shift;
-            const uint32_t s0 = (plan.debug & 2) ? 0u : (uint32_t)atomicAdd(&fill[b], 1ull);
+            const uint32_t s0 = (uint32_t)atomicAdd(&fill[b], 1ull);
             emit_run(b, s0, (uint32_t)d);
         }
         sc.release();
@@ -349,22 +349,27 @@ __device__ __forceinline__ void lds128(uint32_t a, unsigned long long& x, unsign
 __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "LEAF_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra LEAF_DONE;\n"
-        "bra LEAF_WAIT;\n"
-        "LEAF_DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {   // bounded like mbar_wait (common.cuh)
+    for (uint32_t spins = 0; spins < (1u << 26); spins++) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
 }
 
 // cell of the filter bitmaps (15 bits) and, decorrelated from it, the slot hash of the exact table
 __device__ __forceinline__ uint32_t leaf_mix(uint64_t key) {
     return (uint32_t)key * 0x9E3779B1u + (uint32_t)(key >> 32) * 0x85EBCA6Bu;
 }
+// cell of the filter bitmaps (15 bits).  Both halves of the key must go in: hashing the low word alone is one IMAD cheaper but
+// sends 2x as many k-mers to the exact table (measured: 7.0 instead of 6.45 ms for the 1 GB bench)
+__device__ __forceinline__ uint32_t leaf_cell(uint64_t key) { return leaf_mix(key) >> 17; }
 
 struct BucketInfo {
     uint32_t nrec, nk;
@@ -381,14 +386,14 @@ __device__ __forceinline__ BucketInfo bucket_info(const unsigned long long* __re
     return bi;
 }
 
-template <int RECW>
+template <int RECW, bool SPLIT>
 __global__ void __launch_bounds__(LEAF_THREADS, LEAF_MINB) bucket_count_kernel(PartitionPlan plan, int k,
                                                                        const unsigned long long* __restrict__ fill,
                                                                        const Rec<RECW>* __restrict__ recs,
                                                                        kmer_count_pair* __restrict__ out, uint64_t capacity,
                                                                        uint64_t* __restrict__ out_u, uint64_t capacity_u,
                                                                        uint32_t* __restrict__ failed_ids, Rec<RECW>* __restrict__ spill,
-                                                                       DevStatus* status) {
+                                                                       DevStatus* status, uint32_t bucket_begin, uint32_t bucket_end) {
     constexpr bool PACKED = RECW == 1;                        // count in bits 63..52 of the key word (k <= 26)
     constexpr uint32_t RECB = RECW * 8;
     constexpr uint64_t KEYMASK = PACKED ? ((1ull << 52) - 1ull) : ~0ull;
@@ -441,14 +446,15 @@ __global__ void __launch_bounds__(LEAF_THREADS, LEAF_MINB) bucket_count_kernel(P
     uint32_t par = 0, phase = 0, rb = 0;                                // bucket parity, mbarrier phase, record buffer
     BucketInfo cur;
     cur.nrec = 0; cur.nk = 0; cur.overflow = false;
-    if (blockIdx.x < plan.n_buckets) cur = bucket_info(fill, plan, blockIdx.x);
-    if (t == 0 && cur.usable()) issue(blockIdx.x, 0);
+    const uint32_t b_first = bucket_begin + blockIdx.x;
+    if (b_first < bucket_end) cur = bucket_info(fill, plan, b_first);
+    if (t == 0 && cur.usable()) issue(b_first, 0);
 
-    for (uint32_t b = blockIdx.x; b < plan.n_buckets; b += gridDim.x) {
+    for (uint32_t b = b_first; b < bucket_end; b += gridDim.x) {
         const uint32_t b_next = b + gridDim.x;
         BucketInfo nxt;
         nxt.nrec = 0; nxt.nk = 0; nxt.overflow = false;
-        if (b_next < plan.n_buckets) nxt = bucket_info(fill, plan, b_next);   // in flight during the index phase
+        if (b_next < bucket_end) nxt = bucket_info(fill, plan, b_next);   // in flight during the index phase
         if (!cur.usable()) {                                            // uniform across the CTA
             if (t == 0) {
                 if (cur.nrec) {                                         // does not fit on chip: tier 2
@@ -519,7 +525,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, LEAF_MINB) bucket_count_kernel(P
                 if (RECW == 2 && key[i] == kEmpty) special++;           // k == 32, 't'*32: kept out of the tables
                 else {
                     valid |= 1u << i;
-                    const uint32_t cell = leaf_mix(key[i]) >> 17;
+                    const uint32_t cell = leaf_cell(key[i]);
                     const uint32_t bit = 1u << (cell & 31u), w = (cell >> 5) * 4;
                     if (atoms_or32(bma_s + w, bit) & bit) {
                         reds_or32(bmb_s + w, bit);
@@ -537,7 +543,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, LEAF_MINB) bucket_count_kernel(P
             if ((valid >> i) & 1u) {
                 bool slow = (multi >> i) & 1u;
                 if (!slow) {
-                    const uint32_t cell = leaf_mix(key[i]) >> 17;
+                    const uint32_t cell = leaf_cell(key[i]);
                     slow = (lds32(bmb_s + (cell >> 5) * 4) >> (cell & 31u)) & 1u;
                 }
                 if (slow) {
@@ -557,7 +563,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, LEAF_MINB) bucket_count_kernel(P
         unsigned long long ubase = 0;
         if (t == 0) {
             const uint32_t nu = s_nuniq[par];
-            if (nu) ubase = atomicAdd(out_u ? &status->n_unique : &status->n_distinct, (unsigned long long)nu);   // consumed after the next barrier
+            if (nu) ubase = atomicAdd(SPLIT ? &status->n_unique : &status->n_distinct, (unsigned long long)nu);   // consumed after the next barrier
         }
         // both bitmaps are dead: clear them for the next bucket
         for (int i = t; i < 2 * LEAF_CELLS / 128; i += LEAF_THREADS) sts128(bma_s + 16 * i, 0u, 0u, 0u, 0u);
@@ -628,7 +634,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, LEAF_MINB) bucket_count_kernel(P
         // ---- emit the unique k-mers: coalesced 16-byte (k-mer, 1) pairs, ranks by ballot
         {
             const unsigned long long ob = s_obase[par] + woff;
-            const bool fits = ob + wuniq <= (out_u ? capacity_u : capacity);   // uniform per warp
+            const bool fits = ob + wuniq <= (SPLIT ? capacity_u : capacity);   // uniform per warp
             if (!fits && lane == 0) status->out_overflow = 1;
             ulonglong2* const po = reinterpret_cast<ulonglong2*>(out) + ob;
             uint64_t* const pu = out_u + ob;
@@ -641,7 +647,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, LEAF_MINB) bucket_count_kernel(P
                 const uint32_t m = __ballot_sync(0xffffffffu, u);
                 if (u) {
                     const uint32_t o = rank + __popc(m & lane_lt);
-                    if (out_u) pu[o] = key[i];                          // split format: a bare code means count 1
+                    if (SPLIT) pu[o] = key[i];                          // split format: a bare code means count 1
                     else {
                         ulonglong2 v;
                         v.x = key[i];
@@ -924,22 +930,45 @@ __device__ __forceinline__ void tier2_add_record(const Rec<RECW>* p, int kshift,
     }
 }
 
+// one thread: does tier 2 have to run, and does what it must count fit its table?
+__global__ void tier2_decide_kernel(PartitionPlan plan, uint64_t n_slots, DevStatus* status) {
+    const unsigned long long spilled = min(status->n_spill, (unsigned long long)plan.spill_cap);
+    unsigned long long mode = 0, slots = 0;
+    if (status->n_overflow) mode = 2;                                   // the spill list overflowed: the batch is recounted
+    else if (status->n_failed || status->n_spill) {
+        const unsigned long long need = (status->failed_kmers + spilled * 16ull) * 2ull;   // load factor <= 1/2
+        mode = 1;
+        slots = 1024;
+        while (slots < need && slots < n_slots) slots <<= 1;
+        if (slots < need) { mode = 2; atomicAdd(&status->n_overflow, 1ull); }
+    }
+    status->t2_mode = mode;
+    status->t2_slots = slots;
+}
+
+__global__ void __launch_bounds__(256) tier2_clear_kernel(uint4* __restrict__ slots, const DevStatus* status) {
+    if (status->t2_mode != 1ull) return;
+    const uint64_t n_slots = status->t2_slots;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) slots[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+}
+
 template <int RECW>
 __global__ void __launch_bounds__(256) tier2_insert_kernel(PartitionPlan plan, int k, const unsigned long long* __restrict__ fill,
                                                            const Rec<RECW>* __restrict__ recs, const uint32_t* __restrict__ failed_ids,
                                                            const Rec<RECW>* __restrict__ spill, kmer_count_pair* __restrict__ slots,
-                                                           uint64_t mask, DevStatus* status, int n_src) {
+                                                           DevStatus* status) {
+    if (status->t2_mode != 1ull) return;
+    const uint64_t mask = status->t2_slots - 1;
     const int kshift = 64 - 2 * k;
     const uint32_t n_failed = (uint32_t)status->n_failed;
     for (uint32_t fi = blockIdx.x; fi < n_failed; fi += gridDim.x) {
         const uint32_t b = failed_ids[fi];
-        for (int sI = 0; sI < n_src; sI++) {
-            const uint32_t nrec = min((uint32_t)fill[(uint64_t)sI * plan.n_buckets + b] & 0x7fffffffu, plan.cap);   // bit 31: poison (scatter.cuh)
-            const Rec<RECW>* base = recs + ((uint64_t)sI * plan.n_buckets + b) * plan.cap;
-            for (uint32_t r0 = 0; r0 < nrec; r0 += blockDim.x) {
-                uint32_t r = r0 + threadIdx.x;
-                tier2_add_record<RECW>(base + min(r, nrec - 1), kshift, slots, mask, status, r < nrec);
-            }
+        const uint32_t nrec = min((uint32_t)fill[b] & 0x7fffffffu, plan.cap);   // bit 31: poison (scatter.cuh)
+        const Rec<RECW>* base = recs + (uint64_t)b * plan.cap;
+        for (uint32_t r0 = 0; r0 < nrec; r0 += blockDim.x) {
+            uint32_t r = r0 + threadIdx.x;
+            tier2_add_record<RECW>(base + min(r, nrec - 1), kshift, slots, mask, status, r < nrec);
         }
     }
     const uint64_t n_spill = min((uint64_t)status->n_spill, (uint64_t)plan.spill_cap);
@@ -983,8 +1012,9 @@ static uint32_t stage_slots(double lam, uint32_t sect, double dests, double budg
     }
     return c < max_slots ? c : max_slots;
 }
-static size_t stage_bytes(uint32_t dests, uint32_t caps, int recw) { return (((size_t)dests * 4 + 15) & ~(size_t)15) + (size_t)dests * caps * (recw == 1 ? 8 : 16); }
-static size_t scatter_static_smem() { return sizeof(ScanSmem) + (NT / 32) * SCAT_RUNCAP * 4 + (TILE / 32 + 2) * 4 + 64; }
+static size_t stage_fixed_bytes(uint32_t dests) { return (((size_t)dests * 12 + 8 + 15) & ~(size_t)15) + 16; }   // Stage: cnt, gpos, rdy lists
+static size_t stage_bytes(uint32_t dests, uint32_t caps, int recw) { return stage_fixed_bytes(dests) + (size_t)dests * caps * (recw == 1 ? 8 : 16); }
+static size_t scatter_static_smem() { return sizeof(ScanSmem) + (NT / 32) * SCAT_RUNCAP * 6 + (TILE / 32 + 2) * 4 + 64; }
 
 bool make_scatter_plan(const DeviceInfo& di, uint64_t n_bases, uint64_t n_kmers, PartitionPlan& p, ScatterPlan& sp) {
     uint32_t fine_shift = 10;                              // F = 1024 fine buckets per coarse partition: one per refine2 thread
@@ -1001,7 +1031,7 @@ bool make_scatter_plan(const DeviceInfo& di, uint64_t n_bases, uint64_t n_kmers,
     uint32_t caps = 0, per_sm = SCAT_MINB;
     for (; per_sm >= 1; per_sm--) {
         const size_t budget = (size_t)227 * 1024 / per_sm - 1024 - scatter_static_smem();
-        const uint32_t max_slots = (uint32_t)std::min<size_t>(4096, (budget - (((size_t)D * 4 + 15) & ~(size_t)15)) / (D * (p.recw == 1 ? 8 : 16)));
+        const uint32_t max_slots = (uint32_t)std::min<size_t>(4096, (budget - stage_fixed_bytes((uint32_t)D)) / (D * (p.recw == 1 ? 8 : 16)));
         if (max_slots < sect + 2) continue;
         caps = stage_slots(TILE * rpk / (double)D, sect, (double)D, 0.02, max_slots);
         if (caps < max_slots || per_sm == 1) break;       // the slots wanted fit (or nothing smaller is left to try)
@@ -1019,7 +1049,7 @@ bool make_scatter_plan(const DeviceInfo& di, uint64_t n_bases, uint64_t n_kmers,
     sp.seg_cap = ((uint32_t)(1.1 * mean + 6.0 * sqrt(mean) + 32.0) + 3u) & ~3u;
     sp.caps = caps;
     const uint32_t F = 1u << fine_shift;
-    const size_t budget2 = (size_t)227 * 1024 - 1024 - (((size_t)F * 4 + 15) & ~(size_t)15) * 2;
+    const size_t budget2 = (size_t)227 * 1024 - 1024 - (((size_t)F * 4 + 15) & ~(size_t)15) - stage_fixed_bytes(F);
     const uint32_t max2 = (uint32_t)std::min<size_t>(4096, budget2 / ((size_t)F * (p.recw == 1 ? 8 : 16)));
     sp.caps2 = stage_slots((double)RF2_THREADS * RF2_RQ / (double)F, sect, (double)F, 0.02, max2);
     p.n_buckets = (uint32_t)(D << fine_shift);
@@ -1080,12 +1110,14 @@ void launch_scatter_refine(const DeviceInfo& di, const ScanArgs& a, const Partit
 }
 
 
+static int g_forced_window = 0;
+void partition_force_window(int w) { g_forced_window = w; }
+
 PartitionPlan make_partition_plan(uint64_t n_kmers, int k) {
     PartitionPlan p{};
     // minimizer window: the m-mer (m = k - w + 1, capped at 16 bases) must be long enough (>= 14 bases where k allows) that
     // the minimizers spread evenly over the buckets; shorter ones leave few distinct minimizers and lopsided buckets
-    static const char* env_target = getenv("KMER_CUDA_BUCKET_KMERS");   // profiling experiments only
-    const uint32_t target = env_target ? (uint32_t)atoi(env_target) : TARGET_KMERS_PER_BUCKET;
+    const uint32_t target = TARGET_KMERS_PER_BUCKET;
     uint64_t nb = (n_kmers + target - 1) / target;
     if (nb < 1) nb = 1;
     if (nb > 0x7fffffffull) nb = 0x7fffffffull;
@@ -1102,8 +1134,8 @@ PartitionPlan make_partition_plan(uint64_t n_kmers, int k) {
             if (m >= 14 && ldexp(1.0, 2 * m) >= 65.0 * (double)nb) { p.w = ws[i]; break; }
         }
     }
-    if (const char* fw = getenv("KMER_CUDA_DEBUG_W")) {   // tests: force a window (must suit the record width and k)
-        const int w = atoi(fw);
+    if (g_forced_window) {                                 // tests only (kmer_cuda_test_force_window): must suit the record width and k
+        const int w = g_forced_window;
         const bool ok = p.recw == 1 ? (w == 4 || w == 6 || w == 8) : (w == 8 || w == 12 || w == 16);
         if (ok && k - w + 1 >= 2) p.w = w;
     }
@@ -1120,13 +1152,6 @@ PartitionPlan make_partition_plan(uint64_t n_kmers, int k) {
     }
     uint64_t sc = (uint64_t)p.n_buckets * p.cap / 8;          // spill list: 1/8 of the bucket regions
     p.spill_cap = sc < 4096 ? 4096 : sc;
-    if (const char* nbs = getenv("KMER_CUDA_DEBUG_NBUCKETS")) {   // profiling experiment only: scatter to few, large regions
-        p.n_buckets = (uint32_t)atoi(nbs);
-        p.hash_buckets = p.n_buckets;
-        p.cap = (uint32_t)((double)n_kmers * 0.3 / p.n_buckets * 1.3 + 1024) & ~1u;
-    }
-    const char* dbg = getenv("KMER_CUDA_DEBUG_PARTITION");   // profiling experiments only (bit0: no record stores, bit1: no slot atomics)
-    p.debug = dbg ? atoi(dbg) : 0;
     return p;
 }
 
@@ -1134,9 +1159,9 @@ size_t partition_record_bytes(const PartitionPlan& p) { return (size_t)p.n_bucke
 size_t partition_spill_bytes(const PartitionPlan& p) { return (size_t)p.spill_cap * (p.recw == 1 ? 8 : 16); }
 
 void launch_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPlan& p, unsigned long long* d_fill,
-                      void* d_recs, void* d_spill, cudaStream_t st) {
-    cudaMemsetAsync(d_fill, 0, (size_t)p.n_buckets * sizeof(unsigned long long), st);
-    uint64_t n_tiles = (a.n_bases + TILE - 1) / TILE;
+                      void* d_recs, void* d_spill, cudaStream_t st, bool clear_fill) {
+    if (clear_fill) cudaMemsetAsync(d_fill, 0, (size_t)p.n_buckets * sizeof(unsigned long long), st);
+    uint64_t n_tiles = a.tile_end ? a.tile_end - a.tile_begin : (a.n_bases + TILE - 1) / TILE;
     uint64_t grid = (uint64_t)di.sm_count * PART_MINB;
     if (grid > n_tiles) grid = n_tiles;
     if (!n_tiles) return;
@@ -1163,30 +1188,33 @@ static void leaf_configure(size_t smem) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || configured[dev] >= smem) return;
-    cudaFuncSetAttribute(bucket_count_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(bucket_count_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(bucket_count_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(bucket_count_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+#define KMER_LEAF_CONF(RW, SP)                                                                                   \
+    cudaFuncSetAttribute(bucket_count_kernel<RW, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    cudaFuncSetAttribute(bucket_count_kernel<RW, SP>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
+    KMER_LEAF_CONF(1, false); KMER_LEAF_CONF(1, true); KMER_LEAF_CONF(2, false); KMER_LEAF_CONF(2, true);
+#undef KMER_LEAF_CONF
     configured[dev] = smem;
 }
 
 void launch_bucket_count(const DeviceInfo& di, const PartitionPlan& p, int k, const unsigned long long* d_fill,
                          const void* d_recs, void* d_spill, uint32_t* d_failed_ids, kmer_count_pair* d_pairs, uint64_t capacity,
-                         uint64_t* d_uniq, uint64_t uniq_capacity, DevStatus* d_status, cudaStream_t st) {
+                         uint64_t* d_uniq, uint64_t uniq_capacity, DevStatus* d_status, cudaStream_t st, uint32_t bucket_begin,
+                         uint32_t bucket_end) {
+    if (bucket_end == 0 || bucket_end > p.n_buckets) bucket_end = p.n_buckets;
+    if (bucket_begin >= bucket_end) return;
     const size_t leaf_smem = leaf_smem_bytes(p);
     int per_sm = (int)((size_t)227 * 1024 / (leaf_smem + 1024));
     if (per_sm > LEAF_MINB) per_sm = LEAF_MINB;
     if (per_sm < 1) per_sm = 1;
     uint64_t lgrid = (uint64_t)di.sm_count * per_sm;
-    if (lgrid > p.n_buckets) lgrid = p.n_buckets;
-    if (!lgrid) return;
+    if (lgrid > bucket_end - bucket_begin) lgrid = bucket_end - bucket_begin;
     leaf_configure(leaf_smem);
-    if (p.recw == 1)
-        bucket_count_kernel<1><<<(unsigned)lgrid, LEAF_THREADS, leaf_smem, st>>>(p, k, d_fill, (const Rec<1>*)d_recs, d_pairs, capacity, d_uniq,
-                                                                                 uniq_capacity, d_failed_ids, (Rec<1>*)d_spill, d_status);
-    else
-        bucket_count_kernel<2><<<(unsigned)lgrid, LEAF_THREADS, leaf_smem, st>>>(p, k, d_fill, (const Rec<2>*)d_recs, d_pairs, capacity, d_uniq,
-                                                                                 uniq_capacity, d_failed_ids, (Rec<2>*)d_spill, d_status);
+#define KMER_LEAF_GO(RW, SP)                                                                                                            \
+    bucket_count_kernel<RW, SP><<<(unsigned)lgrid, LEAF_THREADS, leaf_smem, st>>>(p, k, d_fill, (const Rec<RW>*)d_recs, d_pairs, capacity, \
+                                                                                  d_uniq, uniq_capacity, d_failed_ids, (Rec<RW>*)d_spill, d_status, bucket_begin, bucket_end)
+    if (p.recw == 1) { if (d_uniq) KMER_LEAF_GO(1, true); else KMER_LEAF_GO(1, false); }
+    else { if (d_uniq) KMER_LEAF_GO(2, true); else KMER_LEAF_GO(2, false); }
+#undef KMER_LEAF_GO
 }
 
 void launch_count_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPlan& p, unsigned long long* d_fill,
@@ -1198,17 +1226,28 @@ void launch_count_partition(const DeviceInfo& di, const ScanArgs& a, const Parti
     if (mark) mark(mark_arg, "bucket_count");
 }
 
-// tier 2 (only when the host saw n_failed or n_spill): slots must be cleared to 0xFF (launch_hash_clear)
-void launch_partition_tier2(const DeviceInfo& di, const PartitionPlan& p, int k, int n_src, const unsigned long long* d_fill,
+uint64_t tier2_table_slots(uint64_t n_kmers) {
+    uint64_t want = n_kmers / 4, p = 1ull << 16;                      // room for 1/8 of the k-mers at load factor 1/2
+    while (p < want) p <<= 1;
+    return p;
+}
+
+void launch_partition_tier2(const DeviceInfo& di, const PartitionPlan& p, int k, const unsigned long long* d_fill,
                             const void* d_recs, const void* d_spill, const uint32_t* d_failed_ids, kmer_count_pair* d_slots,
-                            uint64_t n_slots, DevStatus* d_status, cudaStream_t st) {
-    unsigned grid = (unsigned)di.sm_count * 8;
+                            uint64_t n_slots, kmer_count_pair* d_pairs, uint64_t capacity, DevStatus* d_status, cudaStream_t st,
+                            void (*mark)(void*, const char*), void* mark_arg) {
+    const unsigned grid = (unsigned)di.sm_count * 8;
+    tier2_decide_kernel<<<1, 1, 0, st>>>(p, n_slots, d_status);
+    tier2_clear_kernel<<<grid, 256, 0, st>>>((uint4*)d_slots, d_status);
     if (p.recw == 1)
         tier2_insert_kernel<1><<<grid, 256, 0, st>>>(p, k, d_fill, (const Rec<1>*)d_recs, d_failed_ids, (const Rec<1>*)d_spill,
-                                                     d_slots, n_slots - 1, d_status, n_src);
+                                                     d_slots, d_status);
     else
         tier2_insert_kernel<2><<<grid, 256, 0, st>>>(p, k, d_fill, (const Rec<2>*)d_recs, d_failed_ids, (const Rec<2>*)d_spill,
-                                                     d_slots, n_slots - 1, d_status, n_src);
+                                                     d_slots, d_status);
+    if (mark) mark(mark_arg, "tier2_insert");
+    launch_hash_compact(di, d_slots, n_slots, k, d_pairs, capacity, d_status, st, 1);   // + the k == 32 special key
+    if (mark) mark(mark_arg, "tier2_compact");
 }
 
 void launch_refine(const DeviceInfo& di, const PartitionPlan& p, int k, int n_src, uint32_t n_coarse, uint32_t coarse_cap,
@@ -1218,7 +1257,7 @@ void launch_refine(const DeviceInfo& di, const PartitionPlan& p, int k, int n_sr
     unsigned grid = (unsigned)di.sm_count * 8;
     if (grid > n_coarse) grid = n_coarse;
     const size_t smem = (size_t)(2u << p.fine_shift) * sizeof(uint32_t);
-    if (p.recw == 1 && p.fine_shift == 8 && !getenv("KMER_CUDA_REFINE_DIRECT")) {   // write-combining version (8-byte records)
+    if (p.recw == 1 && p.fine_shift == 8) {   // write-combining version (8-byte records)
         if (p.w == 4) refine_staged_kernel<4><<<grid, 256, 0, st>>>(p, k, n_src, n_coarse, coarse_cap, d_recv_fill, (const Rec<1>*)d_recv_recs, d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill, d_status);
         else if (p.w == 6) refine_staged_kernel<6><<<grid, 256, 0, st>>>(p, k, n_src, n_coarse, coarse_cap, d_recv_fill, (const Rec<1>*)d_recv_recs, d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill, d_status);
         else refine_staged_kernel<8><<<grid, 256, 0, st>>>(p, k, n_src, n_coarse, coarse_cap, d_recv_fill, (const Rec<1>*)d_recv_recs, d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill, d_status);

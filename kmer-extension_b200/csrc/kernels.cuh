@@ -38,9 +38,11 @@ void launch_dense_emit(const DeviceInfo& di, const unsigned long long* d_table, 
 void launch_hash_clear(kmer_count_pair* d_slots, uint64_t n_slots, cudaStream_t st);
 void launch_count_hash_insert(const DeviceInfo& di, const ScanArgs& a, kmer_count_pair* d_slots, uint64_t n_slots,
                               cudaStream_t st);
+void launch_merge_pairs(const DeviceInfo& di, const kmer_count_pair* d_in, uint64_t n, uint32_t rank, uint32_t n_ranks,
+                        kmer_count_pair* d_slots, uint64_t n_slots, DevStatus* d_status, cudaStream_t st);
 // appends every occupied slot (+ the k==32 special key) to d_pairs, bumping status->n_distinct
 void launch_hash_compact(const DeviceInfo& di, const kmer_count_pair* d_slots, uint64_t n_slots, int k,
-                         kmer_count_pair* d_pairs, uint64_t capacity, DevStatus* d_status, cudaStream_t st);
+                         kmer_count_pair* d_pairs, uint64_t capacity, DevStatus* d_status, cudaStream_t st, int gated = 0);
 
 // count_part.cu --------------------------------------------------------------------------------
 struct PartitionPlan {
@@ -53,9 +55,9 @@ struct PartitionPlan {
     uint64_t spill_cap;   // records the spill list holds
     uint32_t hash_buckets; // range the minimizer hash is scaled to (== n_buckets unless partitioning coarsely)
     int fine_shift;       // bucket = scaled hash >> fine_shift (sharded counting: coarse partitions of 2^fine_shift buckets)
-    int debug;            // profiling experiments only (env KMER_CUDA_DEBUG_PARTITION)
 };
 PartitionPlan make_partition_plan(uint64_t n_kmers, int k);
+void partition_force_window(int w);   // tests: 0 = automatic
 // two write-combining passes (scatter.cuh): column -> n_coarse partitions (one segment per scatter CTA) -> fine buckets
 struct ScatterPlan {
     uint32_t n_coarse;   // destinations of the first pass
@@ -80,16 +82,25 @@ size_t partition_spill_bytes(const PartitionPlan& p);
 void launch_count_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPlan& p, unsigned long long* d_fill,
                             void* d_recs, void* d_spill, uint32_t* d_failed_ids, kmer_count_pair* d_pairs, uint64_t capacity,
                             uint64_t* d_uniq, uint64_t uniq_capacity, cudaStream_t st, void (*mark)(void*, const char*), void* mark_arg);
+// a.tile_begin/tile_end: the tiles this launch walks (a column that arrives in pieces); clear_fill = false appends to the regions
 void launch_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPlan& p, unsigned long long* d_fill,
-                      void* d_recs, void* d_spill, cudaStream_t st);
+                      void* d_recs, void* d_spill, cudaStream_t st, bool clear_fill = true);
 void launch_bucket_count(const DeviceInfo& di, const PartitionPlan& p, int k, const unsigned long long* d_fill,
                          const void* d_recs, void* d_spill, uint32_t* d_failed_ids, kmer_count_pair* d_pairs, uint64_t capacity,
-                         uint64_t* d_uniq, uint64_t uniq_capacity, DevStatus* d_status, cudaStream_t st);
+                         uint64_t* d_uniq, uint64_t uniq_capacity, DevStatus* d_status, cudaStream_t st, uint32_t bucket_begin = 0,
+                         uint32_t bucket_end = 0);
+// bucket_begin/bucket_end: the buckets this launch counts (0, 0: all) -- results can leave while later buckets are counted.
 // d_uniq != nullptr: split result format -- k-mers proven unique on chip are written as bare codes to d_uniq (counted in
 // DevStatus::n_unique), everything else as (k-mer, count) pairs
-void launch_partition_tier2(const DeviceInfo& di, const PartitionPlan& p, int k, int n_src, const unsigned long long* d_fill,
+// Tier 2, stream-ordered: the device itself decides whether the failed buckets / spilled records need it (DevStatus::t2_mode);
+// all kernels are always launched and return at once when they are not needed.  d_slots: n_slots (a power of two) table slots;
+// if the failed k-mers do not fit, DevStatus::n_overflow is set (the caller recounts in kmer_cuda_dev_finish).
+// Also appends the k == 32 special key.
+uint64_t tier2_table_slots(uint64_t n_kmers);
+void launch_partition_tier2(const DeviceInfo& di, const PartitionPlan& p, int k, const unsigned long long* d_fill,
                             const void* d_recs, const void* d_spill, const uint32_t* d_failed_ids, kmer_count_pair* d_slots,
-                            uint64_t n_slots, DevStatus* d_status, cudaStream_t st);
+                            uint64_t n_slots, kmer_count_pair* d_pairs, uint64_t capacity, DevStatus* d_status, cudaStream_t st,
+                            void (*mark)(void*, const char*), void* mark_arg);
 // sharded counting, owner side: the coarse partitions received from every source GPU ([src][n_coarse][coarse_cap] records,
 // [src][n_coarse] fills) are split into this GPU's fine buckets (p: n_buckets = n_coarse << fine_shift, cap, spill list)
 void launch_refine(const DeviceInfo& di, const PartitionPlan& p, int k, int n_src, uint32_t n_coarse, uint32_t coarse_cap,

@@ -29,6 +29,7 @@ struct ScanArgs {
     const uint32_t* row_mask;  // row-start bits, ceil((n_bases+1)/32) + MASK_PAD_WORDS words
     int k;
     DevStatus* status;
+    uint64_t tile_begin = 0, tile_end = 0;   // tiles this launch walks (tile_end == 0: all) -- a column that arrives in pieces
 };
 
 struct alignas(16) ScanSmem {
@@ -48,9 +49,10 @@ struct TileScanner {
     uint32_t kmask;            // (1 << (k-1)) - 1
 
     __device__ TileScanner(const ScanArgs& a_, ScanSmem& s_) : a(a_), s(s_) {
-        uint64_t n_tiles = (a.n_bases + TILE - 1) / TILE;
-        tile = n_tiles * blockIdx.x / gridDim.x;
-        tile_end = n_tiles * (blockIdx.x + 1) / gridDim.x;
+        const uint64_t all_tiles = (a.n_bases + TILE - 1) / TILE;
+        const uint64_t first = a.tile_end ? a.tile_begin : 0, n_tiles = (a.tile_end ? a.tile_end : all_tiles) - first;
+        tile = first + n_tiles * blockIdx.x / gridDim.x;
+        tile_end = first + n_tiles * (blockIdx.x + 1) / gridDim.x;
         stage = 0;
         phases = 0;
         kmask = (a.k > 1) ? ((1u << (a.k - 1)) - 1u) : 0u;

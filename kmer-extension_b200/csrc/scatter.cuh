@@ -71,16 +71,31 @@ __device__ __forceinline__ void spill_record(const Rec<RECW>& r, const Partition
 }
 
 // ---------------------------------------------------------------------------------------------
-// staging area in shared memory: cnt[D] + slots [caps][D] (slot-major: the flushing threads read conflict-free)
+// staging area in shared memory:  cnt[D] records staged | gpos[D] records already in the destination's region |
+// rdy[2][D] + rdy_n[2] destinations with a whole sector, per round parity | slots [caps][D] (slot-major)
+// A "round" is: every thread put()s its records -- barrier -- flush_round().  The lane whose record completes a destination's
+// first sector of the round lists the destination, so the flush walks a DENSE list (every lane busy) instead of polling all
+// destinations.
 template <int RECW>
 struct Stage {
-    uint32_t cnt_s, slot_s, D, caps;
+    uint32_t cnt_s, gpos_s, rdy_s, rdyn_s, slot_s, D, caps, rnd;
     static constexpr uint32_t RECB = RECW * 8;
     static constexpr uint32_t SECT = 4 / RECW;            // records per 32-byte sector
-    __device__ __forceinline__ static size_t bytes(uint32_t D, uint32_t caps) { return ((size_t)D * 4 + 15) / 16 * 16 + (size_t)D * caps * RECB; }
     __device__ __forceinline__ void init(uint32_t base_s, uint32_t D_, uint32_t caps_) {
-        cnt_s = base_s; D = D_; caps = caps_;
-        slot_s = base_s + ((D_ * 4 + 15) & ~15u);
+        D = D_; caps = caps_; rnd = 0;
+        cnt_s = base_s;
+        gpos_s = cnt_s + D * 4;
+        rdy_s = gpos_s + D * 4;                            // u16 [2][D]
+        rdyn_s = rdy_s + D * 4;                            // u32 [2] (+ pad)
+        slot_s = (rdyn_s + 8 + 15) & ~15u;
+    }
+    __device__ __forceinline__ static uint32_t ld32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+    __device__ __forceinline__ static void st32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+    // all threads of the CTA; followed by a barrier of the caller
+    __device__ __forceinline__ void reset(uint32_t t, uint32_t nthreads) {
+        for (uint32_t d = t; d < D; d += nthreads) { st32(cnt_s + 4 * d, 0u); st32(gpos_s + 4 * d, 0u); }
+        if (t < 2) st32(rdyn_s + 4 * t, 0u);
+        rnd = 0;
     }
     __device__ __forceinline__ uint32_t slot_addr(uint32_t slot, uint32_t d) const { return slot_s + (slot * D + d) * RECB; }
     __device__ __forceinline__ void store(uint32_t a, const Rec<RECW>& r) const {
@@ -93,56 +108,68 @@ struct Stage {
         else asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(r.hi), "=l"(r.lo) : "r"(a) : "memory");
         return r;
     }
-    // true: staged; false: the destination's slots are taken (the caller retries after the flush)
+    // true: staged; false: the destination's slots are taken (the caller retries in the next round)
     __device__ __forceinline__ bool put(uint32_t d, const Rec<RECW>& r) const {
         uint32_t pos;
         asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(cnt_s + 4 * d) : "memory");
         if (pos >= caps) return false;
         store(slot_addr(pos, d), r);
+        if (pos == SECT - 1) {                             // fewer than SECT were left over: this happens once per round and destination
+            uint32_t i;
+            asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(i) : "r"(rdyn_s + 4 * (rnd & 1u)) : "memory");
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(rdy_s + 2 * ((rnd & 1u) * D + i)), "h"((uint16_t)d) : "memory");
+        }
         return true;
     }
-    // destination d's whole sectors -> dst[gpos ...] (gpos, cap in records; dst is the destination's own region);
-    // what does not fit the region is spilled.  Leaves fewer than SECT records staged.
-    template <int W>
-    __device__ __forceinline__ void flush(uint32_t d, Rec<RECW>* dst, uint32_t& gpos, uint32_t cap, const PartitionPlan& plan,
-                                          unsigned long long* fill, Rec<RECW>* spill, DevStatus* status) const {
-        uint32_t n;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(n) : "r"(cnt_s + 4 * d) : "memory");
-        if (n < SECT) return;
-        n = min(n, caps);
-        const uint32_t q = n / SECT;
-        for (uint32_t s = 0; s < q; s++) {
-            if constexpr (RECW == 1) {
-                const Rec<1> r0 = load(slot_addr(4 * s, d)), r1 = load(slot_addr(4 * s + 1, d)), r2 = load(slot_addr(4 * s + 2, d)),
-                             r3 = load(slot_addr(4 * s + 3, d));
-                if (gpos + 4 <= cap) {
-                    asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(dst + gpos), "l"(r0.v), "l"(r1.v), "l"(r2.v), "l"(r3.v) : "memory");
-                    gpos += 4;
+    // after the round's barrier: the listed destinations' whole sectors -> their regions (region(d) = first record of
+    // destination d's region, cap records long); what does not fit the region is spilled.  Fewer than SECT records stay staged.
+    template <int W, typename RegionFn>
+    __device__ __forceinline__ void flush_round(uint32_t t, uint32_t nthreads, RegionFn region, uint32_t cap, const PartitionPlan& plan,
+                                                unsigned long long* fill, Rec<RECW>* spill, DevStatus* status) {
+        const uint32_t par = rnd & 1u;
+        const uint32_t n_ready = ld32(rdyn_s + 4 * par);
+        if (t == 0) st32(rdyn_s + 4 * (par ^ 1u), 0u);     // the other list was consumed a barrier ago
+        for (uint32_t i = t; i < n_ready; i += nthreads) {
+            uint32_t d;
+            { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(rdy_s + 2 * (par * D + i)) : "memory"); d = v; }
+            const uint32_t n = min(ld32(cnt_s + 4 * d), caps);
+            const uint32_t q = n / SECT;
+            uint32_t gpos = ld32(gpos_s + 4 * d);
+            Rec<RECW>* const dst = region(d);
+            for (uint32_t s = 0; s < q; s++) {
+                if constexpr (RECW == 1) {
+                    const Rec<1> r0 = load(slot_addr(4 * s, d)), r1 = load(slot_addr(4 * s + 1, d)), r2 = load(slot_addr(4 * s + 2, d)),
+                                 r3 = load(slot_addr(4 * s + 3, d));
+                    if (gpos + 4 <= cap) {
+                        asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(dst + gpos), "l"(r0.v), "l"(r1.v), "l"(r2.v), "l"(r3.v) : "memory");
+                        gpos += 4;
+                    } else {
+                        spill_record<W, 1>(r0, plan, fill, spill, status); spill_record<W, 1>(r1, plan, fill, spill, status);
+                        spill_record<W, 1>(r2, plan, fill, spill, status); spill_record<W, 1>(r3, plan, fill, spill, status);
+                    }
                 } else {
-                    spill_record<W, 1>(r0, plan, fill, spill, status); spill_record<W, 1>(r1, plan, fill, spill, status);
-                    spill_record<W, 1>(r2, plan, fill, spill, status); spill_record<W, 1>(r3, plan, fill, spill, status);
-                }
-            } else {
-                const Rec<2> r0 = load(slot_addr(2 * s, d)), r1 = load(slot_addr(2 * s + 1, d));
-                if (gpos + 2 <= cap) {
-                    asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(dst + gpos), "l"(r0.hi), "l"(r0.lo), "l"(r1.hi), "l"(r1.lo) : "memory");
-                    gpos += 2;
-                } else {
-                    spill_record<W, 2>(r0, plan, fill, spill, status); spill_record<W, 2>(r1, plan, fill, spill, status);
+                    const Rec<2> r0 = load(slot_addr(2 * s, d)), r1 = load(slot_addr(2 * s + 1, d));
+                    if (gpos + 2 <= cap) {
+                        asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(dst + gpos), "l"(r0.hi), "l"(r0.lo), "l"(r1.hi), "l"(r1.lo) : "memory");
+                        gpos += 2;
+                    } else {
+                        spill_record<W, 2>(r0, plan, fill, spill, status); spill_record<W, 2>(r1, plan, fill, spill, status);
+                    }
                 }
             }
+            const uint32_t left = n - q * SECT;
+            for (uint32_t j = 0; j < left; j++) store(slot_addr(j, d), load(slot_addr(q * SECT + j, d)));
+            st32(cnt_s + 4 * d, left);
+            st32(gpos_s + 4 * d, gpos);
         }
-        const uint32_t left = n - q * SECT;
-        for (uint32_t j = 0; j < left; j++) store(slot_addr(j, d), load(slot_addr(q * SECT + j, d)));
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(cnt_s + 4 * d), "r"(left) : "memory");
+        rnd++;
     }
-    // the last, partial sector of destination d at the end of the pass; returns the records now in the region
+    // after the last round (and a barrier): destination d's last, partial sector; returns the records now in the region
     template <int W>
-    __device__ __forceinline__ uint32_t finish(uint32_t d, Rec<RECW>* dst, uint32_t gpos, uint32_t cap, const PartitionPlan& plan,
-                                               unsigned long long* fill, Rec<RECW>* spill, DevStatus* status) const {
-        uint32_t n;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(n) : "r"(cnt_s + 4 * d) : "memory");
-        n = min(n, caps);
+    __device__ __forceinline__ uint32_t finish(uint32_t d, Rec<RECW>* dst, uint32_t cap, const PartitionPlan& plan, unsigned long long* fill,
+                                               Rec<RECW>* spill, DevStatus* status) const {
+        const uint32_t n = min(ld32(cnt_s + 4 * d), caps);
+        uint32_t gpos = ld32(gpos_s + 4 * d);
         for (uint32_t j = 0; j < n; j++) {
             const Rec<RECW> r = load(slot_addr(j, d));
             if (gpos < cap) dst[gpos++] = r;
@@ -160,7 +187,8 @@ __global__ void __launch_bounds__(NT, SCAT_MINB) scatter_kernel(ScanArgs a, Part
                                                                  Rec<RECW>* __restrict__ seg, unsigned long long* __restrict__ fill,
                                                                  Rec<RECW>* __restrict__ spill) {
     __shared__ ScanSmem s;
-    __shared__ uint32_t wruns_all[NT / 32][SCAT_RUNCAP];   // (coarse partition << 12) | tile-relative start base
+    __shared__ uint32_t wruns_h[NT / 32][SCAT_RUNCAP];     // minimizer hash of the run ...
+    __shared__ uint16_t wruns_p[NT / 32][SCAT_RUNCAP];     // ... and its tile-relative start base
     __shared__ uint32_t bdm[TILE / 32 + 2];                // bit p: a run cannot continue through window p (run start or invalid window)
     extern __shared__ __align__(16) unsigned char scat_dyn[];
     TileScanner sc(a, s);
@@ -171,13 +199,11 @@ __global__ void __launch_bounds__(NT, SCAT_MINB) scatter_kernel(ScanArgs a, Part
     const uint32_t D = sp.n_coarse;
     Stage<RECW> st;
     st.init(smem_u32(scat_dyn), D, sp.caps);
-    for (uint32_t d = t; d < D; d += NT) asm volatile("st.shared.u32 [%0], %1;" ::"r"(st.cnt_s + 4 * d), "r"(0u) : "memory");
+    st.reset(t, NT);
     if (t < 2) bdm[TILE / 32 + t] = 0xffffffffu;           // the tile end ends every run
-    uint32_t gpos[SCAT_DPT];                               // records written to the segments of destinations t, t+NT, ...
-#pragma unroll
-    for (int i = 0; i < SCAT_DPT; i++) gpos[i] = 0;
     Rec<RECW>* const myseg = seg + (uint64_t)blockIdx.x * D * sp.seg_cap;
-    uint32_t* const wruns = wruns_all[warp];
+    uint32_t* const wh = wruns_h[warp];
+    uint16_t* const wp = wruns_p[warp];
     __syncthreads();
 
     // the super-k-mer record of L windows starting at tile-relative base p
@@ -201,13 +227,8 @@ __global__ void __launch_bounds__(NT, SCAT_MINB) scatter_kernel(ScanArgs a, Part
         }
         return r;
     };
-    auto flush_all = [&]() {
-#pragma unroll
-        for (int i = 0; i < SCAT_DPT; i++) {
-            const uint32_t d = t + i * NT;
-            if (d < D) st.template flush<W>(d, myseg + (uint64_t)d * sp.seg_cap, gpos[i], sp.seg_cap, plan, fill, spill, a.status);
-        }
-    };
+    auto region = [&](uint32_t d) { return myseg + (uint64_t)d * sp.seg_cap; };
+    auto flush_all = [&]() { st.template flush_round<W>(t, NT, region, sp.seg_cap, plan, fill, spill, a.status); };
 
     while (sc.next()) {
         const uint32_t* bnd = sc.bnd();
@@ -304,15 +325,14 @@ __global__ void __launch_bounds__(NT, SCAT_MINB) scatter_kernel(ScanArgs a, Part
 #pragma unroll
                 for (int j = 0; j < 16; j++)
                     if ((starts >> j) & 1u) {
-                        if (rbase < (uint32_t)SCAT_RUNCAP)
-                            wruns[rbase] = ((__umulhi(mix32(h[j + 1]), plan.hash_buckets) >> plan.fine_shift) << 12) | (uint32_t)(16 * t + j);
+                        if (rbase < (uint32_t)SCAT_RUNCAP) { wh[rbase] = h[j + 1]; wp[rbase] = (uint16_t)(16 * t + j); }
                         rbase++;
                     }
             }
             __syncwarp();
             const uint32_t npass = min(n_warp_runs - pass0, (uint32_t)SCAT_RUNCAP);
             for (uint32_t r = lane; r < npass; r += 32) {             // run r of the pass: emitted by lane r % 32
-                const uint32_t d = wruns[r], dest = d >> 12, p0 = d & 4095u;
+                const uint32_t dest = __umulhi(mix32(wh[r]), plan.hash_buckets) >> plan.fine_shift, p0 = wp[r];
                 const uint32_t R = run_length(p0);
                 for (uint32_t off = 0; off < R; off += rmax) put(dest, make_record((int)(p0 + off), (int)min(R - off, rmax)));
             }
@@ -330,13 +350,8 @@ __global__ void __launch_bounds__(NT, SCAT_MINB) scatter_kernel(ScanArgs a, Part
         sc.stage ^= 1;                                                // release(): the barriers above already ordered the tile's reads
     }
     __syncthreads();
-#pragma unroll
-    for (int i = 0; i < SCAT_DPT; i++) {
-        const uint32_t d = t + i * NT;
-        if (d < D)
-            segfill[(uint64_t)blockIdx.x * D + d] =
-                st.template finish<W>(d, myseg + (uint64_t)d * sp.seg_cap, gpos[i], sp.seg_cap, plan, fill, spill, a.status);
-    }
+    for (uint32_t d = t; d < D; d += NT)
+        segfill[(uint64_t)blockIdx.x * D + d] = st.template finish<W>(d, region(d), sp.seg_cap, plan, fill, spill, a.status);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -354,13 +369,10 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) refine2_kernel(PartitionPlan p
     Stage<RECW> st;
     st.init(gk_s + ((F * 4 + 15) & ~15u), F, sp.caps2);
     for (uint32_t c = blockIdx.x; c < D; c += gridDim.x) {
-        uint32_t gpos = 0;                                        // thread f < F: records written to fine bucket f's region
-        if ((uint32_t)t < F) {
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(gk_s + 4 * t), "r"(0u) : "memory");
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(st.cnt_s + 4 * t), "r"(0u) : "memory");
-        }
+        if ((uint32_t)t < F) asm volatile("st.shared.u32 [%0], %1;" ::"r"(gk_s + 4 * t), "r"(0u) : "memory");
+        st.reset(t, RF2_THREADS);
         __syncthreads();
-        Rec<RECW>* const mydst = recs + ((uint64_t)c * F + t) * plan.cap;
+        auto region = [&](uint32_t f) { return recs + ((uint64_t)c * F + f) * plan.cap; };
         // warp w reads the segments w, w+NW, ... of the partition, 32*RF2_RQ records per round
         uint32_t src = warp, off = 0, n_s = 0;
         auto next_segment = [&]() {                               // skip empty segments
@@ -410,17 +422,17 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) refine2_kernel(PartitionPlan p
                 }
             }
             const int any_pending = __syncthreads_or(pend_f != 0xffffffffu);
-            if ((uint32_t)t < F) st.template flush<W>(t, mydst, gpos, plan.cap, plan, fill, spill, status);
+            st.template flush_round<W>(t, RF2_THREADS, region, plan.cap, plan, fill, spill, status);
             if (any_pending) {
                 __syncthreads();
                 if (pend_f != 0xffffffffu && !st.put(pend_f, pend)) spill_record<W, RECW>(pend, plan, fill, spill, status);
                 __syncthreads();
-                if ((uint32_t)t < F) st.template flush<W>(t, mydst, gpos, plan.cap, plan, fill, spill, status);
+                st.template flush_round<W>(t, RF2_THREADS, region, plan.cap, plan, fill, spill, status);
             }
             if (!__syncthreads_or(src < sp.n_src)) break;
         }
         if ((uint32_t)t < F) {
-            const uint32_t total = st.template finish<W>(t, mydst, gpos, plan.cap, plan, fill, spill, status);
+            const uint32_t total = st.template finish<W>(t, region(t), plan.cap, plan, fill, spill, status);
             uint32_t gk;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(gk) : "r"(gk_s + 4 * t) : "memory");
             atomicOr(&fill[(uint64_t)c * F + t], ((unsigned long long)gk << 32) | total);   // keeps a poison bit set by either pass

@@ -23,6 +23,8 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
+KMER_ERR_CAPACITY = 20   # include/kmer_cuda.h
+
 
 class ShardedCounter:
     def __init__(self, engine, group=None, device=None, chunks=None):
@@ -70,12 +72,18 @@ class ShardedCounter:
         return list(self.eng.phases()) if hasattr(self.eng, "phases") else []
 
     def _agree(self, exc):
-        """All ranks raise if any rank failed (the lowest failing rank's error text wins on that rank only)."""
-        bad = self._allreduce_int(0 if exc is None else 1, dist.ReduceOp.MAX)
+        """All ranks raise if any rank failed with an INPUT error (the lowest failing rank's error text wins on that rank
+        only).  Returns True if some rank only ran out of room (KMER_ERR_CAPACITY: segment / spill list / output overflow on
+        skewed input) and nothing worse happened anywhere: every rank then takes the exact fallback together."""
+        code = 0
         if exc is not None:
-            raise exc
-        if bad:
+            code = 1 if getattr(exc, "status", None) == KMER_ERR_CAPACITY else 2
+        worst = self._allreduce_int(code, dist.ReduceOp.MAX)
+        if worst == 2:
+            if exc is not None and code == 2:
+                raise exc
             raise RuntimeError("sharded count aborted: another rank reported an input error")
+        return worst == 1
 
     # ------------------------------------------------------------------ the operation
     def count(self, d_seq, n_bases: int, d_off, n_rows: int, k: int, d_pairs, total_kmers: int | None = None, d_uniq=None):
@@ -158,23 +166,78 @@ class ShardedCounter:
             if timed:
                 torch.cuda.synchronize()
                 phases.append(("all_to_all", sum(a.elapsed_time(b) for a, b in a2a_events)))
-        self._agree(exc)
+        if self._agree(exc):
+            return self._count_fallback(d_seq, n_bases, d_off, n_rows, k, d_pairs, total_kmers)
         if self.world > 1:
             self.last_exchange_bytes = int(recs_bytes + fill_words * 8) * chunks * (self.world - 1) // self.world
         else:
             self.last_exchange_bytes = 0
-        if d_uniq is not None:
-            eng.dev_shard_count_split(plan, recv_recs, recv_fill, d_uniq, d_pairs)
-        else:
-            eng.dev_shard_count(plan, recv_recs, recv_fill, d_pairs)
-        r = eng.dev_finish()
+        r, exc = None, None
+        try:
+            if d_uniq is not None:
+                eng.dev_shard_count_split(plan, recv_recs, recv_fill, d_uniq, d_pairs)
+            else:
+                eng.dev_shard_count(plan, recv_recs, recv_fill, d_pairs)
+            r = eng.dev_finish()
+        except Exception as e:        # spill list / output overflow on this rank: no rank may be left waiting in a collective
+            exc = e
+        if self._agree(exc):
+            return self._count_fallback(d_seq, n_bases, d_off, n_rows, k, d_pairs, total_kmers)
         phases += self._phases()
         self.last_phases = phases
         counted = self._allreduce_int(int(r.n_kmers))
         if counted != total_kmers:
             raise RuntimeError(f"sharded count lost k-mers: counted {counted}, expected {total_kmers}")
         return int(r.n_distinct), int(r.n_kmers), {"tier2_kmers": int(r.n_tier2), "plan": plan,
-                                                  "n_unique": int(getattr(r, "n_unique", 0))}
+                                                  "n_unique": int(getattr(r, "n_unique", 0)), "fallback": False}
+
+    def _count_fallback(self, d_seq, n_bases, d_off, n_rows, k, d_pairs, total_kmers):
+        """Exact on ANY input (HashAggregate never refuses rows, kmer-tests.sql:1208-1213): every rank counts its own rows with
+        the single-GPU counter (tiers 2/3 absorb any skew), then the tables are merged by owner = hash(k-mer) % world: the
+        ranks' tables are broadcast in turn and every rank keeps the groups it owns.  Slower than the minimizer exchange
+        (whole tables travel), only taken when that one ran out of room."""
+        eng = self.eng
+        cap_local = max(eng.max_kmers(n_bases, n_rows, k), 1)
+        local = self._buf("fb_local", cap_local * 16, torch.int64).view(-1, 2)
+        exc, n_loc = None, 0
+        try:
+            eng.dev_count(d_seq, n_bases, d_off, n_rows, k, local)
+            n_loc = int(eng.dev_finish().n_distinct)
+        except Exception as e:
+            exc = e
+        if self._agree(exc):
+            raise exc if exc is not None else RuntimeError("sharded count aborted: another rank ran out of memory")
+        counts = [n_loc]
+        if self.world > 1:
+            t = torch.tensor([n_loc], dtype=torch.int64, device=self.device)
+            all_n = [torch.zeros_like(t) for _ in range(self.world)]
+            dist.all_gather(all_n, t, group=self.group)
+            counts = [int(x.item()) for x in all_n]
+        # the owner hash spreads DISTINCT k-mers evenly whatever their counts: this rank owns about sum/world groups
+        eng.dev_merge_begin(int(sum(counts) / self.world * 1.3) + 65536)
+        buf = self._buf("fb_bcast", max(max(counts), 1) * 16, torch.int64).view(-1, 2) if self.world > 1 else local
+        for src in range(self.world):
+            if counts[src] == 0:
+                continue
+            if self.world > 1:
+                if src == self.rank:
+                    buf[:counts[src]].copy_(local[:counts[src]])
+                dist.broadcast(buf[:counts[src]], src, group=self.group)
+            eng.dev_merge_add(buf, counts[src], self.rank, self.world)
+        exc, r = None, None
+        try:
+            eng.dev_merge_emit(k, d_pairs)
+            r = eng.dev_finish()
+        except Exception as e:
+            exc = e
+        if self._agree(exc) or exc is not None:
+            raise exc if exc is not None else RuntimeError("sharded count aborted: another rank's output buffer is too small")
+        self.last_exchange_bytes = int(sum(counts) * 16)
+        self.last_phases = []
+        counted = self._allreduce_int(int(r.n_kmers))
+        if counted != total_kmers:
+            raise RuntimeError(f"sharded fallback lost k-mers: counted {counted}, expected {total_kmers}")
+        return int(r.n_distinct), int(r.n_kmers), {"tier2_kmers": 0, "plan": None, "n_unique": 0, "fallback": True}
 
     def _count_dense(self, d_seq, n_bases, d_off, n_rows, k, d_pairs, total_kmers):
         eng = self.eng
@@ -185,12 +248,19 @@ class ShardedCounter:
             eng.dev_finish()
         except Exception as e:
             exc = e
-        self._agree(exc)
+        if self._agree(exc):
+            raise exc
         if self.world > 1:
             dist.all_reduce(table, op=dist.ReduceOp.SUM, group=self.group)
             self.last_exchange_bytes = int(table.numel() * 8)
-        eng.dev_dense_emit(table, k, self.rank, self.world, d_pairs)
-        r = eng.dev_finish()
+        r = None
+        try:
+            eng.dev_dense_emit(table, k, self.rank, self.world, d_pairs)
+            r = eng.dev_finish()
+        except Exception as e:            # output buffer too small on this rank: all ranks raise together
+            exc = e
+        if self._agree(exc) or exc is not None:
+            raise exc if exc is not None else RuntimeError("sharded dense count aborted: another rank's output buffer is too small")
         counted = self._allreduce_int(int(r.n_kmers))
         if counted != total_kmers:
             raise RuntimeError(f"sharded dense count lost k-mers: counted {counted}, expected {total_kmers}")

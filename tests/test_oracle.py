@@ -200,3 +200,25 @@ def test_oracle_vs_ref_live(ref, corc):
         want = ref.predicate_column(op, col.reshape(-1), 12, const)
         assert np.array_equal(corc.match_column(orc_op, codes, 12, const), want)
         assert np.array_equal(O.np_match(orc_op, codes, 12, const), want)
+
+
+def test_multiset_checksum_matches_tables(corc):
+    """orc_multiset_checksum (the config-scale parity check of bench.py): sum of mix64(code) over the windows of the rows
+    == sum of count * mix64(code) over the GROUP BY table, for the C port, the numpy port and -- when built -- the reference."""
+    from kmer_extension_b200 import datagen
+    for seed, k in ((1, 5), (2, 21), (3, 31), (4, 32), (5, 1), (6, 14)):
+        flat, off = datagen.synth_ragged(seed, 300, 200, min_len=33, mixed_case=True)
+        s, n = corc.multiset_checksum(flat, off, k)
+        keys, counts, nk = O.np_count(flat, off, k)
+        assert n == nk == int(counts.sum())
+        assert s == O.np_table_checksum(keys, counts)
+        ck, cc, cn = corc.count(flat, off, k)
+        assert s == O.np_table_checksum(ck, cc) and cn == n
+    # a table with one group split in two, or one count off by one, must not pass
+    flat, off = datagen.synth_reads(9, 50, 300)
+    s, n = corc.multiset_checksum(flat, off, 21)
+    keys, counts, _ = O.np_count(flat, off, 21)
+    bad = counts.copy(); bad[0] += 1
+    assert O.np_table_checksum(keys, bad) != s
+    with pytest.raises(O.OracleError):
+        corc.multiset_checksum(np.frombuffer(b"ACGTNACGT", np.uint8), np.array([0, 9], np.uint64), 3)

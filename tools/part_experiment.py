@@ -10,7 +10,7 @@ n_rows = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 flat, off = datagen.synth_reads(2, n_rows, 1000)
 d_seq = torch.from_numpy(np.concatenate([flat, np.zeros(64, np.uint8)])).cuda()
 d_off = torch.from_numpy(off.astype(np.int64)).cuda()
-eng = api.KmerCuda(0)
+eng = api.KmerCuda(0, os.environ.get('KMER_CUDA_LIB', api.LIB_PATH))
 KK = int(os.environ.get("KMER_K", "21"))
 cap = eng.max_kmers(int(off[-1]), n_rows, KK)
 d_pairs = torch.empty((cap, 2), dtype=torch.int64, device="cuda")
