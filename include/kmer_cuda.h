@@ -283,6 +283,24 @@ int kmer_cuda_dev_merge_add(kmer_cuda_ctx *ctx, const kmer_count_pair *d_pairs, 
 							void *stream);
 int kmer_cuda_dev_merge_emit(kmer_cuda_ctx *ctx, int k, kmer_count_pair *d_pairs, uint64_t pairs_capacity, void *stream);
 
+/* ---------------------------------------------------------------- several GPUs, one process (no Python, no NCCL)
+ * What the PostgreSQL glue links when the box has more than one GPU ("Host code stays C ... calls CUDA through a thin C-ABI
+ * layer"): the device list is given once; kmer_cuda_multi_submit_count splits the rows evenly over the devices, runs the
+ * sharded count above with the exchange done as peer copies over NVLink, and hands back ONE TABLE PER DEVICE:
+ * pairs[d][0 .. n_distinct[d]) for d < kmer_cuda_multi_device_count().  The tables are disjoint, their union is the result of
+ * `SELECT kmer, count(*) ... GROUP BY kmer` over all rows (kmer.c:289-351 + kmer_hash_ops).  Same errors as
+ * kmer_cuda_submit_count, the first offending row of the whole batch decides.  Input the minimizer exchange refuses (highly
+ * repetitive rows) and k <= 13 are counted per device and merged by owner, reading the peers' tables over NVLink.
+ * Each table is released with kmer_cuda_multi_release(m, d, pairs[d]). */
+typedef struct kmer_cuda_multi kmer_cuda_multi;
+int kmer_cuda_init_multi(kmer_cuda_multi **m, const int *devices, int n_devices);
+void kmer_cuda_shutdown_multi(kmer_cuda_multi *m);
+int kmer_cuda_multi_device_count(const kmer_cuda_multi *m);
+const kmer_cuda_error *kmer_cuda_multi_last_error(const kmer_cuda_multi *m);
+int kmer_cuda_multi_submit_count(kmer_cuda_multi *m, const char *seq, const uint64_t *row_off, uint64_t n_rows, int k,
+								 kmer_count_pair **pairs, uint64_t *n_distinct, uint64_t *n_kmers);
+void kmer_cuda_multi_release(kmer_cuda_multi *m, int device_index, void *result);
+
 /* Upper bound of the number of k-mers (= groups) a batch can produce: n_bases - n_rows*(k-1). */
 uint64_t kmer_cuda_max_kmers(uint64_t n_bases, uint64_t n_rows, int k);
 

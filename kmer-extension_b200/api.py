@@ -41,6 +41,8 @@ ABI_SYMBOLS = [
     "kmer_cuda_shard_plan", "kmer_cuda_dev_shard_partition", "kmer_cuda_dev_shard_count", "kmer_cuda_dev_dense_table",
     "kmer_cuda_dev_dense_emit", "kmer_cuda_submit_count_split", "kmer_cuda_dev_count_split", "kmer_cuda_submit_count_packed", "kmer_cuda_shard_plan_chunked", "kmer_cuda_dev_shard_count_split",
     "kmer_cuda_dev_merge_begin", "kmer_cuda_dev_merge_add", "kmer_cuda_dev_merge_emit", "kmer_cuda_test_force_window",
+    "kmer_cuda_init_multi", "kmer_cuda_shutdown_multi", "kmer_cuda_multi_device_count", "kmer_cuda_multi_last_error",
+    "kmer_cuda_multi_submit_count", "kmer_cuda_multi_release",
 ]
 
 

@@ -1430,3 +1430,293 @@ extern "C" int kmer_cuda_submit_encode(kmer_cuda_ctx* c, const char* text, const
     *codes = out;
     return KMER_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// several GPUs behind the C ABI, one process (kmer_cuda_init_multi): the rows are split evenly over the devices, every
+// device partitions its share into the coarse minimizer partitions of ALL devices, the segments cross NVLink as peer copies
+// (cudaMemcpyPeerAsync: one copy per ordered pair of devices, all pairs at once), every device counts the partitions it
+// owns.  Same kernels and plan as the one-process-per-GPU path (sharded.py), no NCCL and no Python: what the PostgreSQL
+// glue links.  Input the minimizer exchange refuses (a segment or the spill list overflows) and k <= 13 take the exact
+// merge: per-device GROUP BY, then every device keeps the groups it owns, reading its peers' tables over NVLink.
+
+struct kmer_cuda_multi {
+    std::vector<kmer_cuda_ctx*> ctx;
+    std::vector<int> dev;
+    kmer_cuda_error err{};
+    struct PerDev {
+        Buf send, sendfill, recv, recvfill, local;
+        uint64_t* h_off = nullptr;   // pinned: this device's row offsets, rebased to its first base
+        size_t h_off_cap = 0;
+        uint64_t n_local = 0;        // groups of the device's own GROUP BY (merge path)
+    };
+    std::vector<PerDev> d;
+};
+
+static int multi_fail(kmer_cuda_multi* m, const kmer_cuda_ctx* c) {
+    m->err = c->err;
+    return c->err.status ? c->err.status : KMER_ERR_CUDA;
+}
+
+extern "C" int kmer_cuda_init_multi(kmer_cuda_multi** out, const int* devices, int n_devices) {
+    if (!out || !devices || n_devices < 1 || n_devices > 16)
+        return set_error(&g_init_error, KMER_ERR_BAD_ARGUMENT, "XX000", "kmer_cuda: bad argument: device list (1..16 devices)", "", -1);
+    *out = nullptr;
+    kmer_cuda_multi* m = new (std::nothrow) kmer_cuda_multi();
+    if (!m) return set_error(&g_init_error, KMER_ERR_OOM, "53200", "kmer_cuda: out of host memory", "", -1);
+    for (int i = 0; i < n_devices; i++) {
+        kmer_cuda_ctx* c = nullptr;
+        int rc = kmer_cuda_init(&c, devices[i]);
+        if (rc) {
+            for (auto x : m->ctx) kmer_cuda_shutdown(x);
+            delete m;
+            return rc;
+        }
+        m->ctx.push_back(c);
+        m->dev.push_back(devices[i]);
+    }
+    m->d.resize(n_devices);
+    // peer access both ways (kernels of the merge path read peer tables directly); the same device twice is fine
+    for (int i = 0; i < n_devices; i++)
+        for (int j = 0; j < n_devices; j++) {
+            if (devices[i] == devices[j]) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, devices[i], devices[j]);
+            if (!can) continue;
+            cudaSetDevice(devices[i]);
+            cudaError_t ce = cudaDeviceEnablePeerAccess(devices[j], 0);
+            if (ce != cudaSuccess) cudaGetLastError();   // already enabled
+        }
+    m->err.status = KMER_OK;
+    m->err.row = -1;
+    *out = m;
+    return KMER_OK;
+}
+
+extern "C" void kmer_cuda_shutdown_multi(kmer_cuda_multi* m) {
+    if (!m) return;
+    for (size_t i = 0; i < m->ctx.size(); i++) {
+        cudaSetDevice(m->dev[i]);
+        cudaStreamSynchronize(m->ctx[i]->stream);
+        auto& d = m->d[i];
+        Buf* all[] = {&d.send, &d.sendfill, &d.recv, &d.recvfill, &d.local};
+        for (Buf* b : all) buf_free(*b);
+        if (d.h_off) cudaFreeHost(d.h_off);
+        kmer_cuda_shutdown(m->ctx[i]);
+    }
+    delete m;
+}
+
+extern "C" int kmer_cuda_multi_device_count(const kmer_cuda_multi* m) { return m ? (int)m->ctx.size() : 0; }
+extern "C" const kmer_cuda_error* kmer_cuda_multi_last_error(const kmer_cuda_multi* m) { return m ? &m->err : &g_init_error; }
+extern "C" void kmer_cuda_multi_release(kmer_cuda_multi* m, int device_index, void* result) {
+    if (m && device_index >= 0 && device_index < (int)m->ctx.size()) kmer_cuda_release(m->ctx[device_index], result);
+}
+
+// per-device GROUP BY of the device's own rows, then the merge by owner over peer memory
+static int multi_count_merge(kmer_cuda_multi* m, const std::vector<uint64_t>& nb, const std::vector<uint64_t>& nr, int k,
+                             kmer_count_pair** pairs, uint64_t* n_distinct, uint64_t* n_kmers) {
+    const int n = (int)m->ctx.size();
+    uint64_t total_groups = 0, total_kmers = 0;
+    for (int i = 0; i < n; i++) {
+        kmer_cuda_ctx* c = m->ctx[i];
+        cudaSetDevice(m->dev[i]);
+        uint64_t cap = kmer_cuda_max_kmers(nb[i], nr[i], k);
+        if (k >= 1 && k < 32 && (1ull << (2 * k)) < cap) cap = 1ull << (2 * k);
+        int rc = ws(c, m->d[i].local, (cap ? cap : 1) * sizeof(kmer_count_pair));
+        if (rc) return multi_fail(m, c);
+        rc = kmer_cuda_dev_count(c, (const char*)c->seq.p, nb[i], (const uint64_t*)c->off.p, nr[i], k, (kmer_count_pair*)m->d[i].local.p, cap, 0,
+                                 KMER_OWN_STREAM);
+        if (rc) return multi_fail(m, c);
+    }
+    for (int i = 0; i < n; i++) {
+        kmer_dev_result res;
+        cudaSetDevice(m->dev[i]);
+        int rc = kmer_cuda_dev_finish(m->ctx[i], KMER_OWN_STREAM, &res);
+        if (rc) {                                        // rows of device i: report the row index within the whole batch
+            m->err = m->ctx[i]->err;
+            return rc;
+        }
+        m->d[i].n_local = res.n_distinct;
+        total_groups += res.n_distinct;
+        total_kmers += res.n_kmers;
+    }
+    // the owner hash spreads DISTINCT k-mers evenly whatever their counts: a device owns about total/n groups
+    const uint64_t own_cap = (uint64_t)((double)total_groups / n * 1.3) + 65536;
+    for (int j = 0; j < n; j++) {
+        kmer_cuda_ctx* c = m->ctx[j];
+        cudaSetDevice(m->dev[j]);
+        int rc = ws(c, c->pairs, own_cap * sizeof(kmer_count_pair));
+        if (!rc) rc = kmer_cuda_dev_merge_begin(c, own_cap, KMER_OWN_STREAM);
+        for (int i = 0; i < n && !rc; i++)
+            rc = kmer_cuda_dev_merge_add(c, (const kmer_count_pair*)m->d[i].local.p, m->d[i].n_local, (uint32_t)j, (uint32_t)n, KMER_OWN_STREAM);
+        if (!rc) rc = kmer_cuda_dev_merge_emit(c, k, (kmer_count_pair*)c->pairs.p, own_cap, KMER_OWN_STREAM);
+        if (rc) return multi_fail(m, c);
+    }
+    uint64_t counted = 0;
+    for (int j = 0; j < n; j++) {
+        kmer_cuda_ctx* c = m->ctx[j];
+        cudaSetDevice(m->dev[j]);
+        kmer_dev_result res;
+        int rc = kmer_cuda_dev_finish(c, KMER_OWN_STREAM, &res);
+        if (rc) return multi_fail(m, c);
+        kmer_count_pair* out = (kmer_count_pair*)pinned_get(c, res.n_distinct * sizeof(kmer_count_pair));
+        if (!out) return multi_fail(m, c);
+        if (cudaMemcpyAsync(out, c->pairs.p, res.n_distinct * sizeof(kmer_count_pair), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) {
+            kmer_cuda_release(c, out);
+            cuda_error(c, cudaGetLastError(), "D2H pairs");
+            return multi_fail(m, c);
+        }
+        pairs[j] = out;
+        n_distinct[j] = res.n_distinct;
+        counted += res.n_kmers;
+    }
+    for (int j = 0; j < n; j++) {
+        cudaSetDevice(m->dev[j]);
+        cudaStreamSynchronize(m->ctx[j]->stream);
+    }
+    if (counted != total_kmers) {
+        set_error(&m->err, KMER_ERR_CUDA, "XX000", "kmer_cuda: internal error: merged k-mers != counted k-mers", "", -1);
+        return KMER_ERR_CUDA;
+    }
+    if (n_kmers) *n_kmers = counted;
+    return KMER_OK;
+}
+
+extern "C" int kmer_cuda_multi_submit_count(kmer_cuda_multi* m, const char* seq, const uint64_t* row_off, uint64_t n_rows, int k,
+                                            kmer_count_pair** pairs, uint64_t* n_distinct, uint64_t* n_kmers) {
+    if (!m || !pairs || !n_distinct) return KMER_ERR_BAD_ARGUMENT;
+    const int n = (int)m->ctx.size();
+    for (int i = 0; i < n; i++) { pairs[i] = nullptr; n_distinct[i] = 0; }
+    if (n_kmers) *n_kmers = 0;
+    m->err.status = KMER_OK;
+    if (n == 1) {
+        int rc = kmer_cuda_submit_count(m->ctx[0], seq, row_off, n_rows, k, &pairs[0], &n_distinct[0], n_kmers);
+        if (rc) m->err = m->ctx[0]->err;
+        return rc;
+    }
+    if (n_rows && (!row_off || row_off[0] != 0 || (row_off[n_rows] && !seq))) {
+        set_error(&m->err, KMER_ERR_BAD_ARGUMENT, "XX000", "kmer_cuda: bad argument: seq / row_off", "", -1);
+        return KMER_ERR_BAD_ARGUMENT;
+    }
+    if (n_rows && (k < 1 || k > KMER_CUDA_MAX_K)) return ref_error(&m->err, KMER_ERR_INVALID_K, 0);
+    // 1. rows split evenly; every device gets its slice of the column and its offsets rebased to 0
+    std::vector<uint64_t> r0(n + 1), nb(n), nr(n);
+    for (int i = 0; i <= n; i++) r0[i] = n_rows * (uint64_t)i / n;
+    uint64_t total_kmers = 0;
+    for (int i = 0; i < n; i++) {
+        kmer_cuda_ctx* c = m->ctx[i];
+        auto& d = m->d[i];
+        cudaSetDevice(m->dev[i]);
+        nr[i] = r0[i + 1] - r0[i];
+        const uint64_t base = n_rows ? row_off[r0[i]] : 0;
+        nb[i] = n_rows ? row_off[r0[i + 1]] - base : 0;
+        total_kmers += kmer_cuda_max_kmers(nb[i], nr[i], k);
+        if (d.h_off_cap < nr[i] + 1) {
+            if (d.h_off) cudaFreeHost(d.h_off);
+            d.h_off = nullptr;
+            d.h_off_cap = 0;
+            if (cudaHostAlloc((void**)&d.h_off, (nr[i] + 1) * 8, cudaHostAllocDefault) != cudaSuccess) {
+                cuda_error(c, cudaGetLastError(), "cudaHostAlloc");
+                return multi_fail(m, c);
+            }
+            d.h_off_cap = nr[i] + 1;
+        }
+        for (uint64_t r = 0; r <= nr[i]; r++) d.h_off[r] = row_off[r0[i] + r] - base;
+        int rc = ws(c, c->seq, ((nb[i] + 15) & ~15ull) + 64);
+        if (!rc) rc = ws(c, c->off, (nr[i] + 1) * 8);
+        if (!rc) rc = h2d(c, c->seq.p, seq + base, nb[i], c->stream);
+        if (!rc) rc = h2d(c, c->off.p, d.h_off, (nr[i] + 1) * 8, c->stream);
+        if (rc) return multi_fail(m, c);
+    }
+    auto rebase_error_row = [&](int i) {                  // a device reports rows of its slice
+        if (m->err.row >= 0) m->err.row += (int64_t)r0[i];
+    };
+    if (k <= 13 || total_kmers == 0) {
+        int rc = multi_count_merge(m, nb, nr, k, pairs, n_distinct, n_kmers);
+        if (rc && (rc == KMER_ERR_INVALID_DNA || rc == KMER_ERR_INVALID_K))
+            for (int i = 0; i < n; i++) if (m->ctx[i]->err.status == rc) { m->err = m->ctx[i]->err; rebase_error_row(i); break; }
+        return rc;
+    }
+    // 2. the sharded path: partition on every device, peer copies, count on every owner
+    kmer_shard_plan sp;
+    if (kmer_cuda_shard_plan(total_kmers, k, (uint32_t)n, &sp) != KMER_OK) {
+        set_error(&m->err, KMER_ERR_BAD_ARGUMENT, "XX000", "kmer_cuda: no shard plan for this job", "", -1);
+        return KMER_ERR_BAD_ARGUMENT;
+    }
+    const size_t rb = sp.recs_bytes_per_peer, fb = sp.fill_bytes_per_peer;
+    for (int i = 0; i < n; i++) {
+        kmer_cuda_ctx* c = m->ctx[i];
+        auto& d = m->d[i];
+        cudaSetDevice(m->dev[i]);
+        int rc = ws(c, d.send, rb * n);
+        if (!rc) rc = ws(c, d.sendfill, fb * n);
+        if (!rc) rc = ws(c, d.recv, rb * n);
+        if (!rc) rc = ws(c, d.recvfill, fb * n);
+        if (!rc) rc = kmer_cuda_dev_shard_partition(c, (const char*)c->seq.p, nb[i], (const uint64_t*)c->off.p, nr[i], &sp, d.send.p,
+                                                    (uint64_t*)d.sendfill.p, KMER_OWN_STREAM);
+        if (rc) return multi_fail(m, c);
+    }
+    bool capacity = false;
+    int first_err = KMER_OK, first_dev = -1;
+    for (int i = 0; i < n; i++) {                         // the first offending ROW of the batch decides, as in a sequential scan
+        cudaSetDevice(m->dev[i]);
+        int rc = kmer_cuda_dev_finish(m->ctx[i], KMER_OWN_STREAM, nullptr);
+        if (rc == KMER_ERR_CAPACITY) capacity = true;
+        else if (rc && first_err == KMER_OK) { first_err = rc; first_dev = i; }
+    }
+    if (first_err) {
+        m->err = m->ctx[first_dev]->err;
+        rebase_error_row(first_dev);
+        return first_err;
+    }
+    if (!capacity) {
+        for (int i = 0; i < n; i++)                       // segment block j of device i -> slot i of device j, over NVLink
+            for (int j = 0; j < n; j++) {
+                cudaError_t ce = cudaMemcpyPeerAsync((char*)m->d[j].recv.p + rb * i, m->dev[j], (const char*)m->d[i].send.p + rb * j, m->dev[i], rb,
+                                                     m->ctx[i]->stream);
+                if (ce == cudaSuccess)
+                    ce = cudaMemcpyPeerAsync((char*)m->d[j].recvfill.p + fb * i, m->dev[j], (const char*)m->d[i].sendfill.p + fb * j, m->dev[i], fb,
+                                             m->ctx[i]->stream);
+                if (ce != cudaSuccess) { cuda_error(m->ctx[i], ce, "cudaMemcpyPeerAsync"); return multi_fail(m, m->ctx[i]); }
+            }
+        for (int i = 0; i < n; i++) { cudaSetDevice(m->dev[i]); cudaStreamSynchronize(m->ctx[i]->stream); }
+        const uint64_t own_cap = (uint64_t)((double)total_kmers / n * 1.15) + (1u << 20);
+        for (int j = 0; j < n; j++) {
+            kmer_cuda_ctx* c = m->ctx[j];
+            cudaSetDevice(m->dev[j]);
+            int rc = ws(c, c->pairs, own_cap * sizeof(kmer_count_pair));
+            if (!rc) rc = kmer_cuda_dev_shard_count(c, &sp, m->d[j].recv.p, (const uint64_t*)m->d[j].recvfill.p, (kmer_count_pair*)c->pairs.p,
+                                                    own_cap, KMER_OWN_STREAM);
+            if (rc) return multi_fail(m, c);
+        }
+        std::vector<kmer_dev_result> res(n);
+        for (int j = 0; j < n; j++) {
+            cudaSetDevice(m->dev[j]);
+            int rc = kmer_cuda_dev_finish(m->ctx[j], KMER_OWN_STREAM, &res[j]);
+            if (rc == KMER_ERR_CAPACITY) capacity = true;
+            else if (rc) return multi_fail(m, m->ctx[j]);
+        }
+        if (!capacity) {
+            uint64_t counted = 0;
+            for (int j = 0; j < n; j++) {
+                kmer_cuda_ctx* c = m->ctx[j];
+                cudaSetDevice(m->dev[j]);
+                kmer_count_pair* out = (kmer_count_pair*)pinned_get(c, res[j].n_distinct * sizeof(kmer_count_pair));
+                if (!out) return multi_fail(m, c);
+                cudaMemcpyAsync(out, c->pairs.p, res[j].n_distinct * sizeof(kmer_count_pair), cudaMemcpyDeviceToHost, c->stream);
+                pairs[j] = out;
+                n_distinct[j] = res[j].n_distinct;
+                counted += res[j].n_kmers;
+            }
+            for (int j = 0; j < n; j++) { cudaSetDevice(m->dev[j]); cudaStreamSynchronize(m->ctx[j]->stream); }
+            if (counted != total_kmers) {
+                set_error(&m->err, KMER_ERR_CUDA, "XX000", "kmer_cuda: internal error: counted k-mers != windows", "", -1);
+                return KMER_ERR_CUDA;
+            }
+            if (n_kmers) *n_kmers = counted;
+            return KMER_OK;
+        }
+    }
+    // 3. the exchange ran out of room somewhere (skewed input): exact merge instead
+    return multi_count_merge(m, nb, nr, k, pairs, n_distinct, n_kmers);
+}

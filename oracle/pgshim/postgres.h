@@ -63,6 +63,19 @@ static inline MemoryContext MemoryContextSwitchTo(MemoryContext c) { return c; }
 
 #define PointerGetDatum(p) ((Datum) (uintptr_t) (p))
 #define DatumGetPointer(d) ((void *) (uintptr_t) (d))
+#define Int64GetDatum(x) ((Datum) (int64_t) (x))
+#define DatumGetInt64(d) ((int64_t) (d))
+#define BoolGetDatum(x) ((Datum) ((x) ? 1 : 0))
+#define DatumGetBool(d) ((bool) ((d) != 0))
+#define PG_DETOAST_DATUM(d) ((struct varlena *) DatumGetPointer(d)) /* nothing is ever toasted here */
+typedef int64_t int64;
+extern void pgshim_pfree(void *p);
+#define pfree(p) pgshim_pfree(p)
+/* PG_TRY / PG_CATCH / PG_END_TRY / PG_RE_THROW over the same longjmp handler chain ereport() uses */
+#define PG_TRY() do { jmp_buf *pgshim_saved_ = pgshim_handler; jmp_buf pgshim_local_; pgshim_handler = &pgshim_local_; if (setjmp(pgshim_local_) == 0) {
+#define PG_CATCH() pgshim_handler = pgshim_saved_; } else { pgshim_handler = pgshim_saved_;
+#define PG_END_TRY() } } while (0)
+#define PG_RE_THROW() pgshim_throw()
 
 /* ---- errors ---- */
 #define ERROR 21

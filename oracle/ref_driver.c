@@ -107,6 +107,35 @@ char *pgshim_psprintf(const char *fmt, ...)
 	return p;
 }
 
+void pgshim_pfree(void *p) { (void) p; } /* bump arena: freed by the reset */
+
+/* composite results for the GPU glue's SRFs (funcapi.h) */
+TypeFuncClass pgshim_get_call_result_type(FunctionCallInfo fcinfo, Oid *resultTypeId, TupleDesc *resultTupleDesc)
+{
+	(void) fcinfo;
+	if (resultTypeId)
+		*resultTypeId = 0;
+	TupleDesc d = (TupleDesc) pgshim_palloc(sizeof(*d));
+	d->natts = 2;
+	*resultTupleDesc = d;
+	return TYPEFUNC_COMPOSITE;
+}
+
+HeapTuple pgshim_heap_form_tuple(TupleDesc desc, Datum *values, bool *isnull)
+{
+	HeapTuple t = (HeapTuple) pgshim_palloc(sizeof(*t));
+	t->natts = desc->natts;
+	for (int i = 0; i < desc->natts && i < 8; i++)
+	{
+		t->values[i] = values[i];
+		t->nulls[i] = isnull ? isnull[i] : false;
+	}
+	return t;
+}
+
+/* exported for test drivers outside this file (tests/c/glue_driver.c): per-statement reset of the palloc arena */
+void pgshim_reset(void);
+
 FuncCallContext *pgshim_srf_firstcall_init(FunctionCallInfo fcinfo)
 {
 	FuncCallContext *c = (FuncCallContext *) pgshim_palloc(sizeof(FuncCallContext));
@@ -115,6 +144,8 @@ FuncCallContext *pgshim_srf_firstcall_init(FunctionCallInfo fcinfo)
 	fcinfo->srf_ctx = c;
 	return c;
 }
+
+void pgshim_reset(void) { arena_reset(&tl_arena); }
 
 /* ------------------------------------------------------------------ errors */
 
