@@ -313,8 +313,18 @@ def main():
     ap.add_argument("--match-m", type=int, default=0, help="k-mers in the match workloads (default: the config's size)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short extract / match measurements")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle checksum of the result tables (profiling runs)")
+    ap.add_argument("--k", type=int, default=21, help="k-mer length of the count workload (default: the headline's 21)")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c2x10"],
+                    help="c2 = BASELINE configs[1] (default; weak scaling, --reads per GPU); c3 = configs[2]: k=31 over 10 GB in total, "
+                         "strong-scaled over the GPUs; c2x10 = the north star's shape: k=21 over 10 GB in total")
     args = ap.parse_args()
+    global K, METRIC
+    if args.config == "c3":
+        args.k = 31
+    K = args.k
+    METRIC = f"kmers_counted_per_sec_k{K}"
     if args.warmup < 3 and args.impl == "b200":
         print(f"note: warmup {args.warmup} < 3 is below the timing rule", file=sys.stderr)
     if args.impl == "reference":
@@ -336,7 +346,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = api.KmerCuda(local_rank)
     n_rows = args.reads
-    flat, off = datagen.synth_reads(2 + rank, n_rows, READ_LEN)
+    scaling = "weak"
+    if args.config in ("c3", "c2x10"):                  # 10 GB in total, split by row over the ranks
+        n_rows = 10_000_000 // world
+        scaling = "strong"
+    flat, off = datagen.synth_reads((3 if args.config == "c3" else 2) + rank, n_rows, READ_LEN)
     n_bases = int(off[-1])
     n_kmers = n_rows * (READ_LEN - K + 1)          # per GPU (weak scaling: every rank brings its own 1 GB)
     total_kmers = n_kmers * world
@@ -662,18 +676,90 @@ def main():
         except Exception as ex:  # the baseline must never take the GPU number down with it
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
 
+    # ---------------------------------------------------------------- the other rows of the path, short (rank 0, N=1 only)
+    secondary = None
+    if world == 1 and not args.no_secondary:
+        secondary = {}
+        del d_pairs
+        torch.cuda.empty_cache()
+
+        def timed_dev(fn, reps=5):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps):
+                fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+
+        def sec_line(what, ms, alg, units, unit):
+            ach = alg / (ms * 1e-3) / 1e9
+            return {"workload": what, "ms": ms, "value": units / (ms * 1e-3), "unit": unit,
+                    "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "alg_bytes": alg}}
+
+        try:
+            # generate_kmers over the resident column: B_alg = N + 8 * n_kmers
+            d_codes = torch.empty(n_kmers, dtype=torch.int64, device="cuda")
+
+            def f_extract():
+                eng.dev_extract(d_seq, n_bases, d_off, n_rows, K, d_codes, stream=stream)
+                eng.dev_finish(stream)
+            secondary["extract"] = sec_line(f"generate_kmers over {n_bases / 1e9:.3g} GB, k={K}", timed_dev(f_extract), n_bases + 8 * n_kmers,
+                                            n_kmers, "k-mers/s")
+            del d_codes
+            torch.cuda.empty_cache()
+            # configs[4] at a quarter of its size: equals + starts_with in ONE pass over M 32-mers: B_alg = 8 M + 2 M/8
+            m5 = 250_000_000
+            g = torch.Generator(device="cuda").manual_seed(5)
+            col5 = (torch.randint(0, 1 << 32, (m5,), dtype=torch.int64, device="cuda", generator=g) << 32) | \
+                torch.randint(0, 1 << 32, (m5,), dtype=torch.int64, device="cuda", generator=g)   # uniform 32-mers
+            c0 = int(col5[0].item()) & M64
+            txt = "".join("acgt"[(c0 >> (2 * (31 - j))) & 3] for j in range(32))
+            bits5 = torch.empty(2 * ((m5 + 31) // 32), dtype=torch.int32, device="cuda")
+            hits5 = torch.empty(2, dtype=torch.int64, device="cuda")
+
+            def f_c5():
+                eng.dev_match(api.OP_EQUALS, col5, m5, 32, [txt, txt[:8]], bits5, hits5, ops=[api.OP_EQUALS, api.OP_STARTS_WITH], stream=stream)
+                eng.dev_finish(stream)
+            secondary["match_c5"] = sec_line(f"configs[4] at 1/4 size: equals + starts_with(8-base prefix) in one pass over {m5:.3g} 32-mers",
+                                             timed_dev(f_c5), 8 * m5 + 2 * ((m5 + 7) // 8), 2 * m5, "pair-tests/s")
+            del col5, bits5, hits5
+            torch.cuda.empty_cache()
+            # configs[3] at a quarter of its size: contains, 1000 IUPAC patterns (k=12) x M k-mers, full bit matrix
+            m4, P = 25_000_000, 1000
+            col4 = torch.randint(0, 1 << 24, (m4,), dtype=torch.int64, device="cuda", generator=g)
+            pats = datagen.synth_qkmers(4, P, 12, with_n=True)
+            bits4 = torch.empty(P * ((m4 + 31) // 32), dtype=torch.int32, device="cuda")
+            hits4 = torch.empty(P, dtype=torch.int64, device="cuda")
+
+            def f_c4():
+                eng.dev_match(api.OP_CONTAINS, col4, m4, 12, pats, bits4, hits4, stream=stream)
+                eng.dev_finish(stream)
+            ms4 = timed_dev(f_c4, reps=3)
+            secondary["match_c4"] = sec_line(f"configs[3] at 1/4 size: contains, {P} IUPAC patterns (k=12) x {m4:.3g} k-mers, full bit matrix",
+                                             ms4, 8 * m4 + 16 * P + P * ((m4 + 7) // 8), m4 * P, "pair-tests/s")
+            del col4, bits4, hits4
+            torch.cuda.empty_cache()
+        except Exception as ex:                            # the secondary rows must never take the headline down
+            secondary["error"] = repr(ex)
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
-            "config": {"workload": f"configs[1]: k=21 count over {n_bases / 1e9:.3g} GB synthetic DNA per GPU "
-                                   f"({n_rows} reads x {READ_LEN}, seed 2+rank)", "k": K, "read_len": READ_LEN,
+            "config": {"workload": {"c2": f"configs[1]: k={K} count over {n_bases / 1e9:.3g} GB synthetic DNA per GPU ({n_rows} reads x {READ_LEN}, seed 2+rank)",
+                                    "c3": f"configs[2]: k=31 count over 10 GB synthetic DNA in total, {n_rows} reads x {READ_LEN} per GPU (seed 3+rank)",
+                                    "c2x10": f"north-star shape: k=21 count over 10 GB synthetic DNA in total, {n_rows} reads x {READ_LEN} per GPU (seed 2+rank)"}[args.config],
+                       "k": K, "read_len": READ_LEN,
                        "reads_per_gpu": n_rows, "algo": args.algo, "n_kmers_per_step": n_kmers * world,
                        "n_distinct_rank0": n_distinct, "recounted_kmers": int(res.n_overflow),
                        "tier2_kmers": int(res.n_tier2), "n_distinct_total": n_distinct_total,
                        "exchange_bytes_per_gpu_per_step": (sharder.last_exchange_bytes if sharder is not None else 0), "l2": "inputs and tables larger than L2 (no flush needed)",
                        "bases_per_sec": n_bases * world * args.steps / (ms_total * 1e-3)},
             "roofline": roofline, "roofline_kernels": roofline_kernels, "roofline_step": roofline_step, "phases_ms": phases, "cpu_baseline": cpu, "e2e": e2e,
-            "parity": parity, "gpu_launches": int(launches), "clocks": clocks}
+            "parity": parity, "secondary": secondary, "gpu_launches": int(launches), "clocks": clocks}
     if rank == 0:
         print(json.dumps(line), flush=True)
     eng.close()

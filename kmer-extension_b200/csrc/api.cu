@@ -55,6 +55,7 @@ struct kmer_cuda_ctx {
     uint64_t p_expected_kmers = 0;
     // a partition count whose tiers overflowed is recounted by kmer_cuda_dev_finish through the global hash table
     bool p_recountable = false;
+    bool p_chained = false;       // shard count chained to its partition: finish() also reports the partition's input errors
     const char* p_seq = nullptr;
     const uint64_t* p_off = nullptr;
     kmer_count_pair* p_pairs = nullptr;
@@ -204,6 +205,21 @@ __global__ void status_reset_kernel(DevStatus* s) {
     s->special_count = 0;
     s->out_overflow = 0;
     s->pad = kNoError;
+    s->n_spill = 0;
+    s->n_failed = 0;
+    s->failed_kmers = 0;
+    s->n_unique = 0;
+    s->t2_mode = 0;
+    s->t2_slots = 0;
+}
+
+// sharded counting: the count that follows a partition on the same stream WITHOUT a finish in between keeps what the partition
+// found in the input (first bad character / short row / overflowed segments); one finish at the end reports everything
+__global__ void status_reset_keep_input_kernel(DevStatus* s) {
+    s->n_kmers = 0;
+    s->n_distinct = 0;
+    s->special_count = 0;
+    s->out_overflow = 0;
     s->n_spill = 0;
     s->n_failed = 0;
     s->failed_kmers = 0;
@@ -410,11 +426,12 @@ static cudaStream_t pick_stream(kmer_cuda_ctx* c, void* stream) {
     return stream == KMER_OWN_STREAM ? c->stream : (cudaStream_t)stream;
 }
 
-static int begin_op(kmer_cuda_ctx* c, cudaStream_t st) {
+static int begin_op(kmer_cuda_ctx* c, cudaStream_t st, bool keep_input_findings = false) {
     CU(cudaSetDevice(c->di.device), "cudaSetDevice");
-    c->ev_used = 0;
-    mark(c, st, "");
-    status_reset_kernel<<<1, 1, 0, st>>>(c->d_status);
+    if (!keep_input_findings) c->ev_used = 0;
+    mark(c, st, keep_input_findings ? "exchange" : "");
+    if (keep_input_findings) status_reset_keep_input_kernel<<<1, 1, 0, st>>>(c->d_status);
+    else status_reset_kernel<<<1, 1, 0, st>>>(c->d_status);
     c->launches++;
     c->pending = OP_NONE;
     c->p_recountable = false;
@@ -738,6 +755,12 @@ extern "C" int kmer_cuda_dev_finish(kmer_cuda_ctx* c, void* stream, kmer_dev_res
                              "kmer_cuda: a bucket segment overflowed (input too repetitive for the sharded partition path)", "", -1);
         if (result) result->n_kmers = c->p_expected_kmers;
     } else if (op == OP_SHARD_COUNT) {
+        if (c->p_chained) {
+            c->p_chained = false;
+            uint64_t bad_row = s.bad_char_pos == kNoError ? kNoError : s.pad;
+            if (bad_row != kNoError && bad_row <= s.short_row) return ref_error(&c->err, KMER_ERR_INVALID_DNA, (int64_t)bad_row);
+            if (s.short_row != kNoError) return ref_error(&c->err, KMER_ERR_INVALID_K, (int64_t)s.short_row);
+        }
         if (s.out_overflow)
             return set_error(&c->err, KMER_ERR_CAPACITY, "XX000", "kmer_cuda: output buffer too small", "", -1);
         if (s.n_overflow)
@@ -861,9 +884,11 @@ static int dev_shard_count_impl(kmer_cuda_ctx* c, const kmer_shard_plan* sp, con
                                 void* stream) {
     if (!c || !sp) return KMER_ERR_BAD_ARGUMENT;
     cudaStream_t st = pick_stream(c, stream);
-    int rc = begin_op(c, st);
+    const bool chained = c->pending == OP_SHARD_PART;    // no finish since the partition: its findings stay in the status block
+    int rc = begin_op(c, st, chained);
     if (rc) return rc;
     c->pending = OP_SHARD_COUNT;
+    c->p_chained = chained;
     c->last_overflow = 0;
     c->last_tier2 = 0;
     const int k = sp->k;

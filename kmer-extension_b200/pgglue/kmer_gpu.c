@@ -21,7 +21,21 @@
  */
 #include "postgres.h"
 #include "fmgr.h"
+#include "funcapi.h"
+#include "utils/array.h"
 #include "kmer_cuda.h"
+
+/*
+ * SQL surface a maintainer adds next to kmer--1.0.0.sql (additive; nothing existing changes):
+ *
+ *   CREATE FUNCTION kmer_gpu_counts(dna[], integer) RETURNS TABLE (kmer kmer, count bigint)
+ *       AS 'MODULE_PATHNAME', 'kmer_gpu_counts' LANGUAGE C IMMUTABLE STRICT PARALLEL SAFE;
+ *       -- SELECT * FROM kmer_gpu_counts(ARRAY(SELECT dna FROM reads), 21)
+ *       --   ==  SELECT k.kmer, count(*) FROM reads r, generate_kmers(r.dna, 21) AS k(kmer) GROUP BY k.kmer
+ *   CREATE FUNCTION kmer_gpu_match(kmer[], text, integer) RETURNS SETOF boolean
+ *       AS 'MODULE_PATHNAME', 'kmer_gpu_match' LANGUAGE C IMMUTABLE STRICT PARALLEL SAFE;
+ *       -- element i: op 0 kmer[i] = $2 ; op 1 kmer[i] ^@ $2 ; op 2 $2::qkmer @> kmer[i]
+ */
 
 
 static kmer_cuda_ctx *gpu_ctx = NULL; /* one per backend process */
@@ -99,33 +113,51 @@ kmer_gpu_count_datums(struct varlena **dnas, uint64_t n, int k, struct varlena *
 		kmer_gpu_raise(kmer_cuda_last_error(ctx));
 	d = n_uniq + n_pairs;
 
-	/* text of the groups with the short varlena header already in place: d * (k+1) bytes */
-	codes = (uint64_t *) palloc((d ? d : 1) * sizeof(uint64_t));
-	*counts = (int64_t *) palloc((d ? d : 1) * sizeof(int64_t));
-	for (i = 0; i < n_uniq; i++)
-	{
-		codes[i] = uniq[i];
-		(*counts)[i] = 1;
-	}
-	for (i = 0; i < n_pairs; i++)
-	{
-		codes[n_uniq + i] = pairs[i].code;
-		(*counts)[n_uniq + i] = (int64_t) pairs[i].count;
-	}
-	kmer_cuda_release(ctx, uniq);
-	kmer_cuda_release(ctx, pairs);
-	if (kmer_cuda_submit_decode(ctx, codes, d, k, 1, &text) != KMER_OK)
-		kmer_gpu_raise(kmer_cuda_last_error(ctx));
+	/* The library's result buffers are pinned host memory owned by the context: an ereport(ERROR) between here and the
+	 * releases (palloc can fail) must not leak them in a long-lived backend. */
+	void *volatile r_uniq = uniq, *volatile r_pairs = pairs, *volatile r_text = NULL; /* still to be released */
 
-	*kmers = (struct varlena **) palloc((d ? d : 1) * sizeof(struct varlena *));
-	for (i = 0; i < d; i++)
+	PG_TRY();
 	{
-		struct varlena *v = (struct varlena *) palloc((Size) k + VARHDRSZ_SHORT);
+		/* text of the groups with the short varlena header already in place: d * (k+1) bytes */
+		codes = (uint64_t *) palloc((d ? d : 1) * sizeof(uint64_t));
+		*counts = (int64_t *) palloc((d ? d : 1) * sizeof(int64_t));
+		for (i = 0; i < n_uniq; i++)
+		{
+			codes[i] = uniq[i];
+			(*counts)[i] = 1;
+		}
+		for (i = 0; i < n_pairs; i++)
+		{
+			codes[n_uniq + i] = pairs[i].code;
+			(*counts)[n_uniq + i] = (int64_t) pairs[i].count;
+		}
+		kmer_cuda_release(ctx, r_uniq);
+		r_uniq = NULL;
+		kmer_cuda_release(ctx, r_pairs);
+		r_pairs = NULL;
+		if (kmer_cuda_submit_decode(ctx, codes, d, k, 1, &text) != KMER_OK)
+			kmer_gpu_raise(kmer_cuda_last_error(ctx));
+		r_text = text;
 
-		memcpy(v, text + i * (uint64_t) (k + 1), (size_t) k + 1); /* header byte + k lower-case bases */
-		(*kmers)[i] = v;
+		*kmers = (struct varlena **) palloc((d ? d : 1) * sizeof(struct varlena *));
+		for (i = 0; i < d; i++)
+		{
+			struct varlena *v = (struct varlena *) palloc((Size) k + VARHDRSZ_SHORT);
+
+			memcpy(v, text + i * (uint64_t) (k + 1), (size_t) k + 1); /* header byte + k lower-case bases */
+			(*kmers)[i] = v;
+		}
 	}
-	kmer_cuda_release(ctx, text);
+	PG_CATCH();
+	{
+		kmer_cuda_release(ctx, r_uniq);
+		kmer_cuda_release(ctx, r_pairs);
+		kmer_cuda_release(ctx, r_text);
+		PG_RE_THROW();
+	}
+	PG_END_TRY();
+	kmer_cuda_release(ctx, r_text);
 	*n_groups = d;
 }
 
@@ -162,4 +194,115 @@ kmer_gpu_match_datums(int op, struct varlena **kmers, uint64_t n, const char *co
 	kmer_cuda_release(ctx, codes);
 	kmer_cuda_release(ctx, bits);
 	kmer_cuda_release(ctx, hits);
+}
+
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * fmgr-V1 entry points (SQL-callable)
+ */
+
+typedef struct CountsState
+{
+	struct varlena **kmers;
+	int64_t *counts;
+	TupleDesc tupdesc;
+} CountsState;
+
+PG_FUNCTION_INFO_V1(kmer_gpu_counts);
+/*
+ * kmer_gpu_counts(dna[], k) -> setof (kmer, bigint): value-per-call SRF like generate_kmers (kmer.c:289-351); the whole
+ * batch is counted on the first call, in the multi-call memory context.
+ */
+Datum
+kmer_gpu_counts(PG_FUNCTION_ARGS)
+{
+	FuncCallContext *funcctx;
+	CountsState *st;
+
+	if (SRF_IS_FIRSTCALL())
+	{
+		MemoryContext oldcontext;
+		ArrayType *arr = PG_GETARG_ARRAYTYPE_P(0);
+		int32 k = PG_GETARG_INT32(1);
+		Datum *elems;
+		bool *nulls;
+		int n, i, m = 0;
+		struct varlena **dnas;
+		uint64_t n_groups = 0;
+		TupleDesc tupdesc;
+
+		funcctx = SRF_FIRSTCALL_INIT();
+		oldcontext = MemoryContextSwitchTo(funcctx->multi_call_memory_ctx);
+		if (get_call_result_type(fcinfo, NULL, &tupdesc) != TYPEFUNC_COMPOSITE)
+			ereport(ERROR, (errcode(ERRCODE_INTERNAL_ERROR), errmsg("kmer_gpu_counts must return a composite type")));
+		deconstruct_array(arr, ARR_ELEMTYPE(arr), -1, false, 'i', &elems, &nulls, &n);
+		dnas = (struct varlena **) palloc((n ? n : 1) * sizeof(struct varlena *));
+		for (i = 0; i < n; i++)
+			if (!nulls || !nulls[i]) /* generate_kmers is STRICT: a NULL dna yields no rows (kmer--1.0.0.sql:101-104) */
+				dnas[m++] = PG_DETOAST_DATUM(elems[i]);
+		st = (CountsState *) palloc(sizeof(CountsState));
+		st->tupdesc = BlessTupleDesc(tupdesc);
+		kmer_gpu_count_datums(dnas, (uint64_t) m, k, &st->kmers, &st->counts, &n_groups);
+		funcctx->max_calls = n_groups;
+		funcctx->user_fctx = st;
+		MemoryContextSwitchTo(oldcontext);
+	}
+	funcctx = SRF_PERCALL_SETUP();
+	st = (CountsState *) funcctx->user_fctx;
+	if (funcctx->call_cntr < funcctx->max_calls)
+	{
+		Datum values[2];
+		bool isnull[2] = {false, false};
+
+		values[0] = PointerGetDatum(st->kmers[funcctx->call_cntr]);
+		values[1] = Int64GetDatum(st->counts[funcctx->call_cntr]);
+		SRF_RETURN_NEXT(funcctx, HeapTupleGetDatum(heap_form_tuple(st->tupdesc, values, isnull)));
+	}
+	SRF_RETURN_DONE(funcctx);
+}
+
+PG_FUNCTION_INFO_V1(kmer_gpu_match);
+/*
+ * kmer_gpu_match(kmer[], constant text, op) -> setof boolean, element order: the batched form of kmer_equals /
+ * kmer_starts_with_op / kmer_contains (kmer.c:226-285).  The constant arrives as text so that one function serves kmer and
+ * qkmer constants; it is validated by the library with kmer_in's / qkmer_in's rules and messages.
+ */
+Datum
+kmer_gpu_match(PG_FUNCTION_ARGS)
+{
+	FuncCallContext *funcctx;
+	bool *res;
+
+	if (SRF_IS_FIRSTCALL())
+	{
+		MemoryContext oldcontext;
+		ArrayType *arr = PG_GETARG_ARRAYTYPE_P(0);
+		struct varlena *ctext = PG_GETARG_VARLENA_P(1);
+		int32 op = PG_GETARG_INT32(2);
+		Datum *elems;
+		bool *nulls;
+		int n, i;
+		struct varlena **kmers;
+		char *constant;
+
+		funcctx = SRF_FIRSTCALL_INIT();
+		oldcontext = MemoryContextSwitchTo(funcctx->multi_call_memory_ctx);
+		deconstruct_array(arr, ARR_ELEMTYPE(arr), -1, false, 'i', &elems, &nulls, &n);
+		kmers = (struct varlena **) palloc((n ? n : 1) * sizeof(struct varlena *));
+		for (i = 0; i < n; i++)
+			kmers[i] = PG_DETOAST_DATUM(elems[i]);
+		constant = (char *) palloc((Size) VARSIZE_ANY_EXHDR(ctext) + 1);
+		memcpy(constant, VARDATA_ANY(ctext), (size_t) VARSIZE_ANY_EXHDR(ctext));
+		constant[VARSIZE_ANY_EXHDR(ctext)] = 0;
+		res = (bool *) palloc((n ? n : 1) * sizeof(bool));
+		kmer_gpu_match_datums(op, kmers, (uint64_t) n, constant, res);
+		funcctx->max_calls = (uint64_t) n;
+		funcctx->user_fctx = res;
+		MemoryContextSwitchTo(oldcontext);
+	}
+	funcctx = SRF_PERCALL_SETUP();
+	res = (bool *) funcctx->user_fctx;
+	if (funcctx->call_cntr < funcctx->max_calls)
+		SRF_RETURN_NEXT(funcctx, BoolGetDatum(res[funcctx->call_cntr]));
+	SRF_RETURN_DONE(funcctx);
 }

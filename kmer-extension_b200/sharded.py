@@ -131,6 +131,7 @@ class ShardedCounter:
                 self._comm_stream = torch.cuda.Stream(device=self.device)
             comm = self._comm_stream
         a2a_events = []
+        chained = chunks == 1          # partition -> exchange -> count on the device without a host round trip in between
         for ci, (r0, r1) in enumerate(pieces):
             sr = send_recs[ci * recs_bytes:(ci + 1) * recs_bytes]
             sf = send_fill[ci * fill_words:(ci + 1) * fill_words]
@@ -141,21 +142,22 @@ class ShardedCounter:
                     b0 = int(d_off[r0].item())
                     b1 = int(d_off[r1].item())
                     eng.dev_shard_partition(d_seq[b0:], b1 - b0, d_off[r0:r1 + 1] - b0, r1 - r0, plan, sr, sf)
-                eng.dev_finish()          # the piece is partitioned (host waits): its exchange may start
-                phases += self._phases()
+                    eng.dev_finish()      # the piece is partitioned (host waits): its exchange may start
+                    phases += self._phases()
             except Exception as e:  # input error or segment overflow on this rank
                 exc = exc or e
             if self.world > 1:
                 rr = recv_recs[ci * recs_bytes:(ci + 1) * recs_bytes]
                 rf = recv_fill[ci * fill_words:(ci + 1) * fill_words]
                 if comm is not None:
+                    comm.wait_stream(torch.cuda.current_stream())      # the exchange follows the partition kernel on the device
                     with torch.cuda.stream(comm):
-                        if timed:
+                        if timed and not chained:
                             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                             e0.record()
                         dist.all_to_all_single(rf, sf, group=self.group)
                         dist.all_to_all_single(rr, sr, group=self.group)
-                        if timed:
+                        if timed and not chained:
                             e1.record()
                             a2a_events.append((e0, e1))
                 else:
@@ -163,29 +165,41 @@ class ShardedCounter:
                     dist.all_to_all_single(rr, sr, group=self.group)
         if comm is not None:
             torch.cuda.current_stream().wait_stream(comm)
-            if timed:
+            if timed and not chained:
                 torch.cuda.synchronize()
                 phases.append(("all_to_all", sum(a.elapsed_time(b) for a, b in a2a_events)))
-        if self._agree(exc):
-            return self._count_fallback(d_seq, n_bases, d_off, n_rows, k, d_pairs, total_kmers)
         if self.world > 1:
             self.last_exchange_bytes = int(recs_bytes + fill_words * 8) * chunks * (self.world - 1) // self.world
         else:
             self.last_exchange_bytes = 0
-        r, exc = None, None
-        try:
-            if d_uniq is not None:
-                eng.dev_shard_count_split(plan, recv_recs, recv_fill, d_uniq, d_pairs)
-            else:
-                eng.dev_shard_count(plan, recv_recs, recv_fill, d_pairs)
-            r = eng.dev_finish()
-        except Exception as e:        # spill list / output overflow on this rank: no rank may be left waiting in a collective
-            exc = e
-        if self._agree(exc):
+        # The count is queued right behind the exchange; ONE finish reports the partition's findings (input errors, a
+        # segment overflow) together with the count's, and ONE all-reduce makes every rank act on the same outcome.
+        r = None
+        if exc is None:
+            try:
+                if d_uniq is not None:
+                    eng.dev_shard_count_split(plan, recv_recs, recv_fill, d_uniq, d_pairs)
+                else:
+                    eng.dev_shard_count(plan, recv_recs, recv_fill, d_pairs)
+                r = eng.dev_finish()
+            except Exception as e:        # no rank may be left waiting in a collective
+                exc = e
+        code = 0 if exc is None else (1 if getattr(exc, "status", None) == KMER_ERR_CAPACITY else 2)
+        if self.world > 1:
+            t = torch.tensor([1 if code == 2 else 0, 1 if code == 1 else 0, int(r.n_kmers) if r is not None else 0], dtype=torch.int64,
+                             device=self.device)
+            dist.all_reduce(t, group=self.group)
+            n_input_err, n_capacity, counted = (int(x) for x in t.tolist())
+        else:
+            n_input_err, n_capacity, counted = int(code == 2), int(code == 1), int(r.n_kmers) if r is not None else 0
+        if n_input_err:
+            if code == 2:
+                raise exc
+            raise RuntimeError("sharded count aborted: another rank reported an input error")
+        if n_capacity:                    # skewed input: some segment or spill list ran out of room -- exact fallback, all ranks together
             return self._count_fallback(d_seq, n_bases, d_off, n_rows, k, d_pairs, total_kmers)
         phases += self._phases()
         self.last_phases = phases
-        counted = self._allreduce_int(int(r.n_kmers))
         if counted != total_kmers:
             raise RuntimeError(f"sharded count lost k-mers: counted {counted}, expected {total_kmers}")
         return int(r.n_distinct), int(r.n_kmers), {"tier2_kmers": int(r.n_tier2), "plan": plan,

@@ -119,3 +119,14 @@ def test_bench_reference_arm_prints_one_json_line():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
     assert out.returncode == 0 and not [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_pg_regress_suite_is_generated_from_the_kats():
+    """kmer-extension_b200/pgglue/regress/{sql,expected} are what tools/make_pg_regress.py derives from tests/golden/kat.json"""
+    import subprocess, sys
+    reg = ROOT / "kmer-extension_b200" / "pgglue" / "regress"
+    before = ((reg / "sql" / "kmer_kat.sql").read_text(), (reg / "expected" / "kmer_kat.out").read_text())
+    subprocess.run([sys.executable, str(ROOT / "tools" / "make_pg_regress.py")], check=True, capture_output=True)
+    after = ((reg / "sql" / "kmer_kat.sql").read_text(), (reg / "expected" / "kmer_kat.out").read_text())
+    assert before == after
+    assert "kmer_gpu_counts" in after[0] and "tacg |     1" in after[1]
