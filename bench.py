@@ -619,9 +619,11 @@ def main():
             # sharded e2e: every rank copies its rows from pinned host memory, counts with the all-to-all, and reads
             # its share of the (k-mer,count) table back into pinned host memory
             # (split result format: groups with count 1 as bare 8-byte codes, the rest as 16-byte pairs)
+            nbytes = (2 * K + 7) // 8                       # bare codes cross PCIe as ceil(2k/8)-byte integers (6 at k=21)
             h_pairs = torch.empty((cap // 2 + (1 << 20), 2), dtype=torch.int64).pin_memory()
-            h_uniq = torch.empty(cap, dtype=torch.int64).pin_memory()
+            h_packed = torch.empty(cap * nbytes + 16, dtype=torch.uint8).pin_memory()
             d_uniq = torch.empty(cap, dtype=torch.int64, device="cuda")
+            d_packed = torch.empty(cap * nbytes + 16, dtype=torch.uint8, device="cuda")
             d2h_bytes = [0]
             e2e_last = [0, 0]
 
@@ -631,11 +633,12 @@ def main():
                 nd, nk_, info = sharder.count(d_seq, n_bases, d_off, n_rows, K, d_pairs, total_kmers=total_kmers, d_uniq=d_uniq)
                 nu = info["n_unique"]
                 h_pairs[:nd].copy_(d_pairs[:nd], non_blocking=True)
-                h_uniq[:nu].copy_(d_uniq[:nu], non_blocking=True)
+                eng.dev_pack_codes(d_uniq, nu, K, d_packed, stream=stream)
+                h_packed[:nu * nbytes].copy_(d_packed[:nu * nbytes], non_blocking=True)
                 torch.cuda.synchronize()
-                d2h_bytes[0] = 16 * nd + 8 * nu
+                d2h_bytes[0] = 16 * nd + nbytes * nu
                 e2e_last[0], e2e_last[1] = nd, nu
-                return nd + nu, int(h_uniq[0]) if nu else 0
+                return nd + nu, int(h_packed[0]) if nu else 0
 
             e2e_steps = max(1, min(args.steps, 3))
             for _ in range(2):
@@ -653,7 +656,13 @@ def main():
             e2e_parity = None
             if not args.no_parity:                               # the HOST copies of the last step against the oracle's checksum
                 nd_h, nu_h = int(e2e_last[0]), int(e2e_last[1])
-                a1, c1 = table_checksum(torch, h_uniq[:nu_h].cuda())
+                raw = h_packed[:nu_h * nbytes].cuda().view(-1, nbytes).to(torch.int64)
+                codes_h = torch.zeros(nu_h, dtype=torch.int64, device="cuda")
+                for j in range(nbytes):
+                    codes_h |= raw[:, j] << (8 * j)
+                del raw
+                a1, c1 = table_checksum(torch, codes_h)
+                del codes_h
                 hp = h_pairs[:nd_h].cuda()
                 a2, c2 = table_checksum(torch, hp[:, 0], hp[:, 1]) if nd_h else (0, 0)
                 in_sum2, in_n2 = input_checksum(flat, off, K)
@@ -664,7 +673,8 @@ def main():
             e2e = {"value": total_kmers * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": (n_bases + 8 * (n_rows + 1)) * world,
                    "d2h_bytes_per_step": int(d2h_sum.item()), "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
                    "api": "ShardedCounter.count per rank: pinned host rows -> HBM, partition + NCCL all-to-all + refine + bucket count, "
-                          "this rank's share of the table (split format: bare codes + pairs) -> pinned host",
+                          "this rank's share of the table (packed split format: ceil(2k/8)-byte codes + pairs) -> pinned host",
+                   "d2h_gb_per_s_per_rank_mean": float(d2h_sum.item()) / world / max(dt / e2e_steps, 1e-9) / 1e9,
                    "parity": e2e_parity}
 
     # ---------------------------------------------------------------- CPU baseline beside it (rank 0, bounded sample)

@@ -208,6 +208,10 @@ int kmer_cuda_dev_match(kmer_cuda_ctx *ctx, int op, const int *ops, const uint64
 int kmer_cuda_dev_decode(kmer_cuda_ctx *ctx, const uint64_t *d_codes, uint64_t n, int k, int with_header,
 						 char *d_text, void *stream);
 
+/* Transport form of a column of bare codes (kmer_cuda_submit_count_packed): n little-endian integers of ceil(2k/8) bytes each,
+ * d_packed 16-byte aligned with room for n * ceil(2k/8) bytes.  Stream-ordered, no finish needed. */
+int kmer_cuda_dev_pack_codes(kmer_cuda_ctx *ctx, const uint64_t *d_codes, uint64_t n, int k, uint8_t *d_packed, void *stream);
+
 int kmer_cuda_dev_finish(kmer_cuda_ctx *ctx, void *stream, kmer_dev_result *result);
 
 /* ---------------------------------------------------------------- sharded counting (one process per GPU)

@@ -42,7 +42,7 @@ ABI_SYMBOLS = [
     "kmer_cuda_dev_dense_emit", "kmer_cuda_submit_count_split", "kmer_cuda_dev_count_split", "kmer_cuda_submit_count_packed", "kmer_cuda_shard_plan_chunked", "kmer_cuda_dev_shard_count_split",
     "kmer_cuda_dev_merge_begin", "kmer_cuda_dev_merge_add", "kmer_cuda_dev_merge_emit", "kmer_cuda_test_force_window",
     "kmer_cuda_init_multi", "kmer_cuda_shutdown_multi", "kmer_cuda_multi_device_count", "kmer_cuda_multi_last_error",
-    "kmer_cuda_multi_submit_count", "kmer_cuda_multi_release",
+    "kmer_cuda_multi_submit_count", "kmer_cuda_multi_release", "kmer_cuda_dev_pack_codes",
 ]
 
 
@@ -115,6 +115,7 @@ def load_library(path: Path = LIB_PATH) -> C.CDLL:
     L.kmer_cuda_dev_dense_emit.argtypes = [vp, vp, i32, C.c_uint32, C.c_uint32, vp, u64, vp]
     L.kmer_cuda_test_force_window.argtypes = [i32]
     L.kmer_cuda_test_force_window.restype = None
+    L.kmer_cuda_dev_pack_codes.argtypes = [vp, vp, u64, i32, vp, vp]
     L.kmer_cuda_dev_merge_begin.argtypes = [vp, u64, vp]
     L.kmer_cuda_dev_merge_add.argtypes = [vp, vp, u64, C.c_uint32, C.c_uint32, vp]
     L.kmer_cuda_dev_merge_emit.argtypes = [vp, i32, vp, u64, vp]
@@ -354,6 +355,9 @@ class KmerCuda:
         self._check(self.lib.kmer_cuda_dev_shard_count_split(self.ctx, C.byref(plan), d_recv_recs.data_ptr(), d_recv_fill.data_ptr(),
                                                              d_uniq.data_ptr(), d_uniq.numel(), d_pairs.data_ptr(), d_pairs.numel() // 2,
                                                              self._stream_ptr(stream)))
+
+    def dev_pack_codes(self, d_codes, n: int, k: int, d_packed, stream=None):
+        self._check(self.lib.kmer_cuda_dev_pack_codes(self.ctx, d_codes.data_ptr(), n, k, d_packed.data_ptr(), self._stream_ptr(stream)))
 
     def dev_merge_begin(self, max_groups: int, stream=None):
         self._check(self.lib.kmer_cuda_dev_merge_begin(self.ctx, max_groups, self._stream_ptr(stream)))

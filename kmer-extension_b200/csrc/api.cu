@@ -677,6 +677,18 @@ extern "C" int kmer_cuda_dev_decode(kmer_cuda_ctx* c, const uint64_t* d_codes, u
     return KMER_OK;
 }
 
+extern "C" int kmer_cuda_dev_pack_codes(kmer_cuda_ctx* c, const uint64_t* d_codes, uint64_t n, int k, uint8_t* d_packed, void* stream) {
+    if (!c) return KMER_ERR_BAD_ARGUMENT;
+    if (k < 1 || k > KMER_CUDA_MAX_K) return bad_arg(c, "k-mer length must be 1..32");
+    if ((reinterpret_cast<uintptr_t>(d_packed) & 15) != 0) return bad_arg(c, "d_packed must be 16-byte aligned");
+    cudaStream_t st = pick_stream(c, stream);
+    CU(cudaSetDevice(c->di.device), "cudaSetDevice");
+    launch_pack_codes(c->di, d_codes, n, (2 * k + 7) / 8, d_packed, st);
+    c->launches++;
+    CU(cudaGetLastError(), "pack launch");
+    return KMER_OK;
+}
+
 extern "C" int kmer_cuda_dev_finish(kmer_cuda_ctx* c, void* stream, kmer_dev_result* result) {
     if (!c) return KMER_ERR_BAD_ARGUMENT;
     cudaStream_t st = pick_stream(c, stream);

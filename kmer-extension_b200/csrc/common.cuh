@@ -105,21 +105,24 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// try_wait suspends the thread for a hardware time slice per call; the loop is bounded so that a copy that never arrives
-// (a bug, never a legal state) traps instead of hanging the GPU
+// try_wait suspends the thread for a hardware time slice per call; the poll loop is bounded (2^26 polls: minutes) so that a
+// copy that never arrives -- a bug, never a legal state -- traps instead of hanging the GPU.  One tight PTX loop: written in C
+// the compiler unrolled it and changed the register allocation of every kernel that waits (partition_kernel +5 %).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t a = smem_u32(bar);
-    for (uint32_t spins = 0; spins < (1u << 26); spins++) {
-        uint32_t done;
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(a), "r"(parity) : "memory");
-        if (done) return;
-    }
-    __trap();
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .u32 n;\n"
+        "mov.u32 n, 0;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "add.u32 n, n, 1;\n"
+        "setp.lt.u32 p, n, 0x4000000;\n"
+        "@p bra WAIT_LOOP;\n"
+        "trap;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 // bytes must be a multiple of 16; src and dst 16-byte aligned
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {

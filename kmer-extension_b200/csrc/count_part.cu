@@ -350,17 +350,20 @@ __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint3
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {   // bounded like mbar_wait (common.cuh)
-    for (uint32_t spins = 0; spins < (1u << 26); spins++) {
-        uint32_t done;
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) return;
-    }
-    __trap();
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .u32 n;\n"
+        "mov.u32 n, 0;\n"
+        "LEAF_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LEAF_DONE;\n"
+        "add.u32 n, n, 1;\n"
+        "setp.lt.u32 p, n, 0x4000000;\n"
+        "@p bra LEAF_WAIT;\n"
+        "trap;\n"
+        "LEAF_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
 // cell of the filter bitmaps (15 bits) and, decorrelated from it, the slot hash of the exact table

@@ -254,9 +254,12 @@ kmer_gpu_counts(PG_FUNCTION_ARGS)
 		Datum values[2];
 		bool isnull[2] = {false, false};
 
+		Datum tuple;
+
 		values[0] = PointerGetDatum(st->kmers[funcctx->call_cntr]);
 		values[1] = Int64GetDatum(st->counts[funcctx->call_cntr]);
-		SRF_RETURN_NEXT(funcctx, HeapTupleGetDatum(heap_form_tuple(st->tupdesc, values, isnull)));
+		tuple = HeapTupleGetDatum(heap_form_tuple(st->tupdesc, values, isnull)); /* before SRF_RETURN_NEXT bumps call_cntr */
+		SRF_RETURN_NEXT(funcctx, tuple);
 	}
 	SRF_RETURN_DONE(funcctx);
 }
@@ -303,6 +306,12 @@ kmer_gpu_match(PG_FUNCTION_ARGS)
 	funcctx = SRF_PERCALL_SETUP();
 	res = (bool *) funcctx->user_fctx;
 	if (funcctx->call_cntr < funcctx->max_calls)
-		SRF_RETURN_NEXT(funcctx, BoolGetDatum(res[funcctx->call_cntr]));
+	{
+		/* SRF_RETURN_NEXT increments call_cntr BEFORE it evaluates its result argument: take the element first
+		 * (found by executing this function against the reference, tests/c/glue_driver.c) */
+		Datum d = BoolGetDatum(res[funcctx->call_cntr]);
+
+		SRF_RETURN_NEXT(funcctx, d);
+	}
 	SRF_RETURN_DONE(funcctx);
 }

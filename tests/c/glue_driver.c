@@ -161,15 +161,23 @@ static int check_match(int n, int op, const char *constant)
 	fc.args[0].value = PointerGetDatum(arr);
 	fc.args[1].value = PointerGetDatum(make_varlena(constant, clen, 0));
 	fc.args[2].value = (Datum) op;
-	int i = 0;
+	int i = 0, got_hits = 0, first_bad = -1;
 	for (;; i++)
 	{
 		Datum d = kmer_gpu_match(&fc);
 		if (fc.srf_done) break;
-		if (i < n && DatumGetBool(d) != (want[i] != 0)) ok = 0;
+		got_hits += DatumGetBool(d);
+		if (i < n && DatumGetBool(d) != (want[i] != 0)) { ok = 0; if (first_bad < 0) first_bad = i; }
 	}
 	ok = ok && i == n;
-	printf("[glue] kmer_gpu_match op=%d const=%s: %d kmers, %d hits: %s\n", op, constant, n, hits, ok ? "ok" : "MISMATCH");
+	printf("[glue] kmer_gpu_match op=%d const=%s: %d kmers, %d hits (glue %d, %d results): %s\n", op, constant, n, hits, got_hits, i,
+		   ok ? "ok" : "MISMATCH");
+	if (first_bad >= 0)
+	{
+		struct varlena *v = (struct varlena *) DatumGetPointer(arr->elems[first_bad]);
+		printf("       first mismatch at element %d: kmer '%.*s' (len %d), reference says %d\n", first_bad, (int) VARSIZE_ANY_EXHDR(v), VARDATA_ANY(v),
+			   (int) VARSIZE_ANY_EXHDR(v), (int) want[first_bad]);
+	}
 	return ok;
 }
 
