@@ -406,36 +406,31 @@ __global__ void __launch_bounds__(LEAF_THREADS, LEAF_MINB) bucket_count_kernel(P
     const uint32_t cnt_s = tbl_s + LEAF_SLOTS * 8;                             // u32[LEAF_SLOTS]   (k >= 27 only)
     const uint32_t bma_s = cnt_s + (PACKED ? 0 : LEAF_SLOTS * 4);             // bitmap A
     const uint32_t bmb_s = bma_s + LEAF_CELLS / 8;                             // bitmap B
-    const uint32_t slow_s = bmb_s + LEAF_CELLS / 8;                            // u16[LEAF_KEYS]: slow list (record << 4 | window), then claimed slots
-    const uint32_t rcap = ((uint32_t)plan.cap + 2u + 15u) & ~15u;              // records a region can hold, rounded
-    const uint32_t sig_s = slow_s + LEAF_KEYS * 2;                             // u32[rcap]: R->C: cells of the record's two anchors ; C->E: first output | first unique window | unique windows
-    const uint32_t q_s = sig_s + rcap * 4;                                     // u8 [rcap]: minimizer position in the record | flags
-    const uint32_t cmp_s = q_s + rcap;                                         // u16[rcap]: records that have unique windows, in output order
-    const uint32_t rec0_s = cmp_s + rcap * 2;                                  // staged records, two buffers (16-byte aligned: rcap % 8 == 0)
+    const uint32_t slow_s = bmb_s + LEAF_CELLS / 8;                            // u16[LEAF_KEYS]: slow list (key indices), then claimed slots
+    const uint32_t p_s = slow_s + LEAF_KEYS * 2;                               // u16[cap + 2]: first key index of every record
+    const uint32_t rec0_s = p_s + ((((uint32_t)plan.cap + 2u) * 2u + 15u) & ~15u);   // staged records, two buffers
     const uint32_t rec_stride = (((uint32_t)plan.cap + 2u) * RECB + 15u) & ~15u;
     __shared__ __align__(8) uint64_t s_mbar;
-    __shared__ uint32_t s_mask[2][LEAF_BLOCKS];                                // per bucket parity: bit o&31 of word o>>5: a record's unique windows start at output o
-    __shared__ uint32_t s_blk[LEAF_BLOCKS];                                    // position in cmp[] of the record that covers output 32*block
-    __shared__ uint32_t s_pack[2];                                             // per parity: unique windows << 16 | records that have some
-    __shared__ uint32_t s_nslow[2];
+    __shared__ uint32_t s_mask[2][LEAF_BLOCKS];                                // per bucket parity: bit i&31 of word i>>5: a record starts at key index i
+    __shared__ uint32_t s_blk[LEAF_BLOCKS];                                    // record that covers key index 32*block
+    __shared__ uint32_t s_kcur;                                                // index phase: next free key index (a multiple of 32)
+    __shared__ uint32_t s_nuniq[2], s_nslow[2];                                // per bucket parity
     __shared__ unsigned long long s_obase[2];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint32_t lane_lt = (1u << lane) - 1u;
-    const uint32_t lane_starts = (2u << lane) - 2u;                            // start bits 1..lane of a 32-output block
+    const uint32_t lane_starts = (2u << lane) - 2u;                            // start bits 1..lane of a 32-key block
     const int kshift = 64 - 2 * k;
     const uint32_t mbar_s = smem_u32(&s_mbar);
+    const uint32_t kcur_s = smem_u32(&s_kcur);
     const uint32_t blk_s = smem_u32(s_blk);
-    const int W = plan.w, m = plan.m;
-    const int c2 = W / 2;                                                      // context bases of an anchor: W is even (4..16)
-    const int abases = c2 + m;                                                 // bases of an anchor (<= 24)
     unsigned long long special_total = 0, kmers_total = 0;
     for (int i = t; i < LEAF_SLOTS / 2; i += LEAF_THREADS) sts128(tbl_s + 16 * i, ~0u, ~0u, ~0u, ~0u);
     if (!PACKED)
         for (int i = t; i < LEAF_SLOTS / 4; i += LEAF_THREADS) sts128(cnt_s + 16 * i, 0u, 0u, 0u, 0u);
     for (int i = t; i < 2 * LEAF_CELLS / 128; i += LEAF_THREADS) sts128(bma_s + 16 * i, 0u, 0u, 0u, 0u);   // A and B
     if (t < LEAF_BLOCKS) { s_mask[0][t] = 0; s_mask[1][t] = 0; }
-    if (t < 2) { s_pack[t] = 0; s_nslow[t] = 0; }
-    if (t == 0) { mbar_init(&s_mbar, 1); mbar_fence_init(); }
+    if (t < 2) { s_nuniq[t] = 0; s_nslow[t] = 0; }
+    if (t == 0) { s_kcur = 0; mbar_init(&s_mbar, 1); mbar_fence_init(); }
     __syncthreads();
 
     // thread 0: start the bulk copy of bucket b's records (padded to 16 bytes; read once: L2 evict-first)
@@ -462,7 +457,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, LEAF_MINB) bucket_count_kernel(P
         const uint32_t b_next = b + gridDim.x;
         BucketInfo nxt;
         nxt.nrec = 0; nxt.nk = 0; nxt.overflow = false;
-        if (b_next < bucket_end) nxt = bucket_info(fill, plan, b_next);   // in flight during the record phase
+        if (b_next < bucket_end) nxt = bucket_info(fill, plan, b_next);   // in flight during the index phase
         if (!cur.usable()) {                                            // uniform across the CTA
             if (t == 0) {
                 if (cur.nrec) {                                         // does not fit on chip: tier 2
@@ -489,121 +484,90 @@ __global__ void __launch_bounds__(LEAF_THREADS, LEAF_MINB) bucket_count_kernel(P
             lds128(rec_s + 16 * r, hi, lo);
             return (j ? ((hi << (2 * j)) | (lo >> (64 - 2 * j))) : hi) >> kshift;
         };
-        // n <= 32 bases of a record starting at base s, right aligned
-        auto bases = [&](unsigned long long hi, unsigned long long lo, int s, int n) -> uint64_t {
-            unsigned long long x;
-            if (RECW == 1 || s == 0) x = hi << (2 * s);
-            else if (s < 32) x = (hi << (2 * s)) | (lo >> (64 - 2 * s));
-            else x = lo << (2 * (s - 32));
-            return x >> (64 - 2 * n);
-        };
-        // position (in the record) of the leftmost minimal hashed m-mer among the W m-mers of window j
-        auto window_minimizer = [&](unsigned long long hi, unsigned long long lo, int j) -> int {
-            uint32_t hmin = 0xffffffffu;
-            int q = j;
-            for (int i = 0; i < W; i++) {
-                const uint32_t x = (uint32_t)bases(hi, lo, j + i, m) * 0x9E3779B1u;
-                const uint32_t h = x ^ (x >> 15);
-                if (h < hmin) { hmin = h; q = j + i; }
-            }
-            return q;
-        };
-        // filter cell of an anchor (abases bases from base s on): type 0 = context left of the minimizer, 1 = right
-        auto anchor_cell = [&](unsigned long long hi, unsigned long long lo, int s, uint32_t type) -> uint32_t {
-            const uint64_t a = bases(hi, lo, s, abases) ^ ((uint64_t)type << 63);
-            return leaf_mix(a) >> 17;
-        };
-        auto set_a = [&](uint32_t cell, bool force_b) {                 // mark: first comer sets A, every later one B
-            const uint32_t bit = 1u << (cell & 31u), w = (cell >> 5) * 4;
-            const bool seen = (atoms_or32(bma_s + w, bit) & bit) != 0;
-            if (seen || force_b) reds_or32(bmb_s + w, bit);
-        };
-        // ---- records: thread t takes the records [t*c, t*c + c).  Identical k-mers share the leftmost minimal m-mer of the
-        //      string and its offset, hence -- in records whose every window holds the record's minimizer ("regular") -- the
-        //      anchor (minimizer + W/2 bases of context on the side the window has them): a record whose anchor cell nobody
-        //      else touches has nothing but unique k-mers on that side.  ONE filter access per record side instead of one per k-mer.
+        // ---- index: thread t numbers the k-mers of records [t*c, t*c + c)
         const uint32_t nrec = cur.nrec;
-        const uint32_t c = (nrec + LEAF_THREADS - 1) / LEAF_THREADS;
-        const uint32_t r0 = t * c, r1 = min(r0 + c, nrec);
-        for (uint32_t r = r0; r < r1; r++) {
-            unsigned long long hi, lo = 0;
-            uint32_t L;
-            if (RECW == 1) { hi = lds64(rec_s + 8 * r); L = ((uint32_t)hi & 15u) + 1; }
-            else { lds128(rec_s + 16 * r, hi, lo); L = ((uint32_t)lo & 63u) + 1; }
-            const int q = window_minimizer(hi, lo, 0);
-            bool slow_all = L > (uint32_t)q + 1;                        // a later window lost this minimizer: the value repeats nearby
-            if (RECW == 2 && k == 32)                                   // 't'*32 cannot live in the exact table's key space: counted aside
-                for (uint32_t j = 0; j < L; j++) slow_all |= window(r, j) == kEmpty;
-            uint32_t cells = 0;
-            if (!slow_all) {
-                const int nL = min((int)L, max(0, q - c2 + 1));         // windows j <= q - W/2 have the context on the left
-                if (nL) { const uint32_t ce = anchor_cell(hi, lo, q - c2, 0u); set_a(ce, false); cells |= ce; }
-                if (nL < (int)L) { const uint32_t ce = anchor_cell(hi, lo, q, 1u); set_a(ce, false); cells |= ce << 15; }
-            } else {
-                // every window on its own: its k-mer takes the exact path, and whoever shares its anchor must too
-                for (uint32_t j = 0; j < L; j++) {
-                    const int qj = window_minimizer(hi, lo, (int)j);
-                    const bool left = qj - (int)j >= c2;
-                    set_a(anchor_cell(hi, lo, left ? qj - c2 : qj, left ? 0u : 1u), true);
+        {
+            const uint32_t c = (nrec + LEAF_THREADS - 1) / LEAF_THREADS;
+            const uint32_t r0 = t * c, r1 = min(r0 + c, nrec);
+            uint32_t S = 0;
+            for (uint32_t r = r0; r < r1; r++) S += rec_len(r);
+            uint32_t incl = S;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += n;
+            }
+            uint32_t base = 0;
+            if (lane == 31 && incl) base = atoms_add32(kcur_s, (incl + 31u) & ~31u);   // the warp's index range starts on a 32-key block
+            base = __shfl_sync(0xffffffffu, base, 31);
+            uint32_t p = base + incl - S;
+            for (uint32_t r = r0; r < r1; r++) {
+                const uint32_t L = rec_len(r), e = p + L - 1;
+                sts16(p_s + 2 * r, p);
+                reds_or32(mask_s + 4 * (p >> 5), 1u << (p & 31u));
+                if ((p & 31u) == 0 || (e >> 5) != (p >> 5)) sts32(blk_s + 4 * (e >> 5), r);   // covers the first key of block e>>5
+                p += L;
+            }
+        }
+        __syncthreads();                                                // (E) index complete; the other record buffer is free
+        const uint32_t nkeys = s_kcur;                                  // key indices handed out (padded per warp)
+        if (t == 0 && nxt.usable()) issue(b_next, rb ^ 1u);
+        // ---- mark: thread t owns key indices t, t+128, ...  (block = warp + 4 i, bit = lane)
+        uint64_t key[LEAF_KPT];
+        uint32_t valid = 0, multi = 0, special = 0;                     // bit i: key i exists / shares its cell
+#pragma unroll
+        for (int i = 0; i < LEAF_KPT; i++) {
+            key[i] = 0;
+            if (i * LEAF_THREADS >= (int)nkeys) break;                  // uniform
+            const uint32_t blk = warp + LEAF_WARPS * i;
+            if (blk * 32u >= nkeys) break;                              // uniform per warp: the block was not handed out
+            const uint32_t r = lds32(blk_s + 4 * blk) + __popc(lds32(mask_s + 4 * blk) & lane_starts);
+            const uint32_t j = (uint32_t)(t + i * LEAF_THREADS) - lds16(p_s + 2 * r);
+            if (j < rec_len(r)) {                                       // not in the padding behind the warp's last record
+                key[i] = window(r, j);
+                if (RECW == 2 && key[i] == kEmpty) special++;           // k == 32, 't'*32: kept out of the tables
+                else {
+                    valid |= 1u << i;
+                    const uint32_t cell = leaf_cell(key[i]);
+                    const uint32_t bit = 1u << (cell & 31u), w = (cell >> 5) * 4;
+                    if (atoms_or32(bma_s + w, bit) & bit) {
+                        reds_or32(bmb_s + w, bit);
+                        multi |= 1u << i;
+                    }
                 }
             }
-            sts32(sig_s + 4 * r, cells);
-            asm volatile("st.shared.u8 [%0], %1;" ::"r"(q_s + r), "r"((uint32_t)q | (slow_all ? 0x80u : 0u)) : "memory");
         }
-        __syncthreads();                                                // (M) both bitmaps final; the other record buffer is free
-        if (t == 0 && nxt.usable()) issue(b_next, rb ^ 1u);
-        // ---- classify: per record the run [ja, ja + nuq) of windows proven unique; the others go on the slow list
-        uint32_t s_uq = 0, s_ne = 0, s_sl = 0;
-        for (uint32_t r = r0; r < r1; r++) {
-            const uint32_t L = rec_len(r);
-            uint32_t qf;
-            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(qf) : "r"(q_s + r) : "memory");
-            uint32_t ja = 0, nuq = 0;
-            if (!(qf & 0x80u)) {
-                const uint32_t cells = lds32(sig_s + 4 * r);
-                const int nL = min((int)L, max(0, (int)(qf & 0x7fu) - c2 + 1));
-                const uint32_t cl = cells & 0x7fffu, cr = cells >> 15;
-                const bool uL = nL && !((lds32(bmb_s + (cl >> 5) * 4) >> (cl & 31u)) & 1u);
-                const bool uR = nL < (int)L && !((lds32(bmb_s + (cr >> 5) * 4) >> (cr & 31u)) & 1u);
-                ja = uL ? 0u : (uint32_t)nL;
-                nuq = (uR ? L : (uint32_t)nL) - ja;
-            }
-            sts32(sig_s + 4 * r, (ja << 11) | (nuq << 15));
-            s_uq += nuq;
-            s_ne += nuq != 0;
-            s_sl += L - nuq;
-        }
-        // output positions: warp-wide exclusive scan of (unique windows << 16 | records with some), one shared atomicAdd per warp
-        uint32_t pk = (s_uq << 16) | s_ne, incl = pk;
+        __syncthreads();                                                // (M) both bitmaps final
+        if (t == 0) s_kcur = 0;
+        // ---- classify: unique k-mers stay in their registers, the others put their key index on the slow list
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += n;
-        }
-        uint32_t wb = 0;
-        if (lane == 31 && incl) wb = atoms_add32(smem_u32(&s_pack[par]), incl);
-        wb = __shfl_sync(0xffffffffu, wb, 31);
-        uint32_t o = (wb >> 16) + ((incl - pk) >> 16), ne = (wb & 0xffffu) + ((incl - pk) & 0xffffu);
-        uint32_t sl = 0;
-        if (s_sl) sl = atoms_add32(smem_u32(&s_nslow[par]), s_sl);
-        for (uint32_t r = r0; r < r1; r++) {
-            const uint32_t info = lds32(sig_s + 4 * r), ja = (info >> 11) & 15u, nuq = info >> 15, L = rec_len(r);
-            if (nuq) {
-                sts32(sig_s + 4 * r, info | o);
-                sts16(cmp_s + 2 * ne, r);
-                reds_or32(mask_s + 4 * (o >> 5), 1u << (o & 31u));
-                const uint32_t e = o + nuq - 1;
-                if ((o & 31u) == 0 || (e >> 5) != (o >> 5)) sts32(blk_s + 4 * (e >> 5), ne);   // covers the first output of block e>>5
-                o += nuq;
-                ne++;
+        for (int i = 0; i < LEAF_KPT; i++) {
+            if (i * LEAF_THREADS >= (int)nkeys) break;
+            if ((valid >> i) & 1u) {
+                bool slow = (multi >> i) & 1u;
+                if (!slow) {
+                    const uint32_t cell = leaf_cell(key[i]);
+                    slow = (lds32(bmb_s + (cell >> 5) * 4) >> (cell & 31u)) & 1u;
+                }
+                if (slow) {
+                    multi |= 1u << i;
+                    sts16(slow_s + 2 * atoms_add32(smem_u32(&s_nslow[par]), 1u), t + i * LEAF_THREADS);
+                }
             }
-            for (uint32_t j = 0; j < L; j++)
-                if (j < ja || j >= ja + nuq) { sts16(slow_s + 2 * sl, (r << 4) | j); sl++; }
         }
-        __syncthreads();                                                // (L) output index and slow list complete
-        const uint32_t ns = s_nslow[par], nuniq = s_pack[par] >> 16;
+        const uint32_t uniq = valid & ~multi;
+        // the warp's unique k-mers get a contiguous share of the bucket's output
+        const uint32_t wuniq = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(uniq));
+        uint32_t woff = 0;
+        if (lane == 0 && wuniq) woff = atoms_add32(smem_u32(&s_nuniq[par]), wuniq);
+        woff = __shfl_sync(0xffffffffu, woff, 0);
+        __syncthreads();                                                // (L) slow list complete
+        const uint32_t ns = s_nslow[par];
         unsigned long long ubase = 0;
-        if (t == 0 && nuniq) ubase = atomicAdd(SPLIT ? &status->n_unique : &status->n_distinct, (unsigned long long)nuniq);   // consumed after the next barrier
+        if (t == 0) {
+            const uint32_t nu = s_nuniq[par];
+            if (nu) ubase = atomicAdd(SPLIT ? &status->n_unique : &status->n_distinct, (unsigned long long)nu);   // consumed after the next barrier
+        }
         // both bitmaps are dead: clear them for the next bucket
         for (int i = t; i < 2 * LEAF_CELLS / 128; i += LEAF_THREADS) sts128(bma_s + 16 * i, 0u, 0u, 0u, 0u);
         // ---- count: the slow list is cut into one slice per warp, but never thinner than 32 entries (a warp pays for
@@ -611,28 +575,26 @@ __global__ void __launch_bounds__(LEAF_THREADS, LEAF_MINB) bucket_count_kernel(P
         const uint32_t slice = max(32u, (ns + LEAF_WARPS - 1) / LEAF_WARPS);
         const uint32_t kb = min(ns, warp * slice);
         const uint32_t end = min(ns, kb + slice);
-        uint32_t nwin = 0, special = 0;                                 // warp-uniform: slots this warp has claimed so far
+        uint32_t nwin = 0;                                              // warp-uniform: slots this warp has claimed so far
         if (kb < end) {
             uint32_t next = kb, x = 0, tries = 0;
             uint64_t skey = 0;
             bool active = false;
             for (;;) {
-                const uint32_t mm = __ballot_sync(0xffffffffu, !active);
-                if (mm) {
-                    const uint32_t idx = next + __popc(mm & lane_lt);
-                    next += __popc(mm);
+                const uint32_t m = __ballot_sync(0xffffffffu, !active);
+                if (m) {
+                    const uint32_t idx = next + __popc(m & lane_lt);
+                    next += __popc(m);
                     if (!active && idx < end) {
-                        const uint32_t d = lds16(slow_s + 2 * idx);
-                        skey = window(d >> 4, d & 15u);
-                        if (RECW == 2 && skey == kEmpty) special++;     // k == 32, 't'*32: kept out of the table
-                        else {
-                            x = leaf_mix(skey) * 0x2C1B3C6Du;           // decorrelate from the cell index
-                            tries = 0;
-                            active = true;
-                        }
+                        const uint32_t ki = lds16(slow_s + 2 * idx), blk = ki >> 5;
+                        const uint32_t r = lds32(blk_s + 4 * blk) + __popc(lds32(mask_s + 4 * blk) & ((2u << (ki & 31u)) - 2u));
+                        skey = window(r, ki - lds16(p_s + 2 * r));
+                        x = leaf_mix(skey) * 0x2C1B3C6Du;               // decorrelate from the cell index
+                        tries = 0;
+                        active = true;
                     }
                 }
-                if (__all_sync(0xffffffffu, !active) && next >= end) break;   // the warp's share is exhausted
+                if (__all_sync(0xffffffffu, !active)) break;            // the warp's share is exhausted
                 const uint32_t step = (x >> 6) | 1u;                    // double hashing: an odd step visits every slot
                 const uint32_t h = ((x >> 22) + tries * step) & (LEAF_SLOTS - 1);
                 const uint32_t slot = tbl_s + 8 * h;
@@ -642,7 +604,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, LEAF_MINB) bucket_count_kernel(P
                         const unsigned long long si = atomicAdd(&status->n_spill, 1ull);
                         if (si < plan.spill_cap) {
                             if (RECW == 1) reinterpret_cast<unsigned long long*>(spill)[si] = skey << kshift;
-                            else { ulonglong2 v; v.x = skey << kshift; v.y = 0ull; reinterpret_cast<ulonglong2*>(spill)[si] = v; }
+                            else { ulonglong2 o; o.x = skey << kshift; o.y = 0ull; reinterpret_cast<ulonglong2*>(spill)[si] = o; }
                         } else atomicAdd(&status->n_overflow, 1ull);
                         atomicAdd(&status->n_kmers, ~0ull);            // not counted here
                         active = false;
@@ -670,34 +632,33 @@ __global__ void __launch_bounds__(LEAF_THREADS, LEAF_MINB) bucket_count_kernel(P
         if (t == 0) s_obase[par] = ubase;
         if (RECW == 2) special_total += special;
         __syncthreads();                                                // (B) all counts final
-        if (t < 2) { if (t == 0) s_pack[par ^ 1] = 0; else s_nslow[par ^ 1] = 0; }   // idle until the next bucket's classify phase
+        if (t < 2) { if (t == 0) s_nuniq[par ^ 1] = 0; else s_nslow[par ^ 1] = 0; }   // idle until the next bucket's classify phase
         if (t >= 32 && t < 32 + LEAF_BLOCKS) s_mask[par][t - 32] = 0;   // this bucket's start bits: idle until the bucket after the next
-        // ---- emit the unique k-mers: output o of the bucket = window ja + (o - first output) of the record that covers o;
-        //      all lanes of a warp look at the SAME 32-output block: record = cmp[blk[block] + popc(start bits up to the lane)]
+        // ---- emit the unique k-mers: coalesced 16-byte (k-mer, 1) pairs, ranks by ballot
         {
-            const unsigned long long ob = s_obase[par];
-            const bool fits = ob + nuniq <= (SPLIT ? capacity_u : capacity);   // uniform
-            if (!fits && t == 0 && nuniq) status->out_overflow = 1;
+            const unsigned long long ob = s_obase[par] + woff;
+            const bool fits = ob + wuniq <= (SPLIT ? capacity_u : capacity);   // uniform per warp
+            if (!fits && lane == 0) status->out_overflow = 1;
             ulonglong2* const po = reinterpret_cast<ulonglong2*>(out) + ob;
             uint64_t* const pu = out_u + ob;
-            if (fits) {
-#pragma unroll 4
-                for (uint32_t blk = warp; blk * 32u < nuniq; blk += LEAF_WARPS) {
-                    const uint32_t oo = blk * 32u + lane;
-                    const uint32_t n = lds32(blk_s + 4 * blk) + __popc(lds32(mask_s + 4 * blk) & lane_starts);
-                    if (oo < nuniq) {
-                        const uint32_t r = lds16(cmp_s + 2 * n);
-                        const uint32_t info = lds32(sig_s + 4 * r);
-                        const uint64_t key = window(r, ((info >> 11) & 15u) + oo - (info & 2047u));
-                        if (SPLIT) pu[oo] = key;                        // split format: a bare code means count 1
-                        else {
-                            ulonglong2 v;
-                            v.x = key;
-                            v.y = 1ull;
-                            po[oo] = v;
-                        }
+            uint32_t rank = 0;
+            const uint32_t um = fits ? uniq : 0u;
+#pragma unroll
+            for (int i = 0; i < LEAF_KPT; i++) {
+                if (i * LEAF_THREADS >= (int)nkeys) break;
+                const bool u = (um >> i) & 1u;
+                const uint32_t m = __ballot_sync(0xffffffffu, u);
+                if (u) {
+                    const uint32_t o = rank + __popc(m & lane_lt);
+                    if (SPLIT) pu[o] = key[i];                          // split format: a bare code means count 1
+                    else {
+                        ulonglong2 v;
+                        v.x = key[i];
+                        v.y = 1ull;
+                        po[o] = v;
                     }
                 }
+                rank += __popc(m);
             }
         }
         // ---- emit + reset the table entries this warp claimed
@@ -706,14 +667,14 @@ __global__ void __launch_bounds__(LEAF_THREADS, LEAF_MINB) bucket_count_kernel(P
             const uint32_t h = lds16(slow_s + 2 * (kb + i));
             const unsigned long long v = lds64(tbl_s + 8 * h);
             sts64(tbl_s + 8 * h, kEmpty);
-            unsigned long long cc;
-            if (PACKED) cc = v >> 52;
+            unsigned long long c;
+            if (PACKED) c = v >> 52;
             else {
-                cc = lds32(cnt_s + 4 * h);
-                if (cc) sts32(cnt_s + 4 * h, 0u);
+                c = lds32(cnt_s + 4 * h);
+                if (c) sts32(cnt_s + 4 * h, 0u);
             }
             const uint64_t idx = wbase + i;
-            if (idx < capacity) { ulonglong2 v2; v2.x = v & KEYMASK; v2.y = 1ull + cc; reinterpret_cast<ulonglong2*>(out)[idx] = v2; }
+            if (idx < capacity) { ulonglong2 o; o.x = v & KEYMASK; o.y = 1ull + c; reinterpret_cast<ulonglong2*>(out)[idx] = o; }
             else status->out_overflow = 1;
         }
         if (t == 0) kmers_total += cur.nk;
@@ -1218,9 +1179,8 @@ void launch_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPl
 // p.n_buckets = buckets counted HERE (all of them on one GPU, the owned range when sharded)
 size_t leaf_smem_bytes(const PartitionPlan& p) {
     const size_t recb = p.recw == 1 ? 8 : 16;
-    const size_t rcap = ((size_t)p.cap + 2 + 15) & ~(size_t)15;          // per-record arrays: u32 + u8 + u16
     size_t fixed = (size_t)LEAF_SLOTS * 8 + (p.recw == 1 ? 0 : (size_t)LEAF_SLOTS * 4) + 2 * (size_t)LEAF_CELLS / 8 + (size_t)LEAF_KEYS * 2 +
-                   rcap * 7;
+                   ((((size_t)p.cap + 2) * 2 + 15) & ~(size_t)15);
     size_t staged = ((size_t)p.cap + 2) * recb;                           // padded to 16 bytes
     return fixed + 2 * ((staged + 15) & ~(size_t)15);                     // two record buffers
 }
