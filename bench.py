@@ -483,7 +483,7 @@ def main():
     }
     # DRAM traffic per launch from the committed `ncu --set full` capture of this workload (profiles/), if there is one
     traffic = {}
-    tp = ROOT / "profiles" / "r01_dram_traffic_1g_k21.json"
+    tp = ROOT / "profiles" / "r02_dram_traffic_1g_k21.json"
     if tp.exists() and world == 1 and n_rows == 1_000_000:
         try:
             traffic = json.loads(tp.read_text())["kernels"]

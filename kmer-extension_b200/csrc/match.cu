@@ -15,7 +15,7 @@
 namespace kmer {
 
 constexpr int MT = 256;             // threads per CTA
-constexpr int KPT = 4;              // k-mers per thread -> 1024 k-mers = 32 output words per CTA step
+constexpr int KPT = 8;              // k-mers per thread -> 2048 k-mers = 64 output words per CTA step (8 loads in flight per thread)
 constexpr int CT = 32;              // constants per shared-memory output tile
 
 struct KmerRegs {
@@ -126,10 +126,14 @@ __global__ void __launch_bounds__(MT) match_kernel(int op_default, const uint64_
             __syncthreads();
             // rows of the bit matrix: 32 words = 128 contiguous bytes per constant
             for (uint32_t c = warp; c < nc; c += MT / 32) {
-                uint64_t word_idx = base / 32 + lane;
-                uint32_t wv = tile[c][lane];
-                if (word_idx < wpr) bits[(uint64_t)(c0 + c) * wpr + word_idx] = wv;
-                uint32_t pc = __popc(wv);
+                uint32_t pc = 0;
+#pragma unroll
+                for (int h = 0; h < KPT * MT / 32; h += 32) {
+                    uint64_t word_idx = base / 32 + h + lane;
+                    uint32_t wv = tile[c][h + lane];
+                    if (word_idx < wpr) bits[(uint64_t)(c0 + c) * wpr + word_idx] = wv;
+                    pc += __popc(wv);
+                }
                 for (int d = 16; d; d >>= 1) pc += __shfl_xor_sync(0xffffffffu, pc, d);
                 if (lane == 0 && pc) hit_acc[c0 + c] += pc;   // row c is always handled by the same warp
             }
@@ -335,9 +339,9 @@ void launch_match(const DeviceInfo& di, int op, const int* d_ops, bool any_conta
         return;
     }
     uint64_t n_steps = (m + (uint64_t)KPT * MT - 1) / ((uint64_t)KPT * MT);
-    // few constants: a pure stream of the column (8 bytes per k-mer in, bits out).  6 CTAs/SM (36 registers, 4 KB of shared memory)
-    // keep ~50 KB of loads in flight per SM; at 4 the stream ran at 45 % of the copy bandwidth.
-    uint64_t grid = (uint64_t)di.sm_count * (n_consts <= 8 ? 6 : 4);
+    // few constants: a pure stream of the column (8 bytes per k-mer in, bits out).  5 CTAs/SM x 8 loads per thread (48 registers)
+    // keep ~80 KB of loads in flight per SM; with 4 CTAs x 4 loads the stream ran at 45 % of the copy bandwidth.
+    uint64_t grid = (uint64_t)di.sm_count * (n_consts <= 8 ? 5 : 3);
     if (grid > n_steps) grid = n_steps;
     size_t dyn = (size_t)n_consts * (sizeof(ConstSmem) + sizeof(uint32_t));
     if (d_lens) {
