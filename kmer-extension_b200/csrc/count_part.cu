@@ -197,39 +197,42 @@ __global__ void __launch_bounds__(NT, PART_MINB) partition_kernel(ScanArgs a, Pa
             for (int j = 0; j < 16; j++)
                 if ((starts >> j) & 1u) wruns[rbase++] = ((unsigned long long)h[j + 1] << 32) | (uint32_t)(16 * t + j);
         }
-        // ---- emission: run i of the warp is handled by lane i % 32.  The region slots (64-bit atomicAdd with return on the
-        //      bucket's fill word, record count in the low half) are requested BEFORE the tile barrier: up to EMIT_Q round
-        //      trips per lane are in flight while the warp waits for the other warps' boundary bits.
+        // ---- emission: run i of the warp is handled by lane i % 32.  A run never leaves its warp's 512 windows (lane 0 always
+        //      starts one), so its length follows from the warp's OWN boundary bits: no tile barrier, and ONE 64-bit atomicAdd
+        //      per record on the bucket's fill word -- record count in the low half (the returned value is the region slot),
+        //      k-mer count in the high half.  Up to EMIT_Q round trips per lane are in flight.
         constexpr int EMIT_Q = 6;
         __syncwarp();
-        uint32_t posq[EMIT_Q], bq[EMIT_Q], slot[EMIT_Q];             // start base ; bucket ; region slot
-#pragma unroll
-        for (int q = 0; q < EMIT_Q; q++) {
-            const uint32_t r = q * 32 + lane;
-            posq[q] = 0xffffffffu; bq[q] = 0; slot[q] = 0;
-            if (r < n_warp_runs) {
-                const unsigned long long d = wruns[r];
-                bq[q] = __umulhi(mix32((uint32_t)(d >> 32)), plan.hash_buckets) >> plan.fine_shift;
-                posq[q] = (uint32_t)d;
-                slot[q] = (uint32_t)atomicAdd(&fill[bq[q]], 1ull);
-            }
-        }
-        __syncthreads();                                              // boundary bits of the whole tile are visible
         auto run_length = [&](uint32_t p0) {                          // the run ends before the next boundary bit after its first window
+            const uint32_t wend = (p0 | 511u) + 1u;                   // ... or with the warp's windows
             uint32_t p = p0 + 1, R = 1;
-            for (;;) {
-                const uint32_t nb32 = bits32(bdm, p);
+            while (p < wend) {
+                uint32_t nb32 = bits32(bdm, p);
+                const uint32_t rem = wend - p;
+                if (rem < 32) nb32 |= 0xffffffffu << rem;             // bits past the warp's end belong to another warp
                 if (nb32) { R += __ffs(nb32) - 1; break; }
                 R += 32; p += 32;
             }
             return R;
         };
-        // one run: its first record takes the slot reserved above; the k-mer count of the bucket (high half of the fill
-        // word) is bumped without a return value; a run longer than one record holds takes further slots (repetitive text)
-        auto emit_run = [&](uint32_t b, uint32_t slot0, uint32_t p0) {
-            const uint32_t R = run_length(p0);
+        uint32_t posq[EMIT_Q], bq[EMIT_Q], slot[EMIT_Q], lenq[EMIT_Q];   // start base ; bucket ; region slot ; run length
+#pragma unroll
+        for (int q = 0; q < EMIT_Q; q++) {
+            const uint32_t r = q * 32 + lane;
+            posq[q] = 0xffffffffu; bq[q] = 0; slot[q] = 0; lenq[q] = 0;
+            if (r < n_warp_runs) {
+                const unsigned long long d = wruns[r];
+                bq[q] = __umulhi(mix32((uint32_t)(d >> 32)), plan.hash_buckets) >> plan.fine_shift;
+                posq[q] = (uint32_t)d;
+                lenq[q] = run_length(posq[q]);
+                const uint32_t L0 = lenq[q] < rmax ? lenq[q] : rmax;
+                slot[q] = (uint32_t)atomicAdd(&fill[bq[q]], ((unsigned long long)L0 << 32) | 1ull);
+            }
+        }
+        // one run: its first record takes the slot reserved above; a run longer than one record holds takes further slots
+        // (repetitive text)
+        auto emit_run = [&](uint32_t b, uint32_t slot0, uint32_t p0, uint32_t R) {
             const uint32_t L0 = R < rmax ? R : rmax;
-            atomicAdd(&fill[b], (unsigned long long)L0 << 32);
             put_record(b, slot0, (int)p0, (int)L0);
             for (uint32_t off = rmax; off < R; off += rmax) {
                 const uint32_t L = R - off < rmax ? R - off : rmax;
@@ -239,12 +242,14 @@ __global__ void __launch_bounds__(NT, PART_MINB) partition_kernel(ScanArgs a, Pa
         };
 #pragma unroll
         for (int q = 0; q < EMIT_Q; q++)
-            if (posq[q] != 0xffffffffu) emit_run(bq[q], slot[q], posq[q]);
+            if (posq[q] != 0xffffffffu) emit_run(bq[q], slot[q], posq[q], lenq[q]);
         for (uint32_t r = EMIT_Q * 32 + lane; r < n_warp_runs; r += 32) {   // more than 192 runs in 512 windows: rare
             const unsigned long long d = wruns[r];
             const uint32_t b = __umulhi(mix32((uint32_t)(d >> 32)), plan.hash_buckets) >> plan.fine_shift;
-            const uint32_t s0 = (uint32_t)atomicAdd(&fill[b], 1ull);
-            emit_run(b, s0, (uint32_t)d);
+            const uint32_t R = run_length((uint32_t)d);
+            const uint32_t L0 = R < rmax ? R : rmax;
+            const uint32_t s0 = (uint32_t)atomicAdd(&fill[b], ((unsigned long long)L0 << 32) | 1ull);
+            emit_run(b, s0, (uint32_t)d, R);
         }
         sc.release();
     }
