@@ -266,6 +266,23 @@ int kmer_cuda_dev_shard_count(kmer_cuda_ctx *ctx, const kmer_shard_plan *plan, c
 int kmer_cuda_dev_shard_count_split(kmer_cuda_ctx *ctx, const kmer_shard_plan *plan, const void *d_recv_recs,
 									const uint64_t *d_recv_fill, uint64_t *d_uniq, uint64_t uniq_capacity,
 									kmer_count_pair *d_pairs, uint64_t pairs_capacity, void *stream);
+/* The exchange fused into the count: this rank reads source s's segments where they lie.  src_recs[s] / src_fill[s]
+ * (s < n_ranks * chunks_per_rank; host arrays of device pointers) point at source s's send buffers AT THIS RANK'S
+ * BLOCK -- (char *)send_recs_s + rank * plan->recs_bytes_per_peer and send_fill_s + rank * plan->buckets_per_rank --
+ * in this GPU's memory or, over NVLink, in another GPU's (peer access inside one process; kmer_cuda_ipc_open across
+ * processes).  No all-to-all and no receive buffers: the split kernel pulls the records itself.  The caller orders the
+ * call behind every source's kmer_cuda_dev_shard_partition (an event, or any collective enqueued on `stream`) and
+ * keeps the sources from overwriting their send buffers until this rank's kmer_cuda_dev_finish has returned.
+ * d_uniq may be NULL (pairs only), else the split result format. */
+int kmer_cuda_dev_shard_count_peers(kmer_cuda_ctx *ctx, const kmer_shard_plan *plan, const void *const *src_recs,
+									const uint64_t *const *src_fill, uint64_t *d_uniq, uint64_t uniq_capacity,
+									kmer_count_pair *d_pairs, uint64_t pairs_capacity, void *stream);
+/* CUDA IPC for one-process-per-GPU hosts: export names the cudaMalloc ALLOCATION d_ptr lies in (handle64: 64 bytes to
+ * send to the peers) and d_ptr's offset inside it; open maps a peer's allocation into this process (enabling peer
+ * access from ctx's GPU) and returns its base; close unmaps it.  A handle can be open once per process. */
+int kmer_cuda_ipc_export(kmer_cuda_ctx *ctx, const void *d_ptr, void *handle64, uint64_t *offset);
+int kmer_cuda_ipc_open(kmer_cuda_ctx *ctx, const void *handle64, void **d_base);
+int kmer_cuda_ipc_close(kmer_cuda_ctx *ctx, void *d_base);
 /* k <= 13: the dense 4^k table of uint64 counters of this rank's rows (to be summed across ranks),
  * and the emission of the bins owned by `rank` (bin % n_ranks == rank) of a summed table. */
 int kmer_cuda_dev_dense_table(kmer_cuda_ctx *ctx, const char *d_seq, uint64_t n_bases, const uint64_t *d_row_off,

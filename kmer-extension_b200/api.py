@@ -40,6 +40,7 @@ ABI_SYMBOLS = [
     "kmer_cuda_dev_decode", "kmer_cuda_dev_finish", "kmer_cuda_set_profiling", "kmer_cuda_get_phases",
     "kmer_cuda_shard_plan", "kmer_cuda_dev_shard_partition", "kmer_cuda_dev_shard_count", "kmer_cuda_dev_dense_table",
     "kmer_cuda_dev_dense_emit", "kmer_cuda_submit_count_split", "kmer_cuda_dev_count_split", "kmer_cuda_submit_count_packed", "kmer_cuda_shard_plan_chunked", "kmer_cuda_dev_shard_count_split",
+    "kmer_cuda_dev_shard_count_peers", "kmer_cuda_ipc_export", "kmer_cuda_ipc_open", "kmer_cuda_ipc_close",
     "kmer_cuda_dev_merge_begin", "kmer_cuda_dev_merge_add", "kmer_cuda_dev_merge_emit", "kmer_cuda_test_force_window",
     "kmer_cuda_init_multi", "kmer_cuda_shutdown_multi", "kmer_cuda_multi_device_count", "kmer_cuda_multi_last_error",
     "kmer_cuda_multi_submit_count", "kmer_cuda_multi_release", "kmer_cuda_dev_pack_codes",
@@ -111,6 +112,10 @@ def load_library(path: Path = LIB_PATH) -> C.CDLL:
     L.kmer_cuda_dev_shard_partition.argtypes = [vp, vp, u64, vp, u64, C.POINTER(KmerShardPlan), vp, vp, vp]
     L.kmer_cuda_dev_shard_count.argtypes = [vp, C.POINTER(KmerShardPlan), vp, vp, vp, u64, vp]
     L.kmer_cuda_dev_shard_count_split.argtypes = [vp, C.POINTER(KmerShardPlan), vp, vp, vp, u64, vp, u64, vp]
+    L.kmer_cuda_dev_shard_count_peers.argtypes = [vp, C.POINTER(KmerShardPlan), C.POINTER(vp), C.POINTER(vp), vp, u64, vp, u64, vp]
+    L.kmer_cuda_ipc_export.argtypes = [vp, vp, C.c_char_p, C.POINTER(u64)]
+    L.kmer_cuda_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    L.kmer_cuda_ipc_close.argtypes = [vp, vp]
     L.kmer_cuda_dev_dense_table.argtypes = [vp, vp, u64, vp, u64, i32, vp, vp]
     L.kmer_cuda_dev_dense_emit.argtypes = [vp, vp, i32, C.c_uint32, C.c_uint32, vp, u64, vp]
     L.kmer_cuda_test_force_window.argtypes = [i32]
@@ -355,6 +360,30 @@ class KmerCuda:
         self._check(self.lib.kmer_cuda_dev_shard_count_split(self.ctx, C.byref(plan), d_recv_recs.data_ptr(), d_recv_fill.data_ptr(),
                                                              d_uniq.data_ptr(), d_uniq.numel(), d_pairs.data_ptr(), d_pairs.numel() // 2,
                                                              self._stream_ptr(stream)))
+
+    def dev_shard_count_peers(self, plan: KmerShardPlan, src_recs, src_fill, d_uniq, d_pairs, stream=None):
+        """src_recs / src_fill: device ADDRESSES (ints) of every source's segments for this rank (kmer_cuda.h)."""
+        n = len(src_recs)
+        a_r = (C.c_void_p * n)(*[int(x) for x in src_recs])
+        a_f = (C.c_void_p * n)(*[int(x) for x in src_fill])
+        self._check(self.lib.kmer_cuda_dev_shard_count_peers(
+            self.ctx, C.byref(plan), a_r, a_f, d_uniq.data_ptr() if d_uniq is not None else None,
+            d_uniq.numel() if d_uniq is not None else 0, d_pairs.data_ptr(), d_pairs.numel() // 2, self._stream_ptr(stream)))
+
+    def ipc_export(self, d_tensor):
+        """(64-byte handle of the allocation the tensor lies in, the tensor's byte offset inside it)"""
+        h = C.create_string_buffer(64)
+        off = C.c_uint64(0)
+        self._check(self.lib.kmer_cuda_ipc_export(self.ctx, d_tensor.data_ptr(), h, C.byref(off)))
+        return bytes(h.raw), int(off.value)
+
+    def ipc_open(self, handle: bytes) -> int:
+        base = C.c_void_p(0)
+        self._check(self.lib.kmer_cuda_ipc_open(self.ctx, handle, C.byref(base)))
+        return int(base.value)
+
+    def ipc_close(self, base: int):
+        self._check(self.lib.kmer_cuda_ipc_close(self.ctx, base))
 
     def dev_pack_codes(self, d_codes, n: int, k: int, d_packed, stream=None):
         self._check(self.lib.kmer_cuda_dev_pack_codes(self.ctx, d_codes.data_ptr(), n, k, d_packed.data_ptr(), self._stream_ptr(stream)))

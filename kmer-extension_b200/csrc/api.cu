@@ -891,10 +891,8 @@ extern "C" int kmer_cuda_dev_shard_partition(kmer_cuda_ctx* c, const char* d_seq
     return KMER_OK;
 }
 
-static int dev_shard_count_impl(kmer_cuda_ctx* c, const kmer_shard_plan* sp, const void* d_recv_recs, const uint64_t* d_recv_fill,
-                                uint64_t* d_uniq, uint64_t uniq_capacity, kmer_count_pair* d_pairs, uint64_t pairs_capacity,
-                                void* stream) {
-    if (!c || !sp) return KMER_ERR_BAD_ARGUMENT;
+static int dev_shard_count_impl(kmer_cuda_ctx* c, const kmer_shard_plan* sp, const SrcTable& src, uint64_t* d_uniq,
+                                uint64_t uniq_capacity, kmer_count_pair* d_pairs, uint64_t pairs_capacity, void* stream) {
     cudaStream_t st = pick_stream(c, stream);
     const bool chained = c->pending == OP_SHARD_PART;    // no finish since the partition: its findings stay in the status block
     int rc = begin_op(c, st, chained);
@@ -913,8 +911,8 @@ static int dev_shard_count_impl(kmer_cuda_ctx* c, const kmer_shard_plan* sp, con
     if (!rc) rc = ws(c, c->failed, (size_t)plan.n_buckets * 4);
     if (rc) return rc;
     const int n_src = (int)(sp->n_ranks * (sp->chunks_per_rank ? sp->chunks_per_rank : 1u));
-    launch_refine(c->di, plan, k, n_src, sp->buckets_per_rank, sp->cap, (const unsigned long long*)d_recv_fill,
-                  d_recv_recs, (unsigned long long*)c->fill.p, c->recs.p, c->spill.p, c->d_status, st);
+    launch_refine(c->di, plan, k, n_src, sp->buckets_per_rank, sp->cap, src, (unsigned long long*)c->fill.p, c->recs.p, c->spill.p,
+                  c->d_status, st);
     mark(c, st, "refine");
     launch_bucket_count(c->di, plan, k, (const unsigned long long*)c->fill.p, c->recs.p, c->spill.p, (uint32_t*)c->failed.p, d_pairs,
                         pairs_capacity, d_uniq, d_uniq ? uniq_capacity : 0, c->d_status, st);
@@ -932,17 +930,96 @@ static int dev_shard_count_impl(kmer_cuda_ctx* c, const kmer_shard_plan* sp, con
     return KMER_OK;
 }
 
+// the exchanged layout: [source][coarse partition][cap] records and [source][coarse partition] fills in one buffer each
+static int dev_shard_count_contiguous(kmer_cuda_ctx* c, const kmer_shard_plan* sp, const void* d_recv_recs, const uint64_t* d_recv_fill,
+                                      uint64_t* d_uniq, uint64_t uniq_capacity, kmer_count_pair* d_pairs, uint64_t pairs_capacity,
+                                      void* stream) {
+    if (!c || !sp) return KMER_ERR_BAD_ARGUMENT;
+    const uint32_t n_src = sp->n_ranks * (sp->chunks_per_rank ? sp->chunks_per_rank : 1u);
+    if (n_src > (uint32_t)KMER_MAX_SRC) return bad_arg(c, "shard plan: too many sources");
+    SrcTable src{};
+    for (uint32_t s = 0; s < n_src; s++) {
+        src.recs[s] = (const char*)d_recv_recs + (size_t)s * sp->recs_bytes_per_peer;
+        src.fill[s] = (const unsigned long long*)d_recv_fill + (size_t)s * sp->buckets_per_rank;
+    }
+    return dev_shard_count_impl(c, sp, src, d_uniq, uniq_capacity, d_pairs, pairs_capacity, stream);
+}
+
 extern "C" int kmer_cuda_dev_shard_count(kmer_cuda_ctx* c, const kmer_shard_plan* sp, const void* d_recv_recs,
                                          const uint64_t* d_recv_fill, kmer_count_pair* d_pairs, uint64_t pairs_capacity,
                                          void* stream) {
-    return dev_shard_count_impl(c, sp, d_recv_recs, d_recv_fill, nullptr, 0, d_pairs, pairs_capacity, stream);
+    return dev_shard_count_contiguous(c, sp, d_recv_recs, d_recv_fill, nullptr, 0, d_pairs, pairs_capacity, stream);
 }
 
 extern "C" int kmer_cuda_dev_shard_count_split(kmer_cuda_ctx* c, const kmer_shard_plan* sp, const void* d_recv_recs,
                                                const uint64_t* d_recv_fill, uint64_t* d_uniq, uint64_t uniq_capacity,
                                                kmer_count_pair* d_pairs, uint64_t pairs_capacity, void* stream) {
     if (c && !d_uniq && uniq_capacity) return bad_arg(c, "d_uniq");
-    return dev_shard_count_impl(c, sp, d_recv_recs, d_recv_fill, d_uniq, uniq_capacity, d_pairs, pairs_capacity, stream);
+    return dev_shard_count_contiguous(c, sp, d_recv_recs, d_recv_fill, d_uniq, uniq_capacity, d_pairs, pairs_capacity, stream);
+}
+
+// The exchange fused into the count: source s's segments for this owner are read where they lie -- src_recs[s] / src_fill[s]
+// may be pointers into ANOTHER GPU's send buffers (peer access inside one process, kmer_cuda_ipc_open across processes).  The
+// caller orders this call after every source's partition pass (an event, or any collective on the stream) and keeps the
+// sources from overwriting their send buffers until this GPU's count has finished.
+extern "C" int kmer_cuda_dev_shard_count_peers(kmer_cuda_ctx* c, const kmer_shard_plan* sp, const void* const* src_recs,
+                                               const uint64_t* const* src_fill, uint64_t* d_uniq, uint64_t uniq_capacity,
+                                               kmer_count_pair* d_pairs, uint64_t pairs_capacity, void* stream) {
+    if (!c || !sp) return KMER_ERR_BAD_ARGUMENT;
+    if (!src_recs || !src_fill) return bad_arg(c, "src_recs / src_fill");
+    if (!d_uniq && uniq_capacity) return bad_arg(c, "d_uniq");
+    const uint32_t n_src = sp->n_ranks * (sp->chunks_per_rank ? sp->chunks_per_rank : 1u);
+    if (n_src > (uint32_t)KMER_MAX_SRC) return bad_arg(c, "shard plan: too many sources");
+    SrcTable src{};
+    for (uint32_t s = 0; s < n_src; s++) {
+        if (!src_recs[s] || !src_fill[s]) return bad_arg(c, "src_recs / src_fill: null entry");
+        src.recs[s] = src_recs[s];
+        src.fill[s] = (const unsigned long long*)src_fill[s];
+    }
+    return dev_shard_count_impl(c, sp, src, d_uniq, uniq_capacity, d_pairs, pairs_capacity, stream);
+}
+
+// ---- CUDA IPC: a device buffer of this process opened in another process on the same node (one process per GPU)
+typedef int (*cuMemGetAddressRange_fn)(unsigned long long*, size_t*, unsigned long long);
+
+extern "C" int kmer_cuda_ipc_export(kmer_cuda_ctx* c, const void* d_ptr, void* handle64, uint64_t* offset) {
+    if (!c) return KMER_ERR_BAD_ARGUMENT;
+    if (!d_ptr || !handle64 || !offset) return bad_arg(c, "ipc_export");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    CU(cudaSetDevice(c->di.device), "cudaSetDevice");
+    // the handle names the whole ALLOCATION d_ptr lies in (a caching allocator hands out pieces of larger blocks)
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    CU(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr), "cudaGetDriverEntryPoint");
+    if (!fn || qr != cudaDriverEntryPointSuccess) return cuda_error(c, cudaErrorNotSupported, "cuMemGetAddressRange not found");
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (((cuMemGetAddressRange_fn)fn)(&base, &size, (unsigned long long)(uintptr_t)d_ptr) != 0)
+        return cuda_error(c, cudaErrorInvalidValue, "cuMemGetAddressRange");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, (void*)(uintptr_t)base), "cudaIpcGetMemHandle");
+    memcpy(handle64, &h, 64);
+    *offset = (uint64_t)((uintptr_t)d_ptr - (uintptr_t)base);
+    return KMER_OK;
+}
+
+extern "C" int kmer_cuda_ipc_open(kmer_cuda_ctx* c, const void* handle64, void** d_base) {
+    if (!c) return KMER_ERR_BAD_ARGUMENT;
+    if (!handle64 || !d_base) return bad_arg(c, "ipc_open");
+    CU(cudaSetDevice(c->di.device), "cudaSetDevice");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    // maps the exporter's allocation into this process and enables peer access from this context's GPU to the exporter's
+    CU(cudaIpcOpenMemHandle(d_base, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+    return KMER_OK;
+}
+
+extern "C" int kmer_cuda_ipc_close(kmer_cuda_ctx* c, void* d_base) {
+    if (!c) return KMER_ERR_BAD_ARGUMENT;
+    if (!d_base) return KMER_OK;
+    CU(cudaSetDevice(c->di.device), "cudaSetDevice");
+    CU(cudaIpcCloseMemHandle(d_base), "cudaIpcCloseMemHandle");
+    return KMER_OK;
 }
 
 extern "C" int kmer_cuda_dev_dense_table(kmer_cuda_ctx* c, const char* d_seq, uint64_t n_bases, const uint64_t* d_row_off,
@@ -1480,6 +1557,7 @@ struct kmer_cuda_multi {
     std::vector<kmer_cuda_ctx*> ctx;
     std::vector<int> dev;
     kmer_cuda_error err{};
+    bool all_peers = true;           // every device can read every other device's memory (peer access)
     struct PerDev {
         Buf send, sendfill, recv, recvfill, local;
         uint64_t* h_off = nullptr;   // pinned: this device's row offsets, rebased to its first base
@@ -1518,7 +1596,7 @@ extern "C" int kmer_cuda_init_multi(kmer_cuda_multi** out, const int* devices, i
             if (devices[i] == devices[j]) continue;
             int can = 0;
             cudaDeviceCanAccessPeer(&can, devices[i], devices[j]);
-            if (!can) continue;
+            if (!can) { m->all_peers = false; continue; }
             cudaSetDevice(devices[i]);
             cudaError_t ce = cudaDeviceEnablePeerAccess(devices[j], 0);
             if (ce != cudaSuccess) cudaGetLastError();   // already enabled
@@ -1687,8 +1765,6 @@ extern "C" int kmer_cuda_multi_submit_count(kmer_cuda_multi* m, const char* seq,
         cudaSetDevice(m->dev[i]);
         int rc = ws(c, d.send, rb * n);
         if (!rc) rc = ws(c, d.sendfill, fb * n);
-        if (!rc) rc = ws(c, d.recv, rb * n);
-        if (!rc) rc = ws(c, d.recvfill, fb * n);
         if (!rc) rc = kmer_cuda_dev_shard_partition(c, (const char*)c->seq.p, nb[i], (const uint64_t*)c->off.p, nr[i], &sp, d.send.p,
                                                     (uint64_t*)d.sendfill.p, KMER_OWN_STREAM);
         if (rc) return multi_fail(m, c);
@@ -1707,24 +1783,49 @@ extern "C" int kmer_cuda_multi_submit_count(kmer_cuda_multi* m, const char* seq,
         return first_err;
     }
     if (!capacity) {
-        for (int i = 0; i < n; i++)                       // segment block j of device i -> slot i of device j, over NVLink
-            for (int j = 0; j < n; j++) {
-                cudaError_t ce = cudaMemcpyPeerAsync((char*)m->d[j].recv.p + rb * i, m->dev[j], (const char*)m->d[i].send.p + rb * j, m->dev[i], rb,
-                                                     m->ctx[i]->stream);
-                if (ce == cudaSuccess)
-                    ce = cudaMemcpyPeerAsync((char*)m->d[j].recvfill.p + fb * i, m->dev[j], (const char*)m->d[i].sendfill.p + fb * j, m->dev[i], fb,
-                                             m->ctx[i]->stream);
-                if (ce != cudaSuccess) { cuda_error(m->ctx[i], ce, "cudaMemcpyPeerAsync"); return multi_fail(m, m->ctx[i]); }
-            }
-        for (int i = 0; i < n; i++) { cudaSetDevice(m->dev[i]); cudaStreamSynchronize(m->ctx[i]->stream); }
         const uint64_t own_cap = (uint64_t)((double)total_kmers / n * 1.15) + (1u << 20);
-        for (int j = 0; j < n; j++) {
-            kmer_cuda_ctx* c = m->ctx[j];
-            cudaSetDevice(m->dev[j]);
-            int rc = ws(c, c->pairs, own_cap * sizeof(kmer_count_pair));
-            if (!rc) rc = kmer_cuda_dev_shard_count(c, &sp, m->d[j].recv.p, (const uint64_t*)m->d[j].recvfill.p, (kmer_count_pair*)c->pairs.p,
-                                                    own_cap, KMER_OWN_STREAM);
-            if (rc) return multi_fail(m, c);
+        if (m->all_peers) {
+            // every owner reads its segments straight out of the sources' send buffers (peer memory over NVLink): the
+            // exchange is part of the owner's split kernel.  All partitions have finished (dev_finish above).
+            std::vector<const void*> sr(n);
+            std::vector<const uint64_t*> sf(n);
+            for (int j = 0; j < n; j++) {
+                kmer_cuda_ctx* c = m->ctx[j];
+                cudaSetDevice(m->dev[j]);
+                for (int i = 0; i < n; i++) {
+                    sr[i] = (const char*)m->d[i].send.p + rb * j;
+                    sf[i] = (const uint64_t*)((const char*)m->d[i].sendfill.p + fb * j);
+                }
+                int rc = ws(c, c->pairs, own_cap * sizeof(kmer_count_pair));
+                if (!rc) rc = kmer_cuda_dev_shard_count_peers(c, &sp, sr.data(), sf.data(), nullptr, 0, (kmer_count_pair*)c->pairs.p, own_cap,
+                                                              KMER_OWN_STREAM);
+                if (rc) return multi_fail(m, c);
+            }
+        } else {
+            for (int i = 0; i < n; i++) {
+                cudaSetDevice(m->dev[i]);
+                int rc = ws(m->ctx[i], m->d[i].recv, rb * n);
+                if (!rc) rc = ws(m->ctx[i], m->d[i].recvfill, fb * n);
+                if (rc) return multi_fail(m, m->ctx[i]);
+            }
+            for (int i = 0; i < n; i++)                   // segment block j of device i -> slot i of device j (staged by the driver)
+                for (int j = 0; j < n; j++) {
+                    cudaError_t ce = cudaMemcpyPeerAsync((char*)m->d[j].recv.p + rb * i, m->dev[j], (const char*)m->d[i].send.p + rb * j, m->dev[i], rb,
+                                                         m->ctx[i]->stream);
+                    if (ce == cudaSuccess)
+                        ce = cudaMemcpyPeerAsync((char*)m->d[j].recvfill.p + fb * i, m->dev[j], (const char*)m->d[i].sendfill.p + fb * j, m->dev[i], fb,
+                                                 m->ctx[i]->stream);
+                    if (ce != cudaSuccess) { cuda_error(m->ctx[i], ce, "cudaMemcpyPeerAsync"); return multi_fail(m, m->ctx[i]); }
+                }
+            for (int i = 0; i < n; i++) { cudaSetDevice(m->dev[i]); cudaStreamSynchronize(m->ctx[i]->stream); }
+            for (int j = 0; j < n; j++) {
+                kmer_cuda_ctx* c = m->ctx[j];
+                cudaSetDevice(m->dev[j]);
+                int rc = ws(c, c->pairs, own_cap * sizeof(kmer_count_pair));
+                if (!rc) rc = kmer_cuda_dev_shard_count(c, &sp, m->d[j].recv.p, (const uint64_t*)m->d[j].recvfill.p, (kmer_count_pair*)c->pairs.p,
+                                                        own_cap, KMER_OWN_STREAM);
+                if (rc) return multi_fail(m, c);
+            }
         }
         std::vector<kmer_dev_result> res(n);
         for (int j = 0; j < n; j++) {

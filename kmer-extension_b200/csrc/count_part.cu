@@ -215,17 +215,17 @@ __global__ void __launch_bounds__(NT, PART_MINB) partition_kernel(ScanArgs a, Pa
             }
             return R;
         };
-        uint32_t posq[EMIT_Q], bq[EMIT_Q], slot[EMIT_Q], lenq[EMIT_Q];   // start base ; bucket ; region slot ; run length
+        uint32_t posq[EMIT_Q], bq[EMIT_Q], slot[EMIT_Q];             // run length << 16 | start base ; bucket ; region slot
 #pragma unroll
         for (int q = 0; q < EMIT_Q; q++) {
             const uint32_t r = q * 32 + lane;
-            posq[q] = 0xffffffffu; bq[q] = 0; slot[q] = 0; lenq[q] = 0;
+            posq[q] = 0xffffffffu; bq[q] = 0; slot[q] = 0;
             if (r < n_warp_runs) {
                 const unsigned long long d = wruns[r];
                 bq[q] = __umulhi(mix32((uint32_t)(d >> 32)), plan.hash_buckets) >> plan.fine_shift;
-                posq[q] = (uint32_t)d;
-                lenq[q] = run_length(posq[q]);
-                const uint32_t L0 = lenq[q] < rmax ? lenq[q] : rmax;
+                const uint32_t R = run_length((uint32_t)d);
+                posq[q] = (uint32_t)d | (R << 16);
+                const uint32_t L0 = R < rmax ? R : rmax;
                 slot[q] = (uint32_t)atomicAdd(&fill[bq[q]], ((unsigned long long)L0 << 32) | 1ull);
             }
         }
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(NT, PART_MINB) partition_kernel(ScanArgs a, Pa
         };
 #pragma unroll
         for (int q = 0; q < EMIT_Q; q++)
-            if (posq[q] != 0xffffffffu) emit_run(bq[q], slot[q], posq[q], lenq[q]);
+            if (posq[q] != 0xffffffffu) emit_run(bq[q], slot[q], posq[q] & 0xffffu, posq[q] >> 16);
         for (uint32_t r = EMIT_Q * 32 + lane; r < n_warp_runs; r += 32) {   // more than 192 runs in 512 windows: rare
             const unsigned long long d = wruns[r];
             const uint32_t b = __umulhi(mix32((uint32_t)(d >> 32)), plan.hash_buckets) >> plan.fine_shift;
@@ -708,8 +708,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, LEAF_MINB) bucket_count_kernel(P
 // a record is recomputed from its first window: it is the bucket of the run's minimizer, as in partition_kernel.
 template <int W, int RECW>
 __global__ void __launch_bounds__(256) refine_kernel(PartitionPlan plan, int k, int n_src, uint32_t n_coarse, uint32_t coarse_cap,
-                                                     const unsigned long long* __restrict__ recv_fill,
-                                                     const Rec<RECW>* __restrict__ recv_recs, unsigned long long* __restrict__ fill,
+                                                     const __grid_constant__ SrcTable src, unsigned long long* __restrict__ fill,
                                                      Rec<RECW>* __restrict__ recs, Rec<RECW>* __restrict__ spill, DevStatus* status) {
     extern __shared__ uint32_t refine_smem[];       // [F] records, [F] k-mers
     const uint32_t F = 1u << plan.fine_shift;
@@ -725,8 +724,8 @@ __global__ void __launch_bounds__(256) refine_kernel(PartitionPlan plan, int k, 
         for (uint32_t f = t; f < 2 * F; f += blockDim.x) refine_smem[f] = 0;
         __syncthreads();
         for (int sI = 0; sI < n_src; sI++) {
-            const uint32_t n = min((uint32_t)recv_fill[(uint64_t)sI * n_coarse + c], coarse_cap);
-            const Rec<RECW>* base = recv_recs + ((uint64_t)sI * n_coarse + c) * coarse_cap;
+            const uint32_t n = min((uint32_t)ld_nc_u64(reinterpret_cast<const uint64_t*>(src.fill[sI]) + c), coarse_cap);
+            const Rec<RECW>* base = reinterpret_cast<const Rec<RECW>*>(src.recs[sI]) + (uint64_t)c * coarse_cap;
             constexpr int RQ = 4;                                 // records in flight per thread
             for (uint32_t i0 = t; i0 < n; i0 += RQ * blockDim.x) {
                 uint64_t hi[RQ], lo[RQ];
@@ -792,11 +791,10 @@ __global__ void __launch_bounds__(256) refine_kernel(PartitionPlan plan, int k, 
 constexpr int RF_ROUND = 1024;          // records per round (4 per thread)
 template <int W>
 __global__ void __launch_bounds__(256) refine_staged_kernel(PartitionPlan plan, int k, int n_src, uint32_t n_coarse, uint32_t coarse_cap,
-                                                            const unsigned long long* __restrict__ recv_fill,
-                                                            const Rec<1>* __restrict__ recv_recs, unsigned long long* __restrict__ fill,
+                                                            const __grid_constant__ SrcTable src, unsigned long long* __restrict__ fill,
                                                             Rec<1>* __restrict__ recs, Rec<1>* __restrict__ spill, DevStatus* status) {
     constexpr int F = 256;                                   // fine buckets per coarse partition == threads per CTA
-    __shared__ uint32_t s_hist[F], s_start[F], s_gk[F], s_wtot[8];
+    __shared__ uint32_t s_hist[F], s_start[F], s_gk[F], s_wtot[8], s_n[KMER_MAX_SRC];
     __shared__ __align__(16) unsigned long long s_sorted[RF_ROUND];
     __shared__ unsigned long long s_carry[3][F];             // bucket t's pending records: s_carry[0..n_carry)[t]
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -812,23 +810,41 @@ __global__ void __launch_bounds__(256) refine_staged_kernel(PartitionPlan plan, 
             else overflow_kmers += (r & 15u) + 1;
         };
         s_gk[t] = 0;
-        for (int sI = 0; sI < n_src; sI++) {
-            const uint32_t n = min((uint32_t)recv_fill[(uint64_t)sI * n_coarse + c], coarse_cap);
-            const uint64_t* base = reinterpret_cast<const uint64_t*>(recv_recs + ((uint64_t)sI * n_coarse + c) * coarse_cap);
-            for (uint32_t r0 = 0; r0 < n; r0 += RF_ROUND) {
-                s_hist[t] = 0;
-                uint64_t rec[4];
+        // the sources' segment sizes, all at once (a source may be another GPU's memory: one round trip, not n_src)
+        if (t < n_src) s_n[t] = min((uint32_t)ld_nc_u64(reinterpret_cast<const uint64_t*>(src.fill[t]) + c), coarse_cap);
+        __syncthreads();
+        // rounds of RF_ROUND records over all sources; the loads of the next round are issued before this one is processed
+        auto seek = [&](int& sI, uint32_t& r0) {             // first (source, round) at or after (sI, r0) that holds records
+            while (sI < n_src && r0 >= s_n[sI]) { sI++; r0 = 0; }
+        };
+        auto fetch = [&](int sI, uint32_t r0, uint64_t (&rec)[4]) {
+            const uint64_t* base = reinterpret_cast<const uint64_t*>(src.recs[sI]) + (uint64_t)c * coarse_cap;
+            const uint32_t n = s_n[sI];
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const uint32_t i = r0 + q * 256 + t;
-                    rec[q] = i < n ? ld_nc_u64(base + i) : 0ull;
-                }
+            for (int q = 0; q < 4; q++) {
+                const uint32_t i = r0 + q * 256 + t;
+                rec[q] = i < n ? ld_nc_u64(base + i) : 0ull;
+            }
+        };
+        int sI = 0;
+        uint32_t r0 = 0;
+        uint64_t rec[4], nxt[4];
+        seek(sI, r0);
+        if (sI < n_src) fetch(sI, r0, rec);
+        while (sI < n_src) {
+            const uint32_t n = s_n[sI], r0c = r0;
+            int sN = sI;
+            uint32_t rN = r0 + RF_ROUND;
+            seek(sN, rN);
+            if (sN < n_src) fetch(sN, rN, nxt);
+            {
+                s_hist[t] = 0;
                 __syncthreads();                              // histogram zeroed; previous round fully consumed
                 uint32_t fr[4];                               // fine bucket << 16 | rank within the round
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     fr[q] = 0xffffffffu;
-                    if (r0 + q * 256 + t < n) {
+                    if (r0c + q * 256 + t < n) {
                         uint32_t hmin = 0xffffffffu;          // minimizer hash of the record's first window
 #pragma unroll
                         for (int j = 0; j < W; j++) {
@@ -885,6 +901,9 @@ __global__ void __launch_bounds__(256) refine_staged_kernel(PartitionPlan plan, 
                     n_carry = left;
                 }
             }
+            sI = sN; r0 = rN;
+#pragma unroll
+            for (int q = 0; q < 4; q++) rec[q] = nxt[q];
         }
         // the last, partial sector of every bucket (the region fills up completely before anything is spilled, so
         // min(records, cap) of them are in the region and records > cap marks the overflow, as partition_kernel leaves it)
@@ -1259,36 +1278,27 @@ void launch_partition_tier2(const DeviceInfo& di, const PartitionPlan& p, int k,
 }
 
 void launch_refine(const DeviceInfo& di, const PartitionPlan& p, int k, int n_src, uint32_t n_coarse, uint32_t coarse_cap,
-                   const unsigned long long* d_recv_fill, const void* d_recv_recs, unsigned long long* d_fill,
-                   void* d_recs, void* d_spill, DevStatus* d_status, cudaStream_t st) {
+                   const SrcTable& src, unsigned long long* d_fill, void* d_recs, void* d_spill, DevStatus* d_status, cudaStream_t st) {
     if (!n_coarse) return;
     unsigned grid = (unsigned)di.sm_count * 8;
     if (grid > n_coarse) grid = n_coarse;
     const size_t smem = (size_t)(2u << p.fine_shift) * sizeof(uint32_t);
     if (p.recw == 1 && p.fine_shift == 8) {   // write-combining version (8-byte records)
-        if (p.w == 4) refine_staged_kernel<4><<<grid, 256, 0, st>>>(p, k, n_src, n_coarse, coarse_cap, d_recv_fill, (const Rec<1>*)d_recv_recs, d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill, d_status);
-        else if (p.w == 6) refine_staged_kernel<6><<<grid, 256, 0, st>>>(p, k, n_src, n_coarse, coarse_cap, d_recv_fill, (const Rec<1>*)d_recv_recs, d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill, d_status);
-        else refine_staged_kernel<8><<<grid, 256, 0, st>>>(p, k, n_src, n_coarse, coarse_cap, d_recv_fill, (const Rec<1>*)d_recv_recs, d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill, d_status);
+#define KMER_RS(W_) refine_staged_kernel<W_><<<grid, 256, 0, st>>>(p, k, n_src, n_coarse, coarse_cap, src, d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill, d_status)
+        if (p.w == 4) KMER_RS(4);
+        else if (p.w == 6) KMER_RS(6);
+        else KMER_RS(8);
+#undef KMER_RS
         return;
     }
-    if (p.w == 6)
-        refine_kernel<6, 1><<<grid, 256, smem, st>>>(p, k, n_src, n_coarse, coarse_cap, d_recv_fill, (const Rec<1>*)d_recv_recs,
-                                                     d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill, d_status);
-    else if (p.w == 12)
-        refine_kernel<12, 2><<<grid, 256, smem, st>>>(p, k, n_src, n_coarse, coarse_cap, d_recv_fill, (const Rec<2>*)d_recv_recs,
-                                                      d_fill, (Rec<2>*)d_recs, (Rec<2>*)d_spill, d_status);
-    else if (p.w == 4)
-        refine_kernel<4, 1><<<grid, 256, smem, st>>>(p, k, n_src, n_coarse, coarse_cap, d_recv_fill, (const Rec<1>*)d_recv_recs,
-                                                     d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill, d_status);
-    else if (p.w == 8 && p.recw == 1)
-        refine_kernel<8, 1><<<grid, 256, smem, st>>>(p, k, n_src, n_coarse, coarse_cap, d_recv_fill, (const Rec<1>*)d_recv_recs,
-                                                     d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill, d_status);
-    else if (p.w == 8)
-        refine_kernel<8, 2><<<grid, 256, smem, st>>>(p, k, n_src, n_coarse, coarse_cap, d_recv_fill, (const Rec<2>*)d_recv_recs,
-                                                     d_fill, (Rec<2>*)d_recs, (Rec<2>*)d_spill, d_status);
-    else
-        refine_kernel<16, 2><<<grid, 256, smem, st>>>(p, k, n_src, n_coarse, coarse_cap, d_recv_fill, (const Rec<2>*)d_recv_recs,
-                                                      d_fill, (Rec<2>*)d_recs, (Rec<2>*)d_spill, d_status);
+#define KMER_RF(W_, R_) refine_kernel<W_, R_><<<grid, 256, smem, st>>>(p, k, n_src, n_coarse, coarse_cap, src, d_fill, (Rec<R_>*)d_recs, (Rec<R_>*)d_spill, d_status)
+    if (p.w == 6) KMER_RF(6, 1);
+    else if (p.w == 12) KMER_RF(12, 2);
+    else if (p.w == 4) KMER_RF(4, 1);
+    else if (p.w == 8 && p.recw == 1) KMER_RF(8, 1);
+    else if (p.w == 8) KMER_RF(8, 2);
+    else KMER_RF(16, 2);
+#undef KMER_RF
 }
 
 void launch_append_special(kmer_count_pair* d_pairs, uint64_t capacity, DevStatus* d_status, cudaStream_t st) {

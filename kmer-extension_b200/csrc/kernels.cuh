@@ -103,9 +103,16 @@ void launch_partition_tier2(const DeviceInfo& di, const PartitionPlan& p, int k,
                             void (*mark)(void*, const char*), void* mark_arg);
 // sharded counting, owner side: the coarse partitions received from every source GPU ([src][n_coarse][coarse_cap] records,
 // [src][n_coarse] fills) are split into this GPU's fine buckets (p: n_buckets = n_coarse << fine_shift, cap, spill list)
+// Source s's segments for THIS owner are src.recs[s] ([n_coarse][coarse_cap] records) and src.fill[s] ([n_coarse] fills): plain
+// device pointers, which may point into another GPU's memory (peer access / CUDA IPC) -- the split then pulls the records over
+// NVLink itself and no separate exchange step exists.
+constexpr int KMER_MAX_SRC = 32;
+struct SrcTable {
+    const void* recs[KMER_MAX_SRC];
+    const unsigned long long* fill[KMER_MAX_SRC];
+};
 void launch_refine(const DeviceInfo& di, const PartitionPlan& p, int k, int n_src, uint32_t n_coarse, uint32_t coarse_cap,
-                   const unsigned long long* d_recv_fill, const void* d_recv_recs, unsigned long long* d_fill,
-                   void* d_recs, void* d_spill, DevStatus* d_status, cudaStream_t st);
+                   const SrcTable& src, unsigned long long* d_fill, void* d_recs, void* d_spill, DevStatus* d_status, cudaStream_t st);
 void launch_append_special(kmer_count_pair* d_pairs, uint64_t capacity, DevStatus* d_status, cudaStream_t st);
 
 // match.cu --------------------------------------------------------------------------------------

@@ -5,11 +5,14 @@ the multi-GPU form of `SELECT kmer, count(*) ... GROUP BY kmer` over generate_km
 
   1. every rank partitions ITS rows' k-mers into the same global minimizer buckets
      (kmer_cuda_dev_shard_partition),
-  2. bucket b is owned by rank b // buckets_per_rank; ONE all-to-all (equal splits) moves every
-     (bucket, source) segment of super-k-mer records to its owner, a second small one the fill counts
-     (optionally, chunks=2, the rows are partitioned in two pieces and the exchange of the first piece runs on
-     a side stream while the second piece is being partitioned),
-  3. every owner counts its buckets on chip (kmer_cuda_dev_shard_count).
+  2. bucket b is owned by rank b // buckets_per_rank.  On GPUs (exchange="pull", the default) there is NO separate
+     exchange step: the ranks' send blocks are opened in every process once (CUDA IPC), a tiny all-reduce on the
+     stream tells every rank that all partitions are done, and the owner's split kernel reads its (bucket, source)
+     segments straight out of the sources' memory over NVLink (kmer_cuda_dev_shard_count_peers).
+     exchange="nccl" (and the CPU plumbing tests): ONE all-to-all (equal splits) moves every segment to its owner,
+     a second small one the fill counts (optionally, chunks=2, the rows are partitioned in two pieces and the
+     exchange of the first piece runs on a side stream while the second piece is being partitioned),
+  3. every owner counts its buckets on chip (kmer_cuda_dev_shard_count*).
 
 Identical k-mers share a minimizer, hence a bucket, hence an owner, so the per-rank results are
 disjoint and the GROUP BY result is their concatenation.  k <= 13 uses the dense 4^k table instead:
@@ -27,17 +30,30 @@ KMER_ERR_CAPACITY = 20   # include/kmer_cuda.h
 
 
 class ShardedCounter:
-    def __init__(self, engine, group=None, device=None, chunks=None):
+    def __init__(self, engine, group=None, device=None, chunks=None, exchange=None):
         self.eng = engine
         self.chunks = chunks       # pieces a rank's rows are partitioned in (None: 1)
+        self.exchange = exchange   # "pull" | "nccl" | None: pull on GPUs when the engine can (KMER_SHARD_EXCHANGE overrides)
+        self._pull = None          # {"block": tensor, "addr": [device address of every rank's block], "opened": [bases]}
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self._bufs = {}
         self.last_plan = None
-        self.last_exchange_bytes = 0
+        self._xbytes = 0
         self.last_phases = []      # (name, ms) of the last count when the engine's profiling is on
+
+    @property
+    def last_exchange_bytes(self) -> int:
+        """Bytes this rank's records and fill counts put on the links in the last count."""
+        if callable(self._xbytes):
+            self._xbytes = self._xbytes()
+        return self._xbytes
+
+    @last_exchange_bytes.setter
+    def last_exchange_bytes(self, v):
+        self._xbytes = v
 
     # ------------------------------------------------------------------ helpers
     def _buf(self, name, nbytes, dtype=torch.uint8):
@@ -48,6 +64,58 @@ class ShardedCounter:
             t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
             self._bufs[name] = t
         return t[:n]
+
+    def _use_pull(self, chunks) -> bool:
+        import os
+        mode = self.exchange or os.environ.get("KMER_SHARD_EXCHANGE") or "pull"
+        return (mode == "pull" and chunks == 1 and self.world > 1 and self.device.type == "cuda"
+                and hasattr(self.eng, "ipc_export"))
+
+    def _pull_block(self, nbytes: int):
+        """This rank's send block (records, then fills) and every rank's view of it.  (Re)allocated when the plan outgrows it:
+        the size follows from the plan alone, so every rank takes this branch in the same call -- it is collective."""
+        st = self._pull
+        if st is not None and st["block"].numel() >= nbytes:
+            return st
+        torch.cuda.synchronize(self.device)
+        self.close()
+        block = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        try:
+            mine = self.eng.ipc_export(block)
+        except Exception:                       # e.g. an allocator that does not hand out cudaMalloc memory
+            mine = None
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=self.group)
+        addr, opened, ok = [], [], all(e is not None for e in everyone)
+        if ok:
+            try:
+                for r, (h, o) in enumerate(everyone):
+                    if r == self.rank:
+                        addr.append(block.data_ptr())
+                    else:
+                        base = self.eng.ipc_open(h)
+                        opened.append(base)
+                        addr.append(base + o)
+            except Exception:                   # no peer access between two of the GPUs
+                ok = False
+        self._pull = {"block": block, "addr": addr, "opened": opened,
+                      "token": torch.zeros(1, dtype=torch.int32, device=self.device)}
+        # every rank has opened every block (nobody proceeds, and could free its block, before that) -- or all fall back together
+        if not self._allreduce_int(1 if ok else 0, dist.ReduceOp.MIN):
+            self.close()
+            self.exchange = "nccl"
+            return None
+        return self._pull
+
+    def close(self):
+        """Unmaps the peers' send blocks (collective in spirit: call it on every rank before the process group goes away)."""
+        st, self._pull = self._pull, None
+        if st is not None:
+            for base in st["opened"]:
+                try:
+                    self.eng.ipc_close(base)
+                except Exception:
+                    pass
 
     def _allreduce_int(self, value: int, op=dist.ReduceOp.SUM) -> int:
         if self.world == 1:
@@ -117,10 +185,18 @@ class ShardedCounter:
         self.last_plan = plan
         recs_bytes = plan.recs_bytes_per_peer * self.world       # one piece
         fill_words = plan.buckets_per_rank * self.world
-        send_recs = self._buf("send_recs", recs_bytes * chunks)
-        send_fill = self._buf("send_fill", fill_words * 8 * chunks, torch.int64)
-        recv_recs = self._buf("recv_recs", recs_bytes * chunks) if self.world > 1 else send_recs
-        recv_fill = self._buf("recv_fill", fill_words * 8 * chunks, torch.int64) if self.world > 1 else send_fill
+        pull = self._use_pull(chunks)
+        pst = self._pull_block(recs_bytes + fill_words * 8) if pull else None
+        pull = pst is not None
+        if pull:
+            send_recs = pst["block"][:recs_bytes]
+            send_fill = pst["block"][recs_bytes:recs_bytes + fill_words * 8].view(torch.int64)
+            recv_recs = recv_fill = None
+        else:
+            send_recs = self._buf("send_recs", recs_bytes * chunks)
+            send_fill = self._buf("send_fill", fill_words * 8 * chunks, torch.int64)
+            recv_recs = self._buf("recv_recs", recs_bytes * chunks) if self.world > 1 else send_recs
+            recv_fill = self._buf("recv_fill", fill_words * 8 * chunks, torch.int64) if self.world > 1 else send_fill
         pieces = [(0, n_rows)] if chunks == 1 else [(0, cut), (cut, n_rows)]
         exc = None
         phases = []
@@ -146,7 +222,12 @@ class ShardedCounter:
                     phases += self._phases()
             except Exception as e:  # input error or segment overflow on this rank
                 exc = exc or e
-            if self.world > 1:
+            if pull:
+                # every rank's partition is done when this tiny all-reduce has run on the stream (no host wait): the owners then
+                # read the segments where they are.  The sources do not touch their blocks again before the all-reduce that ends
+                # this call, which every rank joins only after its own count has finished.
+                dist.all_reduce(pst["token"], group=self.group)
+            elif self.world > 1:
                 rr = recv_recs[ci * recs_bytes:(ci + 1) * recs_bytes]
                 rf = recv_fill[ci * fill_words:(ci + 1) * fill_words]
                 if comm is not None:
@@ -168,7 +249,15 @@ class ShardedCounter:
             if timed and not chained:
                 torch.cuda.synchronize()
                 phases.append(("all_to_all", sum(a.elapsed_time(b) for a, b in a2a_events)))
-        if self.world > 1:
+        if pull:       # what the other GPUs' split kernels read from here: the filled part of their segments (evaluated on demand)
+            own = slice(self.rank * plan.buckets_per_rank, (self.rank + 1) * plan.buckets_per_rank)
+            rec_bytes = plan.rec_bytes
+
+            def sent(fill=send_fill, own=own, rec_bytes=rec_bytes):
+                low = fill & 0xffffffff
+                return int((low.sum() - low[own].sum()).item()) * rec_bytes + (fill.numel() - (own.stop - own.start)) * 8
+            self.last_exchange_bytes = sent
+        elif self.world > 1:
             self.last_exchange_bytes = int(recs_bytes + fill_words * 8) * chunks * (self.world - 1) // self.world
         else:
             self.last_exchange_bytes = 0
@@ -177,7 +266,11 @@ class ShardedCounter:
         r = None
         if exc is None:
             try:
-                if d_uniq is not None:
+                if pull:
+                    rb, bpr = plan.recs_bytes_per_peer, plan.buckets_per_rank
+                    eng.dev_shard_count_peers(plan, [a + self.rank * rb for a in pst["addr"]],
+                                              [a + recs_bytes + self.rank * bpr * 8 for a in pst["addr"]], d_uniq, d_pairs)
+                elif d_uniq is not None:
                     eng.dev_shard_count_split(plan, recv_recs, recv_fill, d_uniq, d_pairs)
                 else:
                     eng.dev_shard_count(plan, recv_recs, recv_fill, d_pairs)

@@ -78,10 +78,12 @@ def main():
             wk, wc, wn = O.np_count(allflat, np.array(alloff, dtype=np.uint64), k)
             o = np.argsort(K, kind="stable")
             good = K.size == wk.size and np.array_equal(K[o], wk) and np.array_equal(Cn[o], wc)
-            print(f"[nccl x{world}] {name}: {'ok' if good else 'MISMATCH'} groups={K.size}/{wk.size} tier2={info.get('tier2_kmers')}", flush=True)
+            print(f"[nccl x{world}] {name}: {'ok' if good else 'MISMATCH'} groups={K.size}/{wk.size} tier2={info.get('tier2_kmers')} fallback={info.get('fallback')}", flush=True)
             ok = ok and good
     flag = torch.tensor([1 if ok else 0], dtype=torch.int64, device="cuda")
     dist.broadcast(flag, 0)
+    print(f"[nccl x{world}] rank {rank} exchange={'pull' if sh._pull is not None else 'nccl'}", flush=True)
+    sh.close()
     eng.close()
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) else 1)
