@@ -342,6 +342,9 @@ def main():
         if args.gpus > 1:
             raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
     torch.cuda.set_device(local_rank)
+    # before any pinned allocation: run (and allocate) on the NUMA node the GPU hangs off
+    from kmer_extension_b200 import hostbind
+    placement = hostbind.bind_to_gpu(local_rank) if not os.environ.get("KMER_NO_BIND") else {"bound": False, "why": "KMER_NO_BIND"}
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = api.KmerCuda(local_rank)
@@ -626,16 +629,22 @@ def main():
             d_packed = torch.empty(cap * nbytes + 16, dtype=torch.uint8, device="cuda")
             d2h_bytes = [0]
             e2e_last = [0, 0]
+            ev_d2h = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            d2h_ms = [0.0]
 
             def e2e_step():
                 d_seq.copy_(h_seq, non_blocking=True)
                 d_off.copy_(h_off, non_blocking=True)
                 nd, nk_, info = sharder.count(d_seq, n_bases, d_off, n_rows, K, d_pairs, total_kmers=total_kmers, d_uniq=d_uniq)
                 nu = info["n_unique"]
+                ev_d2h[0].record()
                 h_pairs[:nd].copy_(d_pairs[:nd], non_blocking=True)
+                ev_d2h[1].record()
                 eng.dev_pack_codes(d_uniq, nu, K, d_packed, stream=stream)
                 h_packed[:nu * nbytes].copy_(d_packed[:nu * nbytes], non_blocking=True)
+                ev_d2h[2].record()
                 torch.cuda.synchronize()
+                d2h_ms[0] = ev_d2h[0].elapsed_time(ev_d2h[2])     # both copies + the pack kernel between them
                 d2h_bytes[0] = 16 * nd + nbytes * nu
                 e2e_last[0], e2e_last[1] = nd, nu
                 return nd + nu, int(h_packed[0]) if nu else 0
@@ -653,6 +662,11 @@ def main():
             dt = float(dt.item())
             d2h_sum = torch.tensor([d2h_bytes[0]], dtype=torch.int64, device="cuda")
             dist.all_reduce(d2h_sum)
+            # per-rank D2H rate of the last step (device events around the result copies) and where each rank's host side runs
+            mine = torch.tensor([d2h_bytes[0] / max(d2h_ms[0], 1e-6) / 1e6, float(placement.get("numa_node") if placement.get("numa_node") is not None else -1),
+                                 1.0 if placement.get("bound") else 0.0], dtype=torch.float64, device="cuda")
+            per_rank = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(per_rank, mine)
             e2e_parity = None
             if not args.no_parity:                               # the HOST copies of the last step against the oracle's checksum
                 nd_h, nu_h = int(e2e_last[0]), int(e2e_last[1])
@@ -672,9 +686,12 @@ def main():
                 del hp
             e2e = {"value": total_kmers * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": (n_bases + 8 * (n_rows + 1)) * world,
                    "d2h_bytes_per_step": int(d2h_sum.item()), "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
-                   "api": "ShardedCounter.count per rank: pinned host rows -> HBM, partition + NCCL all-to-all + refine + bucket count, "
+                   "api": "ShardedCounter.count per rank: pinned host rows -> HBM, partition + split (pulls the peers' segments over NVLink) + bucket count, "
                           "this rank's share of the table (packed split format: ceil(2k/8)-byte codes + pairs) -> pinned host",
                    "d2h_gb_per_s_per_rank_mean": float(d2h_sum.item()) / world / max(dt / e2e_steps, 1e-9) / 1e9,
+                   "d2h_copy_gb_per_s_per_rank": [round(float(x[0].item()), 2) for x in per_rank],
+                   "host_numa_node_per_rank": [int(x[1].item()) for x in per_rank],
+                   "host_bound_to_gpu_node_per_rank": [bool(x[2].item()) for x in per_rank],
                    "parity": e2e_parity}
 
     # ---------------------------------------------------------------- CPU baseline beside it (rank 0, bounded sample)
@@ -766,13 +783,21 @@ def main():
                        "reads_per_gpu": n_rows, "algo": args.algo, "n_kmers_per_step": n_kmers * world,
                        "n_distinct_rank0": n_distinct, "recounted_kmers": int(res.n_overflow),
                        "tier2_kmers": int(res.n_tier2), "n_distinct_total": n_distinct_total,
-                       "exchange_bytes_per_gpu_per_step": (sharder.last_exchange_bytes if sharder is not None else 0), "l2": "inputs and tables larger than L2 (no flush needed)",
+                       "exchange_bytes_per_gpu_per_step": (sharder.last_exchange_bytes if sharder is not None else 0),
+                       "exchange": (None if sharder is None else ("peer reads inside the split kernel (CUDA IPC over NVLink)" if sharder._pull is not None
+                                                                  else "NCCL all_to_all")),
+                       "host_placement_rank0": placement, "l2": "inputs and tables larger than L2 (no flush needed)",
                        "bases_per_sec": n_bases * world * args.steps / (ms_total * 1e-3)},
             "roofline": roofline, "roofline_kernels": roofline_kernels, "roofline_step": roofline_step, "phases_ms": phases, "cpu_baseline": cpu, "e2e": e2e,
             "parity": parity, "secondary": secondary, "gpu_launches": int(launches), "clocks": clocks}
     if rank == 0:
         print(json.dumps(line), flush=True)
+    if sharder is not None:
+        sharder.close()
     eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     bad = [k for k in ("checksum_ok", "count_ok", "unique_ok") if parity.get(k) is False]
     for fmt in ([e2e] + [e2e.get("split_format"), e2e.get("pairs_format")] if isinstance(e2e, dict) else []):
         if isinstance(fmt, dict) and isinstance(fmt.get("parity"), dict):

@@ -244,7 +244,7 @@ typedef struct kmer_shard_plan
 	uint32_t fine_shift;	   /* every partition is split into 2^fine_shift fine buckets by its owner */
 	uint32_t fine_cap;		   /* records per fine bucket region (owner side workspace) */
 	uint32_t chunks_per_rank;  /* segments per source GPU (kmer_cuda_shard_plan_chunked), 1 otherwise */
-	uint32_t reserved;
+	uint32_t even_spread;	   /* 1: few distinct m-mers per bucket (short k, huge job): m-mers are spread by a second hash */
 } kmer_shard_plan;
 
 int kmer_cuda_shard_plan(uint64_t total_kmers_all_ranks, int k, uint32_t n_ranks, kmer_shard_plan *plan);

@@ -61,7 +61,7 @@ class KmerShardPlan(C.Structure):
     _fields_ = [("n_ranks", C.c_uint32), ("n_buckets", C.c_uint32), ("buckets_per_rank", C.c_uint32), ("cap", C.c_uint32),
                 ("k", C.c_int32), ("rec_bytes", C.c_int32), ("recs_bytes_per_peer", C.c_uint64),
                 ("fill_bytes_per_peer", C.c_uint64), ("w", C.c_int32), ("m", C.c_int32), ("recw", C.c_int32), ("rmax", C.c_int32),
-                ("fine_shift", C.c_uint32), ("fine_cap", C.c_uint32), ("chunks_per_rank", C.c_uint32), ("reserved", C.c_uint32)]
+                ("fine_shift", C.c_uint32), ("fine_cap", C.c_uint32), ("chunks_per_rank", C.c_uint32), ("even_spread", C.c_uint32)]
 
 
 class KmerSqlError(Exception):

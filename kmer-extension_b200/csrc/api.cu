@@ -827,12 +827,15 @@ extern "C" int kmer_cuda_shard_plan_chunked(uint64_t total_kmers, int k, uint32_
     plan->chunks_per_rank = chunks_per_rank;
     plan->k = k;
     plan->w = p.w; plan->m = p.m; plan->recw = p.recw; plan->rmax = p.rmax;
+    plan->even_spread = (uint32_t)p.even;
     plan->rec_bytes = p.recw == 1 ? 8 : 16;
     {   // records per (coarse partition, source): 1/n_ranks of a partition's k-mers, about 2.1/(w+1) records per k-mer
         double kmers_per_part = (double)total_kmers / (double)plan->n_buckets;
         double rpk = 2.1 / (p.w + 1) + (p.rmax < p.w ? 1.0 / p.rmax : 0.0);
         double mean = kmers_per_part * rpk / (n_ranks * chunks_per_rank);
-        double cap = 1.15 * mean + 6.0 * sqrt(3.0 * mean) + 64.0;
+        // 1.5x: the ranks' shares of the rows are only roughly equal (ragged rows), and a segment that overflows costs the whole
+        // job the exact fallback.  The slack is memory only -- the owners read the filled part of a segment, not its capacity.
+        double cap = 1.5 * mean + 6.0 * sqrt(3.0 * mean) + 64.0;
         plan->cap = ((uint32_t)cap + 1u) & ~1u;   // even: every (partition, source) segment starts 16-byte aligned
     }
     plan->recs_bytes_per_peer = (uint64_t)plan->buckets_per_rank * plan->cap * plan->rec_bytes;
@@ -847,7 +850,7 @@ static PartitionPlan coarse_partition_plan(const kmer_shard_plan* sp) {
     p.hash_buckets = sp->n_buckets << sp->fine_shift;
     p.fine_shift = (int)sp->fine_shift;
     p.cap = sp->cap;
-    p.w = sp->w; p.m = sp->m; p.recw = sp->recw; p.rmax = sp->rmax;
+    p.w = sp->w; p.m = sp->m; p.recw = sp->recw; p.rmax = sp->rmax; p.even = (int)sp->even_spread;
     p.spill_cap = 0;   // no spill list on the source side: a full segment is an error reported by finish()
     return p;
 }
@@ -858,7 +861,7 @@ static PartitionPlan fine_partition_plan(const kmer_shard_plan* sp) {
     p.hash_buckets = sp->n_buckets << sp->fine_shift;
     p.fine_shift = (int)sp->fine_shift;
     p.cap = sp->fine_cap;
-    p.w = sp->w; p.m = sp->m; p.recw = sp->recw; p.rmax = sp->rmax;
+    p.w = sp->w; p.m = sp->m; p.recw = sp->recw; p.rmax = sp->rmax; p.even = (int)sp->even_spread;
     uint64_t sc = (uint64_t)p.n_buckets * p.cap / 8;
     p.spill_cap = sc < 4096 ? 4096 : sc;
     return p;

@@ -92,6 +92,65 @@ __device__ __host__ __forceinline__ uint32_t mix32(uint32_t x) {   // lowbias32 
     return x;
 }
 
+// Minimizer order of an m-mer: `top` holds the m-mer in its top 2m bits (himask covers them; whatever follows is masked off).
+// Two multiply / xor-shift rounds INSIDE that 2m-bit field: a bijection of the 4^m m-mers onto the 4^m evenly spaced values
+// i * 2^(32-2m).  Even spacing matters to the buckets below: a range of the order then holds a fixed number of m-mers, not a
+// Poisson-distributed one (a plain 32-bit hash of a 26..28-bit m-mer scatters them like random points).
+__device__ __forceinline__ uint32_t mmer_hash(uint32_t top, uint32_t himask, int m) {
+    uint32_t t = (top & himask) * 0x9E3779B1u;              // low 32-2m bits stay zero: (x << s) * odd = ((x * odd) mod 4^m) << s
+    t ^= (t >> m) & himask;
+    t *= 0x85EBCA6Bu;
+    t ^= (t >> (m + 1)) & himask;
+    return t;
+}
+
+// Minimizer hash -> position of its bucket in [0, 2^32).  The minimizer of a window is the smallest of W (roughly independent,
+// uniform) hashes, so a fraction F(u) = 1 - (1-u)^W of all windows has its minimizer at or below h = u * 2^32: small hashes
+// are minimizers far more often than large ones.  Spreading the m-mers evenly over the buckets (a second hash) gives every
+// bucket the same NUMBER of m-mers but very unequal loads (simulated at 41 m-mers per bucket, mean 1200 k-mers: 8 % of the
+// k-mers sit in buckets above 1920).  Mapping h through F instead gives every bucket the same expected number of k-mers.
+// Runs of small minimizers are long and runs of large ones short (records per k-mer grow like (1 + (W-1) u) / W), so a bucket
+// of the upper end would hold several times the average number of RECORDS: the tent map 2 min(F, 1-F) pairs every slice of the
+// lower half with its mirror image in the upper half, which evens out the records as well (simulated, same setting: no bucket
+// above 1920 k-mers, 0.02 % of the records beyond the region capacity).  0.32 fixed point; any function of h alone keeps equal
+// k-mers in one bucket.
+template <int W>
+__device__ __forceinline__ uint32_t bucket_position(uint32_t h) {
+    const uint32_t v = ~h;                                  // 1 - u
+    const uint32_t v2 = __umulhi(v, v);
+    const uint32_t v4 = __umulhi(v2, v2);
+    uint32_t p;                                             // (1 - u)^W
+    if (W == 2) p = v2;
+    else if (W == 4) p = v4;
+    else if (W == 6) p = __umulhi(v4, v2);
+    else {
+        const uint32_t v8 = __umulhi(v4, v4);
+        if (W == 8) p = v8;
+        else if (W == 9) p = __umulhi(v8, v);
+        else if (W == 10) p = __umulhi(v8, v2);
+        else if (W == 12) p = __umulhi(v8, v4);
+        else p = __umulhi(v8, v8);                          // W == 16
+    }
+    const uint32_t F = ~p;
+    return (F ^ (uint32_t)((int32_t)F >> 31)) << 1;         // F < 1/2 ? 2F : 2(1 - F)
+}
+// Position -> bucket.  Single pass: bucket = position scaled to the number of buckets.  Two levels (sharded counting, two-pass
+// partition: coarse partitions of F = 2^fine_shift fine buckets each): the TOP fine_shift bits of the position choose the fine
+// bucket inside its coarse partition and the rest, scaled, the coarse partition -- so every coarse partition (and with it every
+// owner GPU) is a comb of F narrow ranges spread evenly over the whole order, not one contiguous range: contiguous ranges
+// would hold equal numbers of k-mers but, the record length depending on the position, unequal numbers of records.
+__device__ __forceinline__ uint32_t coarse_bucket(uint32_t pos, uint32_t hash_buckets, int fine_shift) {
+    return __umulhi(pos << fine_shift, hash_buckets >> fine_shift);
+}
+__device__ __forceinline__ uint32_t fine_in_coarse(uint32_t pos, int fine_shift) {
+    return fine_shift ? pos >> (32 - fine_shift) : 0u;
+}
+// ... unless the m-mers are too coarse for that (plan.even): then they are spread by a second hash, as many per bucket everywhere
+template <int W>
+__device__ __forceinline__ uint32_t bucket_position(uint32_t h, int even) {
+    return even ? mix32(h) : bucket_position<W>(h);
+}
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier + 1-D bulk async copy (TMA engine, SASS: UBLKCP) -- global -> shared staging
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

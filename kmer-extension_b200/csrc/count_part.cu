@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(NT, PART_MINB) partition_kernel(ScanArgs a, Pa
     const int k = a.k;
     const int m = plan.m;
     const uint32_t rmax = plan.rmax;
-    const uint32_t mshift = 32 - 2 * m;
+    const uint32_t himask = 0xffffffffu << (32 - 2 * m);
     unsigned long long overflow_kmers = 0;
     if (t < 2) bdm[TILE / 32 + t] = 0xffffffffu;   // the tile end ends every run
     uint64_t pol_last, pol_first;
@@ -149,9 +149,7 @@ __global__ void __launch_bounds__(NT, PART_MINB) partition_kernel(ScanArgs a, Pa
                     const int q = j >> 4, sh = (j & 15) * 2;
                     top = __funnelshift_l(w[q + 1], w[q], sh);
                 }
-                uint32_t mm = top >> mshift;
-                uint32_t x = mm * 0x9E3779B1u;
-                h[j + 1] = x ^ (x >> 15);
+                h[j + 1] = mmer_hash(top, himask, m);
             }
             // sliding minimum over W consecutive m-mers: log-steps up to the largest power of two P <= W, then two
             // overlapping P-windows cover a W-window
@@ -222,7 +220,7 @@ __global__ void __launch_bounds__(NT, PART_MINB) partition_kernel(ScanArgs a, Pa
             posq[q] = 0xffffffffu; bq[q] = 0; slot[q] = 0;
             if (r < n_warp_runs) {
                 const unsigned long long d = wruns[r];
-                bq[q] = __umulhi(mix32((uint32_t)(d >> 32)), plan.hash_buckets) >> plan.fine_shift;
+                bq[q] = coarse_bucket(bucket_position<W>((uint32_t)(d >> 32), plan.even), plan.hash_buckets, plan.fine_shift);
                 const uint32_t R = run_length((uint32_t)d);
                 posq[q] = (uint32_t)d | (R << 16);
                 const uint32_t L0 = R < rmax ? R : rmax;
@@ -245,7 +243,7 @@ __global__ void __launch_bounds__(NT, PART_MINB) partition_kernel(ScanArgs a, Pa
             if (posq[q] != 0xffffffffu) emit_run(bq[q], slot[q], posq[q] & 0xffffu, posq[q] >> 16);
         for (uint32_t r = EMIT_Q * 32 + lane; r < n_warp_runs; r += 32) {   // more than 192 runs in 512 windows: rare
             const unsigned long long d = wruns[r];
-            const uint32_t b = __umulhi(mix32((uint32_t)(d >> 32)), plan.hash_buckets) >> plan.fine_shift;
+            const uint32_t b = coarse_bucket(bucket_position<W>((uint32_t)(d >> 32), plan.even), plan.hash_buckets, plan.fine_shift);
             const uint32_t R = run_length((uint32_t)d);
             const uint32_t L0 = R < rmax ? R : rmax;
             const uint32_t s0 = (uint32_t)atomicAdd(&fill[b], ((unsigned long long)L0 << 32) | 1ull);
@@ -715,7 +713,7 @@ __global__ void __launch_bounds__(256) refine_kernel(PartitionPlan plan, int k, 
     uint32_t* s_nrec = refine_smem;
     uint32_t* s_nk = refine_smem + F;
     const int t = threadIdx.x;
-    const uint32_t mshift = 32 - 2 * plan.m;
+    const uint32_t himask = 0xffffffffu << (32 - 2 * plan.m);
     unsigned long long overflow_kmers = 0;
     uint64_t pol_last, pol_first;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
@@ -723,7 +721,8 @@ __global__ void __launch_bounds__(256) refine_kernel(PartitionPlan plan, int k, 
     for (uint32_t c = blockIdx.x; c < n_coarse; c += gridDim.x) {
         for (uint32_t f = t; f < 2 * F; f += blockDim.x) refine_smem[f] = 0;
         __syncthreads();
-        for (int sI = 0; sI < n_src; sI++) {
+        for (int sJ = 0; sJ < n_src; sJ++) {
+            const int sI = (int)((c + (uint32_t)sJ) % (uint32_t)n_src);   // CTAs start at different sources: all links busy at all times
             const uint32_t n = min((uint32_t)ld_nc_u64(reinterpret_cast<const uint64_t*>(src.fill[sI]) + c), coarse_cap);
             const Rec<RECW>* base = reinterpret_cast<const Rec<RECW>*>(src.recs[sI]) + (uint64_t)c * coarse_cap;
             constexpr int RQ = 4;                                 // records in flight per thread
@@ -750,10 +749,9 @@ __global__ void __launch_bounds__(256) refine_kernel(PartitionPlan plan, int k, 
 #pragma unroll
                     for (int j = 0; j < W; j++) {
                         const uint32_t top = (uint32_t)((hi[q] << (2 * j)) >> 32);
-                        const uint32_t x = (top >> mshift) * 0x9E3779B1u;
-                        hmin = min(hmin, x ^ (x >> 15));
+                        hmin = min(hmin, mmer_hash(top, himask, plan.m));
                     }
-                    const uint32_t f = __umulhi(mix32(hmin), plan.hash_buckets) & (F - 1);
+                    const uint32_t f = fine_in_coarse(bucket_position<W>(hmin, plan.even), plan.fine_shift);
                     const uint32_t slot = atomicAdd(&s_nrec[f], 1u);
                     atomicAdd(&s_nk[f], L);
                     Rec<RECW>* dst = nullptr;
@@ -798,7 +796,7 @@ __global__ void __launch_bounds__(256) refine_staged_kernel(PartitionPlan plan, 
     __shared__ __align__(16) unsigned long long s_sorted[RF_ROUND];
     __shared__ unsigned long long s_carry[3][F];             // bucket t's pending records: s_carry[0..n_carry)[t]
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const uint32_t mshift = 32 - 2 * plan.m;
+    const uint32_t himask = 0xffffffffu << (32 - 2 * plan.m);
     const uint32_t cap = plan.cap;                           // a multiple of 4 (make_partition_plan): regions are whole sectors
     unsigned long long overflow_kmers = 0;
     for (uint32_t c = blockIdx.x; c < n_coarse; c += gridDim.x) {
@@ -811,14 +809,16 @@ __global__ void __launch_bounds__(256) refine_staged_kernel(PartitionPlan plan, 
         };
         s_gk[t] = 0;
         // the sources' segment sizes, all at once (a source may be another GPU's memory: one round trip, not n_src)
-        if (t < n_src) s_n[t] = min((uint32_t)ld_nc_u64(reinterpret_cast<const uint64_t*>(src.fill[t]) + c), coarse_cap);
+        // position j of the order is source (c + j) % n_src: CTAs start at different sources, so that all GPUs' links are busy at
+        // all times (in the same order everywhere, every owner would read from the same GPU at the same moment)
+        if (t < n_src) s_n[t] = min((uint32_t)ld_nc_u64(reinterpret_cast<const uint64_t*>(src.fill[(c + t) % n_src]) + c), coarse_cap);
         __syncthreads();
         // rounds of RF_ROUND records over all sources; the loads of the next round are issued before this one is processed
         auto seek = [&](int& sI, uint32_t& r0) {             // first (source, round) at or after (sI, r0) that holds records
             while (sI < n_src && r0 >= s_n[sI]) { sI++; r0 = 0; }
         };
         auto fetch = [&](int sI, uint32_t r0, uint64_t (&rec)[4]) {
-            const uint64_t* base = reinterpret_cast<const uint64_t*>(src.recs[sI]) + (uint64_t)c * coarse_cap;
+            const uint64_t* base = reinterpret_cast<const uint64_t*>(src.recs[(c + (uint32_t)sI) % (uint32_t)n_src]) + (uint64_t)c * coarse_cap;
             const uint32_t n = s_n[sI];
 #pragma unroll
             for (int q = 0; q < 4; q++) {
@@ -849,10 +849,9 @@ __global__ void __launch_bounds__(256) refine_staged_kernel(PartitionPlan plan, 
 #pragma unroll
                         for (int j = 0; j < W; j++) {
                             const uint32_t top = (uint32_t)((rec[q] << (2 * j)) >> 32);
-                            const uint32_t x = (top >> mshift) * 0x9E3779B1u;
-                            hmin = min(hmin, x ^ (x >> 15));
+                            hmin = min(hmin, mmer_hash(top, himask, plan.m));
                         }
-                        const uint32_t f = __umulhi(mix32(hmin), plan.hash_buckets) & (F - 1);
+                        const uint32_t f = fine_in_coarse(bucket_position<W>(hmin, plan.even), plan.fine_shift);
                         fr[q] = (f << 16) | atomicAdd(&s_hist[f], 1u);
                         atomicAdd(&s_gk[f], (uint32_t)(rec[q] & 15u) + 1);
                     }
@@ -1127,6 +1126,7 @@ void launch_scatter_refine(const DeviceInfo& di, const ScanArgs& a, const Partit
     if (p.recw == 1) {
         if (p.w == 4) KMER_SR(4, 1);
         else if (p.w == 6) KMER_SR(6, 1);
+        else if (p.w == 9) KMER_SR(9, 1);
         else KMER_SR(8, 1);
     } else {
         if (p.w == 8) KMER_SR(8, 2);
@@ -1142,29 +1142,36 @@ void partition_force_window(int w) { g_forced_window = w; }
 
 PartitionPlan make_partition_plan(uint64_t n_kmers, int k) {
     PartitionPlan p{};
-    // minimizer window: the m-mer (m = k - w + 1, capped at 16 bases) must be long enough (>= 14 bases where k allows) that
-    // the minimizers spread evenly over the buckets; shorter ones leave few distinct minimizers and lopsided buckets
+    // minimizer window: w windows share a record while their minimizer (an m-mer, m = k - w + 1, capped at 16 bases) stays the same
     const uint32_t target = TARGET_KMERS_PER_BUCKET;
     uint64_t nb = (n_kmers + target - 1) / target;
     if (nb < 1) nb = 1;
     if (nb > 0x7fffffffull) nb = 0x7fffffffull;
     p.recw = k <= 26 ? 1 : 2;
-    // The widest window (fewest records) whose m-mers still spread evenly over the buckets: 4^m >= 65 * buckets.  (Measured at
-    // k=21: 14-base m-mers leave 1 bucket of 817 k above the on-chip limit at 1 GB, 0.2 % of them at 4 GB -- still cheaper than
-    // the 30 % more records of the next narrower window -- and would leave ~2 % at 8 GB.)  n_kmers is the size of the WHOLE job.
+    // The widest window (fewest records: about 2/(w+1) per k-mer) whose m-mers are still fine-grained enough for the buckets: a
+    // bucket covers a range of the minimizer order of equal expected load (minimizer_rank), but it cannot split an m-mer, and one
+    // frequent m-mer is the minimizer of up to w windows per occurrence.  4^m >= 30 * buckets keeps that below ~1/4 of a bucket
+    // (simulated: 0.3 % of the k-mers in buckets above the on-chip limit at 41 m-mers per bucket, ~1 % at 30; they go to tier 2).
+    // n_kmers is the size of the WHOLE job.  9 windows need k = 21 or 22: a 13-base m-mer and 9 windows in an 8-byte record.
     {
-        static const int ws1[] = {8, 6, 4}, ws2[] = {16, 12, 8};
+        static const int ws1[] = {9, 8, 6, 4}, ws2[] = {16, 16, 12, 8};
         const int* ws = p.recw == 1 ? ws1 : ws2;
-        p.w = ws[2];
-        for (int i = 0; i < 3; i++) {
+        p.w = ws[3];
+        p.even = 1;                                        // nothing fits: the narrowest window, m-mers spread by a second hash
+        for (int i = 0; i < 4; i++) {
             const int m = k - ws[i] + 1 > 16 ? 16 : k - ws[i] + 1;
-            if (m >= 14 && ldexp(1.0, 2 * m) >= 65.0 * (double)nb) { p.w = ws[i]; break; }
+            if (ws[i] == 9 && k > 22) continue;            // 9 windows do not fit an 8-byte record (30 bases) beyond k = 22
+            if (ldexp(1.0, 2 * m) >= 30.0 * (double)nb) { p.w = ws[i]; p.even = 0; break; }
         }
     }
     if (g_forced_window) {                                 // tests only (kmer_cuda_test_force_window): must suit the record width and k
         const int w = g_forced_window;
-        const bool ok = p.recw == 1 ? (w == 4 || w == 6 || w == 8) : (w == 8 || w == 12 || w == 16);
-        if (ok && k - w + 1 >= 2) p.w = w;
+        const bool ok = p.recw == 1 ? (w == 4 || w == 6 || w == 8 || w == 9) : (w == 8 || w == 12 || w == 16);
+        if (ok && k - w + 1 >= 2) {
+            p.w = w;
+            const int mf = k - w + 1 > 16 ? 16 : k - w + 1;
+            p.even = ldexp(1.0, 2 * mf) >= 30.0 * (double)nb ? 0 : 1;
+        }
     }
     int m = k - p.w + 1;
     p.m = m > 16 ? 16 : m;
@@ -1194,6 +1201,7 @@ void launch_partition(const DeviceInfo& di, const ScanArgs& a, const PartitionPl
     if (!n_tiles) return;
     if (p.w == 4) partition_kernel<4, 1><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill);
     else if (p.w == 6) partition_kernel<6, 1><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill);
+    else if (p.w == 9) partition_kernel<9, 1><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill);
     else if (p.w == 12) partition_kernel<12, 2><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<2>*)d_recs, (Rec<2>*)d_spill);
     else if (p.w == 8 && p.recw == 1) partition_kernel<8, 1><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill);
     else if (p.w == 8) partition_kernel<8, 2><<<(unsigned)grid, NT, 0, st>>>(a, p, d_fill, (Rec<2>*)d_recs, (Rec<2>*)d_spill);
@@ -1287,6 +1295,7 @@ void launch_refine(const DeviceInfo& di, const PartitionPlan& p, int k, int n_sr
 #define KMER_RS(W_) refine_staged_kernel<W_><<<grid, 256, 0, st>>>(p, k, n_src, n_coarse, coarse_cap, src, d_fill, (Rec<1>*)d_recs, (Rec<1>*)d_spill, d_status)
         if (p.w == 4) KMER_RS(4);
         else if (p.w == 6) KMER_RS(6);
+        else if (p.w == 9) KMER_RS(9);
         else KMER_RS(8);
 #undef KMER_RS
         return;
@@ -1295,6 +1304,7 @@ void launch_refine(const DeviceInfo& di, const PartitionPlan& p, int k, int n_sr
     if (p.w == 6) KMER_RF(6, 1);
     else if (p.w == 12) KMER_RF(12, 2);
     else if (p.w == 4) KMER_RF(4, 1);
+    else if (p.w == 9) KMER_RF(9, 1);
     else if (p.w == 8 && p.recw == 1) KMER_RF(8, 1);
     else if (p.w == 8) KMER_RF(8, 2);
     else KMER_RF(16, 2);

@@ -48,13 +48,15 @@ void launch_hash_compact(const DeviceInfo& di, const kmer_count_pair* d_slots, u
 struct PartitionPlan {
     uint32_t n_buckets;   // buckets the k-mers are spread over (about 1200 k-mers each)
     uint32_t cap;         // records a bucket region holds
-    int w;                // m-mers per minimizer window (4, 8 or 16)
+    int w;                // m-mers per minimizer window (4, 6, 8, 9, 12 or 16)
     int m;                // m-mer length (<= 16)
     int recw;             // 64-bit words per super-k-mer record (1: k <= 26, 2: k >= 27)
     int rmax;             // max k-mers per record
     uint64_t spill_cap;   // records the spill list holds
     uint32_t hash_buckets; // range the minimizer hash is scaled to (== n_buckets unless partitioning coarsely)
     int fine_shift;       // bucket = scaled hash >> fine_shift (sharded counting: coarse partitions of 2^fine_shift buckets)
+    int even;             // 1: spread the m-mers over the buckets by a second hash (fewer than 30 m-mers per bucket: the load-aware
+                          // map of bucket_position() cannot split an m-mer); 0: buckets of equal expected load
 };
 PartitionPlan make_partition_plan(uint64_t n_kmers, int k);
 void partition_force_window(int w);   // tests: 0 = automatic

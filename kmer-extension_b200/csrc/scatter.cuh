@@ -33,22 +33,18 @@ constexpr int SCAT_DPT = 4;                               // destinations per th
 constexpr int RF2_THREADS = 1024;
 constexpr int RF2_RQ = 2;                                 // records per thread and round
 
-// hashed m-mer -> minimizer order (shared by both passes and the old partition kernel)
-__device__ __forceinline__ uint32_t mmer_hash(uint32_t mm) {
-    const uint32_t x = mm * 0x9E3779B1u;
-    return x ^ (x >> 15);
-}
 // global fine bucket of a record: the bucket of the minimizer of its first window
 template <int W, int RECW>
 __device__ __forceinline__ uint32_t record_bucket(uint64_t hi, const PartitionPlan& plan) {
-    const uint32_t mshift = 32 - 2 * plan.m;
+    const uint32_t himask = 0xffffffffu << (32 - 2 * plan.m);
     uint32_t hmin = 0xffffffffu;
 #pragma unroll
     for (int j = 0; j < W; j++) {
         const uint32_t top = (uint32_t)((hi << (2 * j)) >> 32);
-        hmin = min(hmin, mmer_hash(top >> mshift));
+        hmin = min(hmin, mmer_hash(top, himask, plan.m));
     }
-    return __umulhi(mix32(hmin), plan.hash_buckets);
+    const uint32_t pos = bucket_position<W>(hmin, plan.even);
+    return (coarse_bucket(pos, plan.hash_buckets, plan.fine_shift) << plan.fine_shift) | fine_in_coarse(pos, plan.fine_shift);
 }
 
 template <int RECW>
@@ -195,7 +191,7 @@ __global__ void __launch_bounds__(NT, SCAT_MINB) scatter_kernel(ScanArgs a, Part
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int k = a.k;
     const uint32_t rmax = plan.rmax;
-    const uint32_t mshift = 32 - 2 * plan.m;
+    const uint32_t himask = 0xffffffffu << (32 - 2 * plan.m);
     const uint32_t D = sp.n_coarse;
     Stage<RECW> st;
     st.init(smem_u32(scat_dyn), D, sp.caps);
@@ -264,7 +260,7 @@ __global__ void __launch_bounds__(NT, SCAT_MINB) scatter_kernel(ScanArgs a, Part
                     const int q = j >> 4, sh = (j & 15) * 2;
                     top = __funnelshift_l(w[q + 1], w[q], sh);
                 }
-                h[j + 1] = mmer_hash(top >> mshift);
+                h[j + 1] = mmer_hash(top, himask, plan.m);
             }
             // sliding minimum over W consecutive m-mers: log-steps up to the largest power of two P <= W, then two
             // overlapping P-windows cover a W-window
@@ -332,7 +328,7 @@ __global__ void __launch_bounds__(NT, SCAT_MINB) scatter_kernel(ScanArgs a, Part
             __syncwarp();
             const uint32_t npass = min(n_warp_runs - pass0, (uint32_t)SCAT_RUNCAP);
             for (uint32_t r = lane; r < npass; r += 32) {             // run r of the pass: emitted by lane r % 32
-                const uint32_t dest = __umulhi(mix32(wh[r]), plan.hash_buckets) >> plan.fine_shift, p0 = wp[r];
+                const uint32_t dest = coarse_bucket(bucket_position<W>(wh[r], plan.even), plan.hash_buckets, plan.fine_shift), p0 = wp[r];
                 const uint32_t R = run_length(p0);
                 for (uint32_t off = 0; off < R; off += rmax) put(dest, make_record((int)(p0 + off), (int)min(R - off, rmax)));
             }

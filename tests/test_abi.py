@@ -81,7 +81,12 @@ def test_shard_plan_invariants(lib):
                     fine_total = p.n_buckets << p.fine_shift
                     assert fine_total * 1200 >= total
                     # minimizer window: suits the record width, m-mer at most 16 bases, windows fit a record
-                    assert p.w in ((4, 6, 8) if k <= 26 else (8, 12, 16))
+                    assert p.w in ((4, 6, 8, 9) if k <= 26 else (8, 12, 16))
+                    assert p.w != 9 or k <= 22                                  # 9 windows + the k-1 overlap in a 30-base record
+                    # the m-mers are fine-grained enough for the buckets (30 per bucket) unless the narrowest window is all that is left
+                    fine = 4 ** p.m >= 30 * ((total + 1199) // 1200)
+                    assert fine or p.w == (4 if k <= 26 else 8)
+                    assert p.even_spread == (0 if fine else 1)                  # too coarse for load-aware buckets: second hash
                     assert p.m == min(16, k - p.w + 1) and p.m >= 2
                     assert 1 <= p.rmax <= 16 and p.rmax + k - 1 <= (30 if k <= 26 else 61)
     bad = api.KmerShardPlan()
@@ -91,13 +96,14 @@ def test_shard_plan_invariants(lib):
 
 
 def test_shard_plan_window_follows_job_size(lib):
-    """Bigger jobs get narrower minimizer windows (longer m-mers) so that buckets stay even."""
+    """Bigger jobs get narrower minimizer windows (longer m-mers): an m-mer cannot be split between buckets."""
     def w(total, k):
         p = api.KmerShardPlan()
         assert lib.kmer_cuda_shard_plan(total, k, 8, C.byref(p)) == 0
         return p.w, p.m
-    assert w(980_000_000, 21) == (8, 14)        # 1 GB: 14-base m-mers are enough
-    assert w(7_840_000_000, 21) == (6, 16)      # 8 GB
+    assert w(980_000_000, 21) == (9, 13)        # 1 GB: 13-base m-mers are enough (82 per bucket)
+    assert w(7_840_000_000, 21) == (8, 14)      # 8 GB: 41 14-base m-mers per bucket
+    assert w(40_000_000_000, 21) == (6, 16)     # 40 GB
     assert w(9_700_000_000, 31) == (16, 16)     # C3: already 16-base m-mers
     assert w(980_000_000, 27) == (12, 16)       # W=16 would leave 12-base m-mers
     assert w(980_000_000, 17)[0] == 4

@@ -18,7 +18,8 @@ eng.set_profiling(True)
 for it in range(3):
     try:
         eng.dev_count(d_seq, int(off[-1]), d_off, n_rows, KK, d_pairs, algo=int(os.environ.get('KMER_ALGO','3')))
-        eng.dev_finish()
+        r = eng.dev_finish()
+        extra = f"tier2_kmers={r.n_tier2} recounted={r.n_overflow} distinct={r.n_distinct}"
     except api.KmerSqlError as e:
-        pass
-    print(os.environ.get("KMER_CUDA_DEBUG_PARTITION", "0"), eng.phases())
+        extra = f"error: {e}"
+    print(f"k={KK}", [(n, round(ms, 3)) for n, ms in eng.phases()], extra)
