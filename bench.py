@@ -100,6 +100,12 @@ def table_checksum(torch, keys, counts=None, chunk=1 << 26):
 def keys_unique(torch, keys):
     if keys.numel() < 2:
         return True
+    if keys.numel() >= (1 << 30):        # torch.sort takes at most INT_MAX elements: equal keys share their low bits, sort by piece
+        pieces = 1
+        while keys.numel() // pieces >= (1 << 29):
+            pieces *= 2
+        low = keys & (pieces - 1)
+        return all(keys_unique(torch, keys[low == r]) for r in range(pieces))
     s, _ = torch.sort(keys)
     return not bool((s[1:] == s[:-1]).any().item())
 
