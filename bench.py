@@ -2,7 +2,9 @@
 """bench.py -- k-mers counted per second (whole job) at k=21 on synthetic 1 kb reads.
 
     python bench.py --gpus 1 --steps K --warmup W            # this repository's CUDA path
-    python bench.py --impl reference --steps K --warmup W     # the reference's C functions on the host cores
+    python bench.py --impl reference --steps K --warmup W     # the reference's C functions on the host cores: every step a
+                                                              # bounded sample of the same workload, sized from a calibration
+                                                              # pass (--ref-seconds), + one larger pass reported beside it
 
 One "step" = one full pass of the hot path (generate_kmers over every row + GROUP BY count) over one
 batch.  N=1 workload = BASELINE.json configs[1]: k=21 count over 1 GB of synthetic DNA
@@ -43,6 +45,14 @@ def load_pkg():
     g.load_package()
     from kmer_extension_b200 import api, datagen
     return g, api, datagen
+
+
+def workload_name(config: str, k: int, n_rows: int) -> str:
+    """config.workload of BOTH arms (the reference arm runs bounded samples of the same workload)."""
+    gb = n_rows * READ_LEN / 1e9
+    return {"c2": f"configs[1]: k={k} count over {gb:.3g} GB synthetic DNA per GPU ({n_rows} reads x {READ_LEN}, seed 2+rank)",
+            "c3": f"configs[2]: k=31 count over 10 GB synthetic DNA in total, {n_rows} reads x {READ_LEN} per GPU (seed 3+rank)",
+            "c2x10": f"north-star shape: k=21 count over 10 GB synthetic DNA in total, {n_rows} reads x {READ_LEN} per GPU (seed 2+rank)"}[config]
 
 
 def measured_peaks():
@@ -208,21 +218,58 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def ref_sample_plan(args, rate_small: float, threads: int):
+    """How many reads one step of the reference arm counts: sized from a calibration pass so that warm-up + steps take about
+    --ref-seconds, and bounded by what the executor stand-in's hash table can hold in this host's RAM."""
+    import psutil
+    kmers_per_read = READ_LEN - K + 1
+    avail = psutil.virtual_memory().available
+    # measured on the reference driver (oracle/ref_driver.c): ~155 B of RSS per group at k=21 (entry + ASCII key + per-thread
+    # partial tables + the merged table), random DNA has one group per window
+    bytes_per_group = 160
+    fit_reads = int(0.6 * avail / bytes_per_group / kmers_per_read)
+    if args.ref_reads > 0:
+        return args.ref_reads, fit_reads, avail
+    per_step = min(max(args.ref_seconds / max(args.steps + args.warmup, 1), 0.5), 30.0)
+    n = int(0.8 * rate_small * per_step / kmers_per_read)     # 0.8: the rate drops as the table outgrows the caches
+    return max(2000, min(n, fit_reads, args.reads)), fit_reads, avail
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path, all host threads."""
+    """--impl reference: the reference's CPU implementation of the path, all host threads.  Every step counts a bounded
+    sample (a prefix of the same seeded workload); the sample is sized from a calibration pass, and ONE more pass over the
+    largest sample that is affordable in time and host RAM is reported beside it so that the per-k-mer rate is not
+    extrapolated from a table that fits the caches."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     _, api, datagen = load_pkg()
     threads = host_threads()
-    n_reads = args.ref_reads
+    cal = cpu_reference_run(datagen, 2000, threads, 1, 0)
+    n_reads, fit_reads, avail = ref_sample_plan(args, cal["value"], threads)
     r = cpu_reference_run(datagen, n_reads, threads, args.steps, args.warmup)
+    kmers_per_read = READ_LEN - K + 1
+    scaling_info = {"calibration": {"reads": 2000, "value": cal["value"]},
+                    "host_ram_available_bytes": int(avail),
+                    "largest_sample_that_fits_host_ram_reads": int(fit_reads),
+                    "whole_workload_reads": int(args.reads),
+                    "whole_workload_fits_host_ram": bool(fit_reads >= args.reads)}
+    if args.ref_large_seconds > 0:
+        n_large = int(min(fit_reads, args.reads, r["value"] * args.ref_large_seconds / kmers_per_read))
+        if n_large > 2 * n_reads:
+            big = cpu_reference_run(datagen, n_large, threads, 1, 0)
+            scaling_info["largest_pass"] = {"reads": n_large, "value": big["value"], "unit": UNIT, "seconds": big["seconds"],
+                                            "what": "one untimed-by-the-driver pass over the largest sample affordable in "
+                                                    f"{args.ref_large_seconds:.0f} s and in host RAM; not the line's value"}
+    cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    cpu["sample_scaling"] = scaling_info
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"k=21 count, bounded sample of configs[1]: {n_reads} reads x 1000 bases per step",
-                       "k": K, "read_len": READ_LEN},
-            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "config": {"workload": workload_name(args.config, K, args.reads), "k": K, "read_len": READ_LEN,
+                       "reads_per_gpu": args.reads, "algo": 0,
+                       "sample_per_step": f"{n_reads} reads x {READ_LEN} bases (prefix of the workload, seed 2)"},
+            "cpu_baseline": cpu,
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -312,7 +359,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU (1 kb each); default = 1 GB")
     ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 dense, 2 hash, 3 minimizer partition")
-    ap.add_argument("--ref-reads", type=int, default=4000, help="sample size of the reference arm per step")
+    ap.add_argument("--ref-reads", type=int, default=0, help="reads per step of the reference arm (0 = sized from a calibration pass "
+                                                             "so that the run takes about --ref-seconds)")
+    ap.add_argument("--ref-seconds", type=float, default=120.0, help="time budget of the reference arm's warm-up + timed steps")
+    ap.add_argument("--ref-large-seconds", type=float, default=45.0,
+                    help="reference arm: one extra pass over the largest sample affordable in this many seconds (0 = skip)")
     ap.add_argument("--cpu-reads", type=int, default=20000, help="sample size of the cpu_baseline leg")
     ap.add_argument("--workload", default="count", choices=["count", "extract", "match_c4", "match_c5"],
                     help="count = the headline (configs[1]); the others are secondary parity-config measurements")
@@ -782,9 +833,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
-            "config": {"workload": {"c2": f"configs[1]: k={K} count over {n_bases / 1e9:.3g} GB synthetic DNA per GPU ({n_rows} reads x {READ_LEN}, seed 2+rank)",
-                                    "c3": f"configs[2]: k=31 count over 10 GB synthetic DNA in total, {n_rows} reads x {READ_LEN} per GPU (seed 3+rank)",
-                                    "c2x10": f"north-star shape: k=21 count over 10 GB synthetic DNA in total, {n_rows} reads x {READ_LEN} per GPU (seed 2+rank)"}[args.config],
+            "config": {"workload": workload_name(args.config, K, n_rows),
                        "k": K, "read_len": READ_LEN,
                        "reads_per_gpu": n_rows, "algo": args.algo, "n_kmers_per_step": n_kmers * world,
                        "n_distinct_rank0": n_distinct, "recounted_kmers": int(res.n_overflow),

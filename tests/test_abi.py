@@ -113,7 +113,8 @@ def test_bench_reference_arm_prints_one_json_line():
     """`bench.py --impl reference` (the reference's C functions on the host cores) needs no GPU: one JSON line with the
     keys the driver reads; under torchrun every rank but 0 stays silent."""
     import json, os, subprocess, sys
-    cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-reads", "200"]
+    cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-reads", "200",
+           "--ref-large-seconds", "0"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
@@ -122,6 +123,19 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["metric"] == "kmers_counted_per_sec_k21" and d["unit"] == "k-mers/s"
     assert d["value"] > 0 and d["higher_is_better"] is True and d["cpu_baseline"]["kind"] in ("reference", "port")
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+    # the reference arm runs on the CUDA arm's config: same workload name, its own sample stated beside it
+    assert d["config"]["workload"].startswith("configs[1]: k=21 count over 1 GB") and "200 reads" in d["config"]["sample_per_step"]
+    assert d["cpu_baseline"]["sample_scaling"]["largest_sample_that_fits_host_ram_reads"] > 0
+    # sized from a calibration pass when --ref-reads is not given; one larger pass beside it
+    auto = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-seconds", "2",
+            "--ref-large-seconds", "3"]
+    out2 = subprocess.run(auto, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out2.returncode == 0, out2.stderr[-2000:]
+    d2 = json.loads([ln for ln in out2.stdout.splitlines() if ln.startswith("{")][0])
+    sc = d2["cpu_baseline"]["sample_scaling"]
+    assert sc["calibration"]["value"] > 0 and d2["value"] > 0
+    if "largest_pass" in sc:
+        assert sc["largest_pass"]["reads"] <= sc["largest_sample_that_fits_host_ram_reads"]
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
     assert out.returncode == 0 and not [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
