@@ -321,6 +321,15 @@ const kmer_cuda_error *kmer_cuda_multi_last_error(const kmer_cuda_multi *m);
 int kmer_cuda_multi_submit_count(kmer_cuda_multi *m, const char *seq, const uint64_t *row_off, uint64_t n_rows, int k,
 								 kmer_count_pair **pairs, uint64_t *n_distinct, uint64_t *n_kmers);
 void kmer_cuda_multi_release(kmer_cuda_multi *m, int device_index, void *result);
+/* kmer_cuda_submit_match on every device of the handle (kmer_equals / kmer_starts_with[_op] / kmer_contains / kmer_containing,
+ * kmer.c:226-285, are independent per k-mer: the column is sharded, the constants are replicated, nothing is exchanged).
+ * The column is cut on multiples of 32 k-mers, device d matches its slice, and its words of every row are copied straight to
+ * their place in ONE bit matrix with the layout of kmer_cuda_submit_match (row c = constant c, words_per_row = ceil(m/32));
+ * (*hits)[c] is the sum over the devices.  Same errors as kmer_cuda_submit_match (a bad constant: row = its index).
+ * Both results belong to device 0 of the handle: kmer_cuda_multi_release(m, 0, *bits) / (m, 0, *hits). */
+int kmer_cuda_multi_submit_match(kmer_cuda_multi *m, int op, const int *ops, const uint64_t *codes, const uint8_t *lens,
+								 uint64_t n_kmers, int k, const char *const *consts, uint32_t n_consts, uint32_t **bits,
+								 uint64_t *words_per_row, uint64_t **hits);
 
 /* Upper bound of the number of k-mers (= groups) a batch can produce: n_bases - n_rows*(k-1). */
 uint64_t kmer_cuda_max_kmers(uint64_t n_bases, uint64_t n_rows, int k);

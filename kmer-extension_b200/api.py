@@ -43,7 +43,7 @@ ABI_SYMBOLS = [
     "kmer_cuda_dev_shard_count_peers", "kmer_cuda_ipc_export", "kmer_cuda_ipc_open", "kmer_cuda_ipc_close",
     "kmer_cuda_dev_merge_begin", "kmer_cuda_dev_merge_add", "kmer_cuda_dev_merge_emit", "kmer_cuda_test_force_window",
     "kmer_cuda_init_multi", "kmer_cuda_shutdown_multi", "kmer_cuda_multi_device_count", "kmer_cuda_multi_last_error",
-    "kmer_cuda_multi_submit_count", "kmer_cuda_multi_release", "kmer_cuda_dev_pack_codes",
+    "kmer_cuda_multi_submit_count", "kmer_cuda_multi_release", "kmer_cuda_dev_pack_codes", "kmer_cuda_multi_submit_match",
 ]
 
 

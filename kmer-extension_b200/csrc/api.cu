@@ -1861,3 +1861,99 @@ extern "C" int kmer_cuda_multi_submit_count(kmer_cuda_multi* m, const char* seq,
     // 3. the exchange ran out of room somewhere (skewed input): exact merge instead
     return multi_count_merge(m, nb, nr, k, pairs, n_distinct, n_kmers);
 }
+
+// equals / starts_with / contains over a host column on every device of the handle ("shard M, replicate patterns, no
+// collective").  The column is cut on multiples of 32 k-mers, so every device's words of a bit row are whole 32-bit words of the
+// P x M matrix: device i matches its slice against all constants and its words land in place -- one strided copy per device
+// straight into the one pinned result matrix -- and the per-constant hit counts are added on the host.  Same result layout as
+// kmer_cuda_submit_match; both result buffers belong to device 0's context (kmer_cuda_multi_release(m, 0, ...)).
+extern "C" int kmer_cuda_multi_submit_match(kmer_cuda_multi* m, int op, const int* ops, const uint64_t* codes, const uint8_t* lens,
+                                            uint64_t n_kmers, int k, const char* const* consts, uint32_t n_consts, uint32_t** bits,
+                                            uint64_t* words_per_row, uint64_t** hits) {
+    if (!m || !bits || !words_per_row) return KMER_ERR_BAD_ARGUMENT;
+    *bits = nullptr;
+    if (hits) *hits = nullptr;
+    m->err.status = KMER_OK;
+    const int n = (int)m->ctx.size();
+    if (n == 1) {
+        int rc = kmer_cuda_submit_match(m->ctx[0], op, ops, codes, lens, n_kmers, k, consts, n_consts, bits, words_per_row, hits);
+        if (rc) m->err = m->ctx[0]->err;
+        return rc;
+    }
+    if ((n_kmers && !codes) || (n_consts && !consts)) {
+        set_error(&m->err, KMER_ERR_BAD_ARGUMENT, "XX000", "kmer_cuda: bad argument: codes / consts", "", -1);
+        return KMER_ERR_BAD_ARGUMENT;
+    }
+    const uint64_t wpr = (n_kmers + 31) / 32;
+    *words_per_row = wpr;
+    std::vector<uint64_t> cut(n + 1);
+    for (int i = 0; i <= n; i++) cut[i] = i == n ? n_kmers : ((n_kmers / n * i + n_kmers % n * i / n) & ~31ull);
+    kmer_cuda_ctx* c0 = m->ctx[0];
+    cudaSetDevice(m->dev[0]);
+    PinGuard g_bits(c0), g_hits(c0);
+    g_bits.p = pinned_get(c0, (size_t)n_consts * wpr * 4);
+    if (!g_bits.p) return multi_fail(m, c0);
+    g_hits.p = pinned_get(c0, (size_t)n_consts * 8);
+    if (!g_hits.p) return multi_fail(m, c0);
+    std::vector<uint64_t*> part(n, nullptr);      // every device's own hit counters, pinned in its context
+    auto drop_parts = [&]() {
+        for (int i = 0; i < n; i++)
+            if (part[i]) { kmer_cuda_release(m->ctx[i], part[i]); part[i] = nullptr; }
+    };
+    for (int i = 0; i < n; i++) {
+        kmer_cuda_ctx* c = m->ctx[i];
+        cudaSetDevice(m->dev[i]);
+        const uint64_t ml = cut[i + 1] - cut[i], wl = (ml + 31) / 32;
+        int rc = ws(c, c->codes, ml * 8);
+        if (!rc && lens) rc = ws(c, c->lens, ml);
+        if (!rc) rc = ws(c, c->bits, (size_t)n_consts * wl * 4);
+        if (!rc) rc = ws(c, c->hits, (size_t)n_consts * 8);
+        if (!rc) rc = h2d(c, c->codes.p, codes + cut[i], ml * 8, c->stream);
+        if (!rc && lens) rc = h2d(c, c->lens.p, lens + cut[i], ml, c->stream);
+        // a bad constant is found on the host before anything is launched, on the first device: reported once
+        if (!rc) rc = kmer_cuda_dev_match(c, op, ops, (const uint64_t*)c->codes.p, lens ? (const uint8_t*)c->lens.p : nullptr, ml, k, consts,
+                                          n_consts, (uint32_t*)c->bits.p, (uint64_t*)c->hits.p, KMER_OWN_STREAM);
+        if (!rc && !(part[i] = (uint64_t*)pinned_get(c, (size_t)n_consts * 8))) rc = c->err.status;
+        cudaError_t ce = cudaSuccess;
+        if (!rc && wl && n_consts) {
+            char* dst = (char*)g_bits.p + (cut[i] / 32) * 4;
+            if (wpr * 4 < (1ull << 31))
+                ce = cudaMemcpy2DAsync(dst, wpr * 4, c->bits.p, wl * 4, wl * 4, n_consts, cudaMemcpyDeviceToHost, c->stream);
+            else                                  // a row longer than the largest pitch: row by row
+                for (uint32_t p = 0; p < n_consts && ce == cudaSuccess; p++)
+                    ce = cudaMemcpyAsync(dst + (size_t)p * wpr * 4, (const char*)c->bits.p + (size_t)p * wl * 4, wl * 4, cudaMemcpyDeviceToHost,
+                                         c->stream);
+        }
+        if (!rc && ce == cudaSuccess && n_consts)
+            ce = cudaMemcpyAsync(part[i], c->hits.p, (size_t)n_consts * 8, cudaMemcpyDeviceToHost, c->stream);
+        if (!rc && ce != cudaSuccess) rc = cuda_error(c, ce, "D2H match result");
+        if (rc) {
+            for (int j = 0; j <= i; j++) {        // let what is queued drain before the buffers go back
+                cudaSetDevice(m->dev[j]);
+                cudaStreamSynchronize(m->ctx[j]->stream);
+            }
+            drop_parts();
+            return multi_fail(m, c);
+        }
+    }
+    int first = KMER_OK, first_dev = -1;
+    for (int i = 0; i < n; i++) {
+        cudaSetDevice(m->dev[i]);
+        int rc = kmer_cuda_dev_finish(m->ctx[i], KMER_OWN_STREAM, nullptr);
+        if (rc && first == KMER_OK) { first = rc; first_dev = i; }
+    }
+    if (first) {
+        drop_parts();
+        return multi_fail(m, m->ctx[first_dev]);
+    }
+    uint64_t* hsum = (uint64_t*)g_hits.p;
+    for (uint32_t p = 0; p < n_consts; p++) {
+        uint64_t s = 0;
+        for (int i = 0; i < n; i++) s += part[i][p];
+        hsum[p] = s;
+    }
+    drop_parts();
+    *bits = (uint32_t*)g_bits.take();
+    if (hits) *hits = (uint64_t*)g_hits.take();
+    return KMER_OK;
+}

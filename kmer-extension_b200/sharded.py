@@ -1,4 +1,4 @@
-"""Sharded k-mer counting: one process per GPU, rows split across ranks, one all-to-all.
+"""Sharded k-mer counting and matching: one process per GPU; counting splits the rows across ranks (one all-to-all or none), matching splits the k-mer column (no data-path collective: class ShardedMatcher at the end).
 
 The reference has no distributed path (its only parallelism is PostgreSQL's parallel query); this is
 the multi-GPU form of `SELECT kmer, count(*) ... GROUP BY kmer` over generate_kmers (kmer.c:289-351):
@@ -22,6 +22,8 @@ all-reduce(sum) of the per-rank tables, every rank emits the bins it owns.
 a stand-in).  The library itself never communicates.
 """
 from __future__ import annotations
+
+import contextlib
 
 import torch
 import torch.distributed as dist
@@ -372,3 +374,88 @@ class ShardedCounter:
         if counted != total_kmers:
             raise RuntimeError(f"sharded dense count lost k-mers: counted {counted}, expected {total_kmers}")
         return int(r.n_distinct), int(r.n_kmers), {"tier2_kmers": 0, "plan": None}
+
+
+class ShardedMatcher:
+    """Batched equals / starts_with / contains over a k-mer column that is sharded across the ranks ("matching is
+    embarrassingly parallel over k-mers: shard M, replicate patterns, no collective").
+
+    The reference evaluates these predicates one (constant, k-mer) pair per fmgr call (kmer_equals kmer.c:226-245,
+    kmer_starts_with* kmer.c:248-265, kmer_contains / kmer_containing kmer.c:268-285); here every rank holds the slice
+    [lo, hi) of the column given by `slice_of` -- slices start on a multiple of 32 k-mers, so the ranks' rows of the P x M bit
+    matrix are whole 32-bit words and concatenate without shifting -- and the constants are replicated.  A rank's bits never
+    leave it (the caller reads its slice of every row back, or filters its slice of the rows); the only communication is one
+    all-reduce of P hit counters plus an error flag, on the stream, so that a rank that fails does not leave the others waiting.
+    """
+
+    def __init__(self, engine, group=None, device=None):
+        self.eng = engine
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._acc = None
+
+    @staticmethod
+    def slice_of(m_total: int, rank: int, world: int):
+        """k-mers [lo, hi) of the column that `rank` matches: even split, cut points on multiples of 32."""
+        def cut(r):
+            return m_total if r >= world else (m_total * r // world) & ~31
+        return cut(rank), cut(rank + 1)
+
+    @staticmethod
+    def words_per_row(m: int) -> int:
+        return (m + 31) // 32
+
+    def match(self, op, d_codes, m_local: int, k: int, consts, d_bits, d_hits, d_lens=None, ops=None, stream=None):
+        """This rank's slice against the replicated constants.  d_bits: int32[P * words_per_row(m_local)] (this rank's words
+        of every row), d_hits: int64[P] -- on return the hit counts over the WHOLE column (summed over the ranks).
+        Returns the local dev_finish result.  Raises on every rank if any rank failed."""
+        consts = [consts] if isinstance(consts, str) else list(consts)
+        P = len(consts)
+        if self._acc is None or self._acc.numel() < P + 1:
+            self._acc = torch.zeros(P + 1, dtype=torch.int64, device=self.device)
+        acc = self._acc[:P + 1]
+        # the counters are copied and reduced on the stream the kernels run on (NCCL takes torch's current stream)
+        on = torch.cuda.stream(stream) if (stream is not None and self.device.type == "cuda") else contextlib.nullcontext()
+        exc = None
+        with on:
+            try:
+                self.eng.dev_match(op, d_codes, m_local, k, consts, d_bits, d_hits, d_lens=d_lens, ops=ops, stream=stream)
+            except Exception as e:     # constants are replicated, so a bad constant raises everywhere; a device error may not
+                exc = e
+            if exc is None:
+                acc[:P].copy_(d_hits[:P])
+                acc[P:].zero_()
+            else:
+                acc.zero_()
+                acc[P:].fill_(1)
+            if self.world > 1:
+                dist.all_reduce(acc, group=self.group)
+            res = None
+            try:
+                res = self.eng.dev_finish(stream)
+            except Exception as e:
+                exc = exc or e
+            failed = int(acc[P].item())
+            if exc is not None:
+                raise exc
+            if failed:
+                raise RuntimeError(f"sharded match: {failed} other rank(s) failed")
+            d_hits[:P].copy_(acc[:P])
+        return res
+
+    def gather_bits(self, d_bits, m_local: int, m_total: int, P: int):
+        """The whole P x words_per_row(m_total) bit matrix on every rank (tests / small results; the product path keeps a
+        rank's words on the rank).  Rows are the concatenation of the ranks' words in rank order."""
+        wl = self.words_per_row(m_local)
+        if self.world == 1:
+            return d_bits[:P * wl].view(P, wl).clone()
+        cuts = [self.slice_of(m_total, r, self.world) for r in range(self.world)]
+        wmax = max(self.words_per_row(hi - lo) for lo, hi in cuts)
+        mine = torch.zeros((P, wmax), dtype=d_bits.dtype, device=d_bits.device)
+        if wl:
+            mine[:, :wl] = d_bits[:P * wl].view(P, wl)
+        parts = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(parts, mine, group=self.group)
+        return torch.cat([parts[r][:, :self.words_per_row(hi - lo)] for r, (lo, hi) in enumerate(cuts)], dim=1)

@@ -94,6 +94,22 @@ class StandInEngine:
         out[: bins.size, 1] = t[bins].astype(np.uint64)
         self._res = _Res(n_kmers=int(t[bins].sum()), n_distinct=int(bins.size))
 
+    def dev_match(self, op, d_codes, m, k, consts, d_bits, d_hits, d_lens=None, ops=None, stream=None):
+        """same bit layout as kmer_cuda_dev_match: row c = words_per_row int32 words, bit i%32 of word i/32 = k-mer i"""
+        co = self.O.COracle()
+        codes = d_codes.numpy().view(np.uint64)[:m]
+        wpr = (m + 31) // 32
+        bits = d_bits.numpy().view(np.uint32)[: len(consts) * wpr].reshape(len(consts), wpr)
+        for c, text in enumerate(consts):
+            if text == "boom":
+                raise ValueError("bad constant")
+            o = op if ops is None else int(ops[c])
+            b = co.match_column(o, codes, k, text.lower()).astype(np.uint8)
+            row = np.packbits(np.concatenate([b, np.zeros(wpr * 32 - m, np.uint8)]), bitorder="little").view(np.uint32)
+            bits[c] = row
+            d_hits[c] = int(b.sum())
+        self._res = _Res()
+
     def dev_finish(self, stream=None):
         return self._res
 
@@ -159,3 +175,61 @@ def test_sharded_count_two_ranks_gloo(tmp_path):
         order = np.argsort(keys)
         assert np.array_equal(keys[order], ok) and np.array_equal(counts[order], oc)
         assert sum(int(o[f"k{k}_nk"]) for o in outs) == on
+
+
+def _match_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import conftest  # noqa: F401
+    from kmer_extension_b200 import datagen, sharded
+    from oracle import oracle as O
+    try:
+        sm = sharded.ShardedMatcher(StandInEngine(O), device=torch.device("cpu"))
+        m_total, k = 1000 + 37, 12                                   # not a multiple of 32: the last rank's row ends mid-word
+        col = datagen.synth_kmer_codes(44, m_total, k)
+        consts = datagen.synth_qkmers(45, 7, k, with_n=True) + ["n" * k]
+        lo, hi = sm.slice_of(m_total, rank, world)
+        assert lo % 32 == 0 and (hi % 32 == 0 or hi == m_total)
+        d_codes = torch.from_numpy(col[lo:hi].view(np.int64).copy())
+        wl = sm.words_per_row(hi - lo)
+        d_bits = torch.zeros(len(consts) * wl, dtype=torch.int32)
+        d_hits = torch.zeros(len(consts), dtype=torch.int64)
+        sm.match(2, d_codes, hi - lo, k, consts, d_bits, d_hits)
+        full = sm.gather_bits(d_bits, hi - lo, m_total, len(consts))
+        hits = d_hits.numpy().copy()
+        # one rank fails alone (a device error would look like this): every rank must raise, nobody may hang
+        raised = False
+        try:
+            sm.match(2, d_codes, hi - lo, k, ["boom"] if rank == 1 else ["acgtacgtacgt"], d_bits, d_hits)
+        except Exception:
+            raised = True
+        np.savez(Path(out_dir) / f"m{rank}.npz", bits=full.numpy(), hits=hits, lo=lo, hi=hi, raised=raised)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_match_two_ranks_gloo(tmp_path):
+    """ShardedMatcher: the column split on 32-k-mer boundaries, constants replicated, hit counts all-reduced; the ranks' words
+    concatenate to the oracle's bit matrix of the whole column."""
+    import conftest  # noqa: F401
+    from kmer_extension_b200 import datagen
+    from oracle import oracle as O
+    world = 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_match_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    outs = [np.load(tmp_path / f"m{r}.npz") for r in range(world)]
+    m_total, k = 1037, 12
+    col = datagen.synth_kmer_codes(44, m_total, k)
+    consts = datagen.synth_qkmers(45, 7, k, with_n=True) + ["n" * k]
+    co = O.COracle()
+    want = np.stack([co.match_column(2, col, k, c.lower()).astype(bool) for c in consts])
+    assert int(outs[0]["hi"]) == int(outs[1]["lo"]) and int(outs[1]["hi"]) == m_total and int(outs[0]["lo"]) == 0
+    for o in outs:
+        assert bool(o["raised"]), "a failure on one rank must raise on every rank"
+        got = np.unpackbits(o["bits"].view(np.uint32).view(np.uint8), axis=1, bitorder="little")[:, :m_total].astype(bool)
+        assert np.array_equal(got, want)
+        assert np.array_equal(o["hits"].astype(np.int64), want.sum(axis=1).astype(np.int64))
+    assert want[-1].all() and want[:-1].sum() > 0
