@@ -372,6 +372,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the short extract / match measurements")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle checksum of the result tables (profiling runs)")
+    ap.add_argument("--devgen", action="store_true", help="generate the reads in HBM (kmer_cuda_dev_synth_reads: one seeded table, every rank "
+                                                          "its own row range) instead of on the host with numpy")
     ap.add_argument("--k", type=int, default=21, help="k-mer length of the count workload (default: the headline's 21)")
     ap.add_argument("--config", default="c2", choices=["c2", "c3", "c2x10"],
                     help="c2 = BASELINE configs[1] (default; weak scaling, --reads per GPU); c3 = configs[2]: k=31 over 10 GB in total, "
@@ -410,7 +412,20 @@ def main():
     if args.config in ("c3", "c2x10"):                  # 10 GB in total, split by row over the ranks
         n_rows = 10_000_000 // world
         scaling = "strong"
-    flat, off = datagen.synth_reads((3 if args.config == "c3" else 2) + rank, n_rows, READ_LEN)
+    seed = 3 if args.config == "c3" else 2
+    if args.devgen:
+        # rows [rank*n_rows, (rank+1)*n_rows) of ONE seeded table, generated in HBM (csrc/synth.cu); the host copy is only what
+        # the e2e arm and the oracle's checksum read
+        nb = n_rows * READ_LEN
+        g_seq = torch.zeros(((nb + 15) & ~15) + 64, dtype=torch.uint8, device="cuda")
+        g_off = torch.zeros(n_rows + 1, dtype=torch.int64, device="cuda")
+        eng.dev_synth_reads(seed, rank * n_rows, n_rows, READ_LEN, g_seq, g_off)
+        eng.dev_finish()
+        flat = g_seq[:nb].cpu().numpy()
+        off = g_off.cpu().numpy().astype(np.uint64)
+        del g_seq, g_off
+    else:
+        flat, off = datagen.synth_reads(seed + rank, n_rows, READ_LEN)
     n_bases = int(off[-1])
     n_kmers = n_rows * (READ_LEN - K + 1)          # per GPU (weak scaling: every rank brings its own 1 GB)
     total_kmers = n_kmers * world
@@ -841,6 +856,8 @@ def main():
                        "exchange_bytes_per_gpu_per_step": (sharder.last_exchange_bytes if sharder is not None else 0),
                        "exchange": (None if sharder is None else ("peer reads inside the split kernel (CUDA IPC over NVLink)" if sharder._pull is not None
                                                                   else "NCCL all_to_all")),
+                       "generator": ("device: counter-based table, csrc/synth.cu, rows split over the ranks" if args.devgen
+                                     else "host: numpy PCG64, seed + rank"),
                        "host_placement_rank0": placement, "l2": "inputs and tables larger than L2 (no flush needed)",
                        "bases_per_sec": n_bases * world * args.steps / (ms_total * 1e-3)},
             "roofline": roofline, "roofline_kernels": roofline_kernels, "roofline_step": roofline_step, "phases_ms": phases, "cpu_baseline": cpu, "e2e": e2e,

@@ -331,6 +331,15 @@ int kmer_cuda_multi_submit_match(kmer_cuda_multi *m, int op, const int *ops, con
 								 uint64_t n_kmers, int k, const char *const *consts, uint32_t n_consts, uint32_t **bits,
 								 uint64_t *words_per_row, uint64_t **hits);
 
+/* Benchmark inputs generated in HBM (the reference's data_generator.py:4-11 distribution -- bases i.i.d. uniform
+ * over ACGT, upper case -- made seeded and shape-parameterised): rows [first_row, first_row + n_rows) of the table of
+ * read_len-base reads that `seed` defines; base g of the table depends on (seed, g) only, so the ranks of a sharded run each
+ * generate their own row range of ONE table.  d_seq: n_rows*read_len bytes rounded up to 16 (+64 bytes of padding as every
+ * dev_* call wants), 16-byte aligned; d_row_off: n_rows+1 offsets, starting at 0.  Asynchronous on `stream`.
+ * Restated in numpy by kmer-extension_b200/datagen.py: synth_reads_counter. */
+int kmer_cuda_dev_synth_reads(kmer_cuda_ctx *ctx, uint64_t seed, uint64_t first_row, uint64_t n_rows, uint64_t read_len,
+							  char *d_seq, uint64_t *d_row_off, void *stream);
+
 /* Upper bound of the number of k-mers (= groups) a batch can produce: n_bases - n_rows*(k-1). */
 uint64_t kmer_cuda_max_kmers(uint64_t n_bases, uint64_t n_rows, int k);
 

@@ -43,7 +43,7 @@ ABI_SYMBOLS = [
     "kmer_cuda_dev_shard_count_peers", "kmer_cuda_ipc_export", "kmer_cuda_ipc_open", "kmer_cuda_ipc_close",
     "kmer_cuda_dev_merge_begin", "kmer_cuda_dev_merge_add", "kmer_cuda_dev_merge_emit", "kmer_cuda_test_force_window",
     "kmer_cuda_init_multi", "kmer_cuda_shutdown_multi", "kmer_cuda_multi_device_count", "kmer_cuda_multi_last_error",
-    "kmer_cuda_multi_submit_count", "kmer_cuda_multi_release", "kmer_cuda_dev_pack_codes", "kmer_cuda_multi_submit_match",
+    "kmer_cuda_multi_submit_count", "kmer_cuda_multi_release", "kmer_cuda_dev_pack_codes", "kmer_cuda_multi_submit_match", "kmer_cuda_dev_synth_reads",
 ]
 
 
@@ -335,6 +335,12 @@ class KmerCuda:
         self._check(self.lib.kmer_cuda_dev_match(self.ctx, op, opsp, d_codes.data_ptr(),
                                                  d_lens.data_ptr() if d_lens is not None else None, m, k, arr, len(consts),
                                                  d_bits.data_ptr(), d_hits.data_ptr(), self._stream_ptr(stream)))
+
+    def dev_synth_reads(self, seed: int, first_row: int, n_rows: int, read_len: int, d_seq, d_off, stream=None):
+        """Rows [first_row, first_row+n_rows) of the seeded synthetic table, written into d_seq (uint8, >= n_rows*read_len
+        rounded up to 16 bytes) and d_off (int64/uint64 [n_rows+1]); datagen.synth_reads_counter is the numpy restatement."""
+        self._check(self.lib.kmer_cuda_dev_synth_reads(self.ctx, C.c_uint64(seed & ((1 << 64) - 1)), C.c_uint64(first_row), C.c_uint64(n_rows),
+                                                       C.c_uint64(read_len), d_seq.data_ptr(), d_off.data_ptr(), self._stream_ptr(stream)))
 
     def dev_decode(self, d_codes, n: int, k: int, with_header: bool, d_text, stream=None):
         self._check(self.lib.kmer_cuda_dev_decode(self.ctx, d_codes.data_ptr(), n, k, int(with_header), d_text.data_ptr(),

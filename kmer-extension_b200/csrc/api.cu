@@ -677,6 +677,21 @@ extern "C" int kmer_cuda_dev_decode(kmer_cuda_ctx* c, const uint64_t* d_codes, u
     return KMER_OK;
 }
 
+// seeded synthetic reads written straight into HBM (synth.cu): the benchmark shapes of SURVEY 8d2 without host generation
+extern "C" int kmer_cuda_dev_synth_reads(kmer_cuda_ctx* c, uint64_t seed, uint64_t first_row, uint64_t n_rows, uint64_t read_len,
+                                         char* d_seq, uint64_t* d_row_off, void* stream) {
+    if (!c) return KMER_ERR_BAD_ARGUMENT;
+    if (!d_row_off || (n_rows * read_len && !d_seq)) return bad_arg(c, "d_seq / d_row_off");
+    if ((reinterpret_cast<uintptr_t>(d_seq) & 15) != 0) return bad_arg(c, "d_seq must be 16-byte aligned");
+    if (read_len && n_rows > (~0ull >> 1) / read_len) return bad_arg(c, "n_rows * read_len overflows");
+    cudaStream_t st = pick_stream(c, stream);
+    CU(cudaSetDevice(c->di.device), "cudaSetDevice");
+    launch_synth_reads(c->di, seed, first_row, n_rows, read_len, d_seq, d_row_off, st);
+    c->launches += n_rows * read_len ? 2 : 1;
+    CU(cudaGetLastError(), "synth launch");
+    return KMER_OK;
+}
+
 extern "C" int kmer_cuda_dev_pack_codes(kmer_cuda_ctx* c, const uint64_t* d_codes, uint64_t n, int k, uint8_t* d_packed, void* stream) {
     if (!c) return KMER_ERR_BAD_ARGUMENT;
     if (k < 1 || k > KMER_CUDA_MAX_K) return bad_arg(c, "k-mer length must be 1..32");

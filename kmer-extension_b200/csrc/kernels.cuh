@@ -18,6 +18,9 @@ struct DeviceInfo {
 void launch_rows_prepare(const uint64_t* d_off, uint64_t n_rows, uint64_t n_bases, int k, uint32_t* d_mask,
                          uint64_t mask_words, DevStatus* d_status, cudaStream_t st);
 // row index of the row containing the first base of every tile
+// synth.cu: n_rows reads of read_len uniform ACGT bases, rows [first_row, first_row + n_rows) of the table `seed` defines
+void launch_synth_reads(const DeviceInfo& di, uint64_t seed, uint64_t first_row, uint64_t n_rows, uint64_t read_len, char* d_seq,
+                        uint64_t* d_row_off, cudaStream_t st);
 void launch_tile_row_base(const uint64_t* d_off, uint64_t n_rows, uint64_t n_tiles, uint32_t* d_tile_row, cudaStream_t st);
 
 // extract.cu ------------------------------------------------------------------------------------

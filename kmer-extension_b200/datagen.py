@@ -61,3 +61,34 @@ def synth_qkmers(seed: int, p: int, k: int, with_n: bool = False) -> list[str]:
     chars = QKMER_CHARS if not with_n else np.concatenate([QKMER_CHARS, np.frombuffer(b"N", np.uint8)])
     a = chars[rng.integers(0, len(chars), size=(p, k))]
     return [bytes(r).decode() for r in a]
+
+
+# --------------------------------------------------------------------------- counter-based table (the device-side generator)
+_GOLD = np.uint64(0x9E3779B97F4A7C15)
+_ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def _splitmix64(z: np.ndarray) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def synth_reads_counter(seed: int, n_rows: int, read_len: int, first_row: int = 0):
+    """Rows [first_row, first_row + n_rows) of the table kmer_cuda_dev_synth_reads writes (csrc/synth.cu), bit for bit:
+    base g of the whole table = "ACGT"[(splitmix64(seed + (g//32 + 1) * 0x9E3779B97F4A7C15) >> 2*(g%32)) & 3].
+    Same distribution as synth_reads (data_generator.py:4-11: i.i.d. uniform ACGT, upper case), but every base depends on
+    (seed, position) only, so a rank of a sharded run generates its own row range of ONE table."""
+    n = n_rows * read_len
+    g0 = first_row * read_len
+    flat = np.empty(n, dtype=np.uint8)
+    step = 1 << 24
+    for lo in range(0, n, step):
+        hi = min(n, lo + step)
+        g = np.arange(g0 + lo, g0 + hi, dtype=np.uint64)
+        with np.errstate(over="ignore"):
+            w = _splitmix64(np.uint64(seed & ((1 << 64) - 1)) + ((g >> np.uint64(5)) + np.uint64(1)) * _GOLD)
+        flat[lo:hi] = _ACGT[((w >> (np.uint64(2) * (g & np.uint64(31)))) & np.uint64(3)).astype(np.int64)]
+    off = np.arange(n_rows + 1, dtype=np.uint64) * np.uint64(read_len)
+    return flat, off
