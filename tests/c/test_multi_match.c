@@ -131,7 +131,7 @@ int main(int argc, char **argv)
 			lens[i] = (uint8_t) (rnd64() % 9);            /* 0..8 */
 			codes[i] = lens[i] ? rnd64() & ((1ull << (2 * lens[i])) - 1) : 0;
 		}
-		const char *consts[4] = {"acg", "ac", "nnrya", ""};
+		const char *consts[4] = {"acg", "ac", "nnrya", "t"};
 		int ops[4] = {KMER_OP_EQUALS, KMER_OP_STARTS_WITH, KMER_OP_CONTAINS, KMER_OP_EQUALS};
 		failures += run_case(mh, nd, "mixed lengths 0..8", codes, lens, m, 0, consts, ops, 4);
 		free(codes); free(lens);
