@@ -124,6 +124,7 @@ def load_library(path: Path = LIB_PATH) -> C.CDLL:
     L.kmer_cuda_dev_merge_begin.argtypes = [vp, u64, vp]
     L.kmer_cuda_dev_merge_add.argtypes = [vp, vp, u64, C.c_uint32, C.c_uint32, vp]
     L.kmer_cuda_dev_merge_emit.argtypes = [vp, i32, vp, u64, vp]
+    L.kmer_cuda_dev_synth_reads.argtypes = [vp, u64, u64, u64, u64, vp, vp, vp]
     return L
 
 
@@ -339,8 +340,8 @@ class KmerCuda:
     def dev_synth_reads(self, seed: int, first_row: int, n_rows: int, read_len: int, d_seq, d_off, stream=None):
         """Rows [first_row, first_row+n_rows) of the seeded synthetic table, written into d_seq (uint8, >= n_rows*read_len
         rounded up to 16 bytes) and d_off (int64/uint64 [n_rows+1]); datagen.synth_reads_counter is the numpy restatement."""
-        self._check(self.lib.kmer_cuda_dev_synth_reads(self.ctx, C.c_uint64(seed & ((1 << 64) - 1)), C.c_uint64(first_row), C.c_uint64(n_rows),
-                                                       C.c_uint64(read_len), d_seq.data_ptr(), d_off.data_ptr(), self._stream_ptr(stream)))
+        self._check(self.lib.kmer_cuda_dev_synth_reads(self.ctx, seed & ((1 << 64) - 1), first_row, n_rows, read_len, d_seq.data_ptr(),
+                                                       d_off.data_ptr(), self._stream_ptr(stream)))
 
     def dev_decode(self, d_codes, n: int, k: int, with_header: bool, d_text, stream=None):
         self._check(self.lib.kmer_cuda_dev_decode(self.ctx, d_codes.data_ptr(), n, k, int(with_header), d_text.data_ptr(),

@@ -150,3 +150,19 @@ def test_pg_regress_suite_is_generated_from_the_kats():
     after = ((reg / "sql" / "kmer_kat.sql").read_text(), (reg / "expected" / "kmer_kat.out").read_text())
     assert before == after
     assert "kmer_gpu_counts" in after[0] and "tacg |     1" in after[1]
+
+
+def test_every_library_call_of_the_python_host_side_has_argtypes():
+    """ctypes passes a bare Python int as a 32-bit C int: a device pointer handed to a function without argtypes is truncated
+    (found on the GPU: kmer_cuda_dev_synth_reads wrote through half a pointer).  Every kmer_cuda_* function the Python host side
+    calls with arguments must declare them."""
+    import re
+    from kmer_extension_b200 import api
+    lib = api.load_library()
+    called = set()
+    for f in ("api.py", "sharded.py"):
+        called |= set(re.findall(r"lib\.(kmer_cuda_\w+)\(", (ROOT / "kmer-extension_b200" / f).read_text()))
+    called |= set(re.findall(r"lib\.(kmer_cuda_\w+)\(", (ROOT / "bench.py").read_text()))
+    no_args = {"kmer_cuda_abi_version", "kmer_cuda_device_count"}
+    missing = sorted(n for n in called - no_args if getattr(lib, n).argtypes is None)
+    assert not missing, f"no argtypes: {missing}"
