@@ -840,6 +840,23 @@ def main():
             ms4 = timed_dev(f_c4, reps=3)
             secondary["match_c4"] = sec_line(f"configs[3] at 1/4 size: contains, {P} IUPAC patterns (k=12) x {m4:.3g} k-mers, full bit matrix",
                                              ms4, 8 * m4 + 16 * P + P * ((m4 + 7) // 8), m4 * P, "pair-tests/s")
+            # this kernel is INT32-bound, not HBM-bound -- its fraction of the integer issue rates, from the static SASS
+            # count of its round loop (tools/sass_loop_count.py -> profiles/), the trip count of this workload and the measured time
+            sp = ROOT / "profiles" / "r02_match_table_sass_counts.json"
+            if sp.exists():
+                sc = json.loads(sp.read_text())
+                trips = ((m4 + 31) // 32) * ((P + 1023) // 1024)                 # warp rounds: 32 k-mers x one group of 1024 constants
+                mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
+                sm_count = torch.cuda.get_device_properties(0).multi_processor_count
+                smsp_cycles = ms4 * 1e-3 * mhz * 1e6 * sm_count * 4               # cycles x SM sub-partitions
+                alu, allins = sc["by_pipe"].get("alu", 0), sc["instructions"]
+                secondary["match_c4"]["int32"] = {
+                    "alu_pipe_frac": trips * alu * 2.0 / smsp_cycles,             # LOP3/SHF/...: one warp instruction per 2 cycles per sub-partition
+                    "issue_slot_frac": trips * allins / smsp_cycles,              # any instruction: one per cycle per sub-partition
+                    "warp_instr_per_round": allins, "alu_pipe_warp_instr_per_round": alu, "rounds": trips,
+                    "pair_tests_per_round": sc["pair_tests_per_loop_trip"], "sm_mhz": mhz, "sm_count": sm_count,
+                    "source": "static SASS count of the round loop (profiles/r02_match_table_sass_counts.json) x trip count / measured time; "
+                              "pipe rates from B300_MICROARCH.md (alu pipe rt_SMSP = 2); an estimate, not an ncu counter"}
             del col4, bits4, hits4
             torch.cuda.empty_cache()
         except Exception as ex:                            # the secondary rows must never take the headline down
