@@ -218,12 +218,26 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def available_host_ram() -> int:
+    """what this process may still allocate: /proc/meminfo's MemAvailable, or less under a cgroup limit (v2 or v1)"""
+    import psutil
+    avail = int(psutil.virtual_memory().available)
+    for lim, cur in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                     ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        try:
+            limit = Path(lim).read_text().strip()
+            if limit != "max" and int(limit) < (1 << 60):
+                avail = min(avail, max(int(limit) - int(Path(cur).read_text().strip()), 0))
+        except (OSError, ValueError):
+            pass
+    return avail
+
+
 def ref_sample_plan(args, rate_small: float, threads: int):
     """How many reads one step of the reference arm counts: sized from a calibration pass so that warm-up + steps take about
     --ref-seconds, and bounded by what the executor stand-in's hash table can hold in this host's RAM."""
-    import psutil
     kmers_per_read = READ_LEN - K + 1
-    avail = psutil.virtual_memory().available
+    avail = available_host_ram()
     # measured on the reference driver (oracle/ref_driver.c): ~155 B of RSS per group at k=21 (entry + ASCII key + per-thread
     # partial tables + the merged table), random DNA has one group per window
     bytes_per_group = 160
@@ -255,7 +269,8 @@ def run_reference(args):
                     "whole_workload_reads": int(args.reads),
                     "whole_workload_fits_host_ram": bool(fit_reads >= args.reads)}
     if args.ref_large_seconds > 0:
-        n_large = int(min(fit_reads, args.reads, r["value"] * args.ref_large_seconds / kmers_per_read))
+        # half of what fits: the per-group figure is a measurement at k=21 on one box, not a guarantee
+        n_large = int(min(fit_reads // 2, args.reads, r["value"] * args.ref_large_seconds / kmers_per_read))
         if n_large > 2 * n_reads:
             big = cpu_reference_run(datagen, n_large, threads, 1, 0)
             scaling_info["largest_pass"] = {"reads": n_large, "value": big["value"], "unit": UNIT, "seconds": big["seconds"],
