@@ -18,7 +18,12 @@
  * whose rows are exactly the groups of the original query: (kmer, count(*)::bigint), unordered like a HashAggregate's.  An
  * ORDER BY / LIMIT over the two output columns is kept (it only refers to target entries).  Everything else -- HAVING, extra
  * columns, other aggregates, count(DISTINCT ...), FILTER, a second SRF, WHERE on the outer level, WITH ORDINALITY, a parameter for k --
- * is left to PostgreSQL untouched.  `SET kmer.gpu_offload = off` disables the rewrite.
+ * is left to PostgreSQL untouched.  `SET kmer.gpu_offload = off` disables the rewrite.  The counting query may itself be a
+ * sub-select in FROM of a larger statement (offload_walk).
+ *
+ * Limit of this form: the column travels as ONE dna[] datum, and PostgreSQL caps a datum at 1 GB (MaxAllocSize); a table beyond
+ * that needs the batched form (several kmer_gpu_counts calls merged, or a CustomScan feeding the library page by page) --
+ * DESIGN.md section 8.
  *
  * The rewrite happens on the analyzed Query in planner_hook, before standard_planner(): no new plan node type, no executor
  * hook; the function scan runs kmer_gpu.c's SRF.  Semantics that make it exact: generate_kmers is STRICT (a NULL dna yields no
@@ -359,23 +364,70 @@ rewrite_count_query(Query *q, const KmerCatalog *c, const KmerCountShape *m)
 	q->hasAggs = false;
 }
 
-/* Exposed for the test driver: true if the query was rewritten. */
+/*
+ * The counting query need not be the statement itself: it is found at any depth of sub-selects in FROM, e.g.
+ *   SELECT kmer::text, count FROM (SELECT kmer, count(*) AS count FROM (SELECT generate_kmers(dna, 21) ...) s GROUP BY kmer) t ORDER BY 2 DESC;
+ * (CREATE TABLE AS / INSERT ... SELECT / EXPLAIN hand their SELECT to the planner as a statement of its own.)  A level that
+ * matches is rewritten in place; its output columns keep their numbers, names and types, so the levels above do not notice.
+ * Returns the number of levels rewritten.
+ */
+static int
+offload_walk(Query *q, const KmerCatalog *cat, int depth)
+{
+	KmerCountShape m;
+	ListCell *lc;
+	int n = 0;
+
+	if (q == NULL || depth > 16)
+		return 0;
+	if (q->commandType == CMD_SELECT && q->hasAggs && q->groupClause != NIL && match_count_query(q, cat, &m))
+	{
+		rewrite_count_query(q, cat, &m);
+		return 1;
+	}
+	foreach (lc, q->rtable)
+	{
+		RangeTblEntry *rte = (RangeTblEntry *) lfirst(lc);
+
+		if (rte->rtekind == RTE_SUBQUERY && rte->subquery != NULL)
+			n += offload_walk(rte->subquery, cat, depth + 1);
+	}
+	return n;
+}
+
+/* does any level have an aggregate under a GROUP BY?  (cheap, before any catalog lookup) */
+static bool
+has_grouped_aggregate(const Query *q, int depth)
+{
+	ListCell *lc;
+
+	if (q == NULL || depth > 16)
+		return false;
+	if (q->hasAggs && q->groupClause != NIL)
+		return true;
+	foreach (lc, q->rtable)
+	{
+		RangeTblEntry *rte = (RangeTblEntry *) lfirst(lc);
+
+		if (rte->rtekind == RTE_SUBQUERY && has_grouped_aggregate(rte->subquery, depth + 1))
+			return true;
+	}
+	return false;
+}
+
+/* Exposed for the test driver: true if some level of the query was rewritten. */
 bool
 kmer_gpu_try_offload(Query *parse)
 {
 	KmerCatalog cat;
-	KmerCountShape m;
 
-	if (!kmer_gpu_offload || parse == NULL || parse->commandType != CMD_SELECT)
+	if (!kmer_gpu_offload || parse == NULL)
 		return false;
-	if (!parse->hasAggs || parse->groupClause == NIL) /* cheap exit before any catalog lookup */
+	if (!has_grouped_aggregate(parse, 0))
 		return false;
 	if (!kmer_catalog_lookup(&cat))
 		return false;
-	if (!match_count_query(parse, &cat, &m))
-		return false;
-	rewrite_count_query(parse, &cat, &m);
-	return true;
+	return offload_walk(parse, &cat, 0) > 0;
 }
 
 static PlannedStmt *

@@ -204,6 +204,24 @@ static Query *stock_s1(const char *dna, int k)
 	return q;
 }
 
+/* SELECT t.kmer, t.count FROM (<counting query>) t ORDER BY 2 DESC */
+static Query *wrap_in_select(Query *inner)
+{
+	Query *q = select_query();
+	RangeTblEntry *t = makeNode(RangeTblEntry);
+	TargetEntry *t1 = makeTargetEntry((Expr *) makeVar(1, 1, KMER_OID, -1, InvalidOid, 0), 1, "kmer", false);
+	TargetEntry *t2 = makeTargetEntry((Expr *) makeVar(1, 2, INT8OID, -1, InvalidOid, 0), 2, "count", false);
+	t->rtekind = RTE_SUBQUERY; t->subquery = inner; t->inFromCl = true;
+	t->alias = makeAlias("t", NIL);
+	t->eref = makeAlias("t", list_make2(makeString("kmer"), makeString("count")));
+	t2->ressortgroupref = 1;
+	q->rtable = list_make1(t);
+	q->jointree = from_refs(1, NULL);
+	q->targetList = list_make2(t1, t2);
+	q->sortClause = list_make1(sgc(1));
+	return q;
+}
+
 /* ------------------------------------------------------------------ structure checks */
 static int prev_hook_calls;
 static PlannedStmt *previous_hook(Query *parse, const char *qs, int co, ParamListInfo bp)
@@ -308,7 +326,16 @@ static void structure_tests(void)
 				 ((ArrayExpr *) arr)->element_typeid == DNA_OID && list_length(((ArrayExpr *) arr)->elements) == 1 && !p->hasSubLinks;
 		CHECK(ok, "S1 (TEST 13.1): FROM generate_kmers('ACGTACGT'::dna, 4) AS k(kmer) -> kmer_gpu_counts(ARRAY['ACGTACGT'::dna], 4)");
 	}
-	CHECK(prev_hook_calls >= 6, "the planner hook that was installed before _PG_init is still called (hook chain)");
+	/* the counting query as a sub-select of a larger statement: SELECT kmer, count FROM (<S2>) t ORDER BY 2 DESC */
+	{
+		Query *in = stock_s2(21, 1), *top = wrap_in_select(in);
+		Query *p = plan(top);
+		RangeTblEntry *t = (RangeTblEntry *) linitial(p->rtable);
+		CHECK(p == top && t->rtekind == RTE_SUBQUERY && t->subquery == in && is_rewritten(in, &arr, &kc) && !top->hasAggs &&
+				  list_length(top->sortClause) == 1,
+			  "S2 as a sub-select in FROM of a larger statement: the inner level is rewritten, the outer one untouched");
+	}
+	CHECK(prev_hook_calls >= 7, "the planner hook that was installed before _PG_init is still called (hook chain)");
 
 	/* ---- queries that must reach the planner untouched ---- */
 #define UNTOUCHED(q, what) do { Query *q__ = (q); int n__ = list_length(q__->rtable); RTEKind k__ = ((RangeTblEntry *) linitial(q__->rtable))->rtekind; \
@@ -488,6 +515,8 @@ static void exec_case(const char *what, Query *q, const FakeTable *t, Node *orig
 	Query *p = plan(q);
 	Node *arr;
 	Const *kc;
+	if (!p->hasAggs && p->groupClause == NIL && ((RangeTblEntry *) linitial(p->rtable))->rtekind == RTE_SUBQUERY)
+		p = ((RangeTblEntry *) linitial(p->rtable))->subquery;   /* a pass-through outer level: execute the level below it */
 	if (!is_rewritten(p, &arr, &kc)) { CHECK(0, what); return; }
 	size_t n = execute_rewritten(p, t, &got);
 	int ok = n == g;
@@ -507,13 +536,14 @@ static void exec_tests(void)
 	for (int r = 0; r < t.n; r++)
 	{
 		int len = 40 + (int) (rnd() % 300);
-		if (r % 9 == 0) rng_state = 77;                      /* repeated reads: counts above 1 */
+		if (r % 9 == 0) rng_state = 77 + (uint64_t) (r % 63); /* some reads repeat: counts above 1 */
 		for (int i = 0; i < len; i++) buf[i] = "ACGTacgt"[rnd() & 7];
 		t.dna[r] = make_varlena(buf, len, r & 1);            /* both header forms, as on disk / in memory */
 	}
 	fill_catalog(1);
 	exec_case("S2 k=21", stock_s2(21, 0), &t, NULL, NULL, 21);
 	exec_case("S2 k=31 WHERE id % 2 = 0", stock_s2(31, 1), &t, where_id_is_even(), NULL, 31);
+	exec_case("S2 k=22 inside a larger statement", wrap_in_select(stock_s2(22, 1)), &t, where_id_is_even(), NULL, 22);
 	exec_case("S3 k=5", stock_s3(5), &t, NULL, NULL, 5);
 	exec_case("S3 k=32", stock_s3(32), &t, NULL, NULL, 32);
 	{
