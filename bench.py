@@ -259,6 +259,7 @@ def run_reference(args):
         return
     _, api, datagen = load_pkg()
     threads = host_threads()
+    reads_per_gpu = args.reads if args.config == "c2" else 10_000_000 // max(args.gpus, 1)   # as the CUDA arm splits the job
     cal = cpu_reference_run(datagen, 2000, threads, 1, 0)
     n_reads, fit_reads, avail = ref_sample_plan(args, cal["value"], threads)
     r = cpu_reference_run(datagen, n_reads, threads, args.steps, args.warmup)
@@ -281,8 +282,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_name(args.config, K, args.reads), "k": K, "read_len": READ_LEN,
-                       "reads_per_gpu": args.reads, "algo": 0,
+            "config": {"workload": workload_name(args.config, K, reads_per_gpu), "k": K, "read_len": READ_LEN,
+                       "reads_per_gpu": reads_per_gpu, "algo": 0,
                        "sample_per_step": f"{n_reads} reads x {READ_LEN} bases (prefix of the workload, seed 2)"},
             "cpu_baseline": cpu,
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
