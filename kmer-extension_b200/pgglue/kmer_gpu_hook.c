@@ -48,6 +48,7 @@
 #define KMER_COUNT_STAR_OID 2803 /* pg_proc.dat: count(*) ; count("any") is 2147 and is not count(*) */
 
 void _PG_init(void);
+bool kmer_gpu_try_offload(Query *parse); /* also called by the test driver */
 
 static bool kmer_gpu_offload = true;
 static planner_hook_type prev_planner_hook = NULL;

@@ -166,3 +166,28 @@ def test_every_library_call_of_the_python_host_side_has_argtypes():
     no_args = {"kmer_cuda_abi_version", "kmer_cuda_device_count"}
     missing = sorted(n for n in called - no_args if getattr(lib, n).argtypes is None)
     assert not missing, f"no argtypes: {missing}"
+
+
+def test_multi_and_generator_entry_points_reject_bad_arguments_without_touching_a_device(lib):
+    """NULL handles / missing out-pointers come back as KMER_ERR_BAD_ARGUMENT, and a device list cannot be opened without a
+    GPU (KMER_ERR_NO_DEVICE: the multi-device handle has no CPU path either)."""
+    BAD = 16  # KMER_ERR_BAD_ARGUMENT, include/kmer_cuda.h
+    hdr = (ROOT / "include" / "kmer_cuda.h").read_text()
+    assert re.search(r"KMER_ERR_BAD_ARGUMENT\s*=\s*16", hdr)
+    vp, u64 = C.c_void_p, C.c_uint64
+    lib.kmer_cuda_multi_submit_match.argtypes = [vp, C.c_int, vp, vp, vp, u64, C.c_int, vp, C.c_uint32, vp, vp, vp]
+    lib.kmer_cuda_multi_submit_count.argtypes = [vp, vp, vp, u64, C.c_int, vp, vp, vp]
+    lib.kmer_cuda_init_multi.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int]
+    bits, wpr, hits = vp(), u64(), vp()
+    assert lib.kmer_cuda_multi_submit_match(None, 0, None, None, None, 0, 12, None, 0, C.byref(bits), C.byref(wpr), C.byref(hits)) == BAD
+    assert lib.kmer_cuda_multi_submit_count(None, None, None, 0, 21, None, None, None) == BAD
+    assert lib.kmer_cuda_dev_synth_reads(None, 1, 0, 1, 1, None, None, None) == BAD
+    h = vp()
+    assert lib.kmer_cuda_init_multi(C.byref(h), None, 0) == BAD
+    assert lib.kmer_cuda_init_multi(C.byref(h), (C.c_int * 17)(), 17) == BAD
+    if lib.kmer_cuda_device_count() == 0:
+        devs = (C.c_int * 2)(0, 1)
+        rc = lib.kmer_cuda_init_multi(C.byref(h), devs, 2)
+        assert rc == api.KMER_ERR_NO_DEVICE and not h.value
+        e = lib.kmer_cuda_last_error(None).contents
+        assert b"no CPU path" in e.message
