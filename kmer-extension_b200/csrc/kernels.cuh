@@ -72,7 +72,8 @@ struct ScatterPlan {
     uint32_t caps2;      // staging slots per fine bucket, second pass
 };
 // Adjusts p (n_buckets = n_coarse << fine_shift) and fills sp; false: the job does not suit the two-pass path (the caller uses
-// launch_partition).  n_ranks > 1: the coarse partitions of ALL ranks (sharded counting; not built yet).
+// launch_partition).  Single GPU only: sharded counting scatters into coarse partitions with partition_kernel and splits them
+// with refine_staged_kernel on the owner.
 bool make_scatter_plan(const DeviceInfo& di, uint64_t n_bases, uint64_t n_kmers, PartitionPlan& p, ScatterPlan& sp);
 size_t scatter_seg_bytes(const PartitionPlan& p, const ScatterPlan& sp);
 size_t scatter_segfill_bytes(const ScatterPlan& sp);
