@@ -191,3 +191,23 @@ def test_multi_and_generator_entry_points_reject_bad_arguments_without_touching_
         assert rc == api.KMER_ERR_NO_DEVICE and not h.value
         e = lib.kmer_cuda_last_error(None).contents
         assert b"no CPU path" in e.message
+
+
+def test_committed_sass_counts_belong_to_the_built_library():
+    """bench.py's secondary.match_c4.int32 multiplies the static instruction counts of match_table_kernel's round loop
+    (profiles/r02_match_table_sass_counts.json) by the trip count: the committed counts must be those of the library as built
+    from the current sources."""
+    import importlib.util
+    import json
+    import shutil
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    spec = importlib.util.spec_from_file_location("sass_loop_count", ROOT / "tools" / "sass_loop_count.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    committed = json.loads((ROOT / "profiles" / "r02_match_table_sass_counts.json").read_text())
+    now = mod.loop_counts(committed["function"])
+    assert now["instructions"] == committed["instructions"] and now["by_pipe"] == committed["by_pipe"], \
+        "match.cu changed: run `python tools/sass_loop_count.py` and commit profiles/r02_match_table_sass_counts.json"
+    assert committed["by_pipe"]["alu"] > committed["instructions"] // 2      # the loop is LOP3 / SHF work
+    assert committed["pair_tests_per_loop_trip"] == 32 * 1024
