@@ -878,6 +878,24 @@ def main():
         except Exception as ex:                            # the secondary rows must never take the headline down
             secondary["error"] = repr(ex)
 
+    # multi-GPU runs also state their NVLink traffic against 900 GB/s per direction per GPU
+    nvlink = None
+    try:
+        if sharder is not None:
+            pulled = sharder._pull is not None
+            ms_x = phases.get("refine") if pulled else phases.get("exchange")
+            if ms_x:
+                xb = int(sharder.last_exchange_bytes)      # pull: filled records + fill words of this rank's send block that OTHER owners read
+                gbs = xb / (ms_x * 1e-3) / 1e9
+                nvlink = {"bytes_per_gpu_per_step": xb,
+                          "kernel": ("refine (the owner's split kernel pulls its segments from the peers' HBM; the transfer overlaps its own work)"
+                                     if pulled else "exchange (NCCL all_to_all of the segments, capacity not fill)"),
+                          "kernel_ms": ms_x, "gb_per_s_per_direction": gbs, "peak": 900.0, "frac": gbs / 900.0,
+                          "what": "rank 0's egress = what its peers take out of its send block, by symmetry each GPU's ingress; counted from "
+                                  "the fill words / buffer sizes, not a hardware counter"}
+    except Exception as ex:                               # never take the headline down
+        nvlink = {"error": repr(ex)}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
@@ -894,7 +912,7 @@ def main():
                        "host_placement_rank0": placement, "l2": "inputs and tables larger than L2 (no flush needed)",
                        "bases_per_sec": n_bases * world * args.steps / (ms_total * 1e-3)},
             "roofline": roofline, "roofline_kernels": roofline_kernels, "roofline_step": roofline_step, "phases_ms": phases, "cpu_baseline": cpu, "e2e": e2e,
-            "parity": parity, "secondary": secondary, "gpu_launches": int(launches), "clocks": clocks}
+            "parity": parity, "secondary": secondary, "nvlink": nvlink, "gpu_launches": int(launches), "clocks": clocks}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if sharder is not None:
